@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the randomized low-rank hot path (BASELINE.json metric, configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle)
+
+One "step" = one rank-64 (+10) randomized SVD of a 65536 x 8192 f64 matrix with an exponentially
+decaying spectrum and 2 power iterations, exactly as the reference executes it
+(src/random_sampling.rs:131-160 then src/svd.rs:171-183; every power-iteration trip is executed,
+quirk Q1 included).  At N > 1 every rank owns a 65536-row block of a taller matrix (weak scaling,
+row-sharded; TSQR R-factors all-gathered, A^H Q partials all-reduced over NCCL).
+
+Prints ONE JSON line on rank 0.  `value` = algorithmic GFLOP/s with A resident in HBM;
+`e2e` = the same through the C ABI with host buffers (H2D of A and D2H of U, s, Vt timed).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(m=65536, n=8192, k=64, p=10, it=2, r0=512, decade_every=16.0, seed=1234, omega_seed=42)
+
+
+def algorithmic_flops(m, n, k, p, it):
+    """GEMMs once at 2MNK, tall QR at 2ml^2 - 2/3 l^3 for the factor plus the same
+    for forming Q, as executed by the reference (all `it` trips)."""
+    l = k + p
+    gemm = 2.0 * m * n * (l * (1 + 2 * it) + k)
+    qr = lambda rows, w: 2.0 * (2.0 * rows * w * w - (2.0 / 3.0) * w ** 3)
+    qrs = (it + 1) * qr(m, l) + it * qr(n, l)
+    svd = qr(n, k) + 12.0 * k ** 3
+    return gemm + qrs + svd + 2.0 * m * k * k
+
+
+def algorithmic_bytes(m, n, k, p, it, es=8):
+    """One read of A per product with A, plus read/write of the skinny operands."""
+    passes = 1 + 2 * it + 1
+    l = k + p
+    return passes * m * n * es + (2 * passes + 6) * (m + n) * l * es
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, flag in zip(names, r[5:9]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def own_fp64_peaks():
+    exe = os.path.join(ROOT, "rusty_compression_b200", "build", "rc_peaks")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)}
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def run_cpu_pipeline(a, omega, k, p, it, route):
+    from oracle import reference_path as ref
+    q = ref.sample_range_power_iteration(a, k, p, it, ref.OmegaStream(a.dtype, blocks=[omega]), route=route)
+    svd = ref.SVD.compute_from_range_estimate(q, a, route=route)
+    return svd
+
+
+def cpu_sample(m_sample, route, reps=1):
+    """The oracle (the reference's LAPACK path restated) on a row sample of the workload."""
+    from oracle.inputs import decaying_spectrum_matrix
+    from oracle.philox import random_gaussian
+    c = CFG
+    a, _ = decaying_spectrum_matrix(m_sample, c["n"], np.float64, c["seed"], r0=c["r0"], decade_every=c["decade_every"])
+    omega = random_gaussian((c["n"], c["k"] + c["p"]), np.float64, c["omega_seed"])
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        run_cpu_pipeline(a, omega, c["k"], c["p"], c["it"], route)
+        best = min(best, time.perf_counter() - t0)
+    flops = algorithmic_flops(m_sample, c["n"], c["k"], c["p"], c["it"])
+    return flops / best / 1e9, best
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port, the
+    Rust crate cannot be built here), all host threads, bounded row sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    m_sample = 8192
+    c = CFG
+    vals, faithful = [], None
+    for i in range(args.warmup + args.steps):
+        gf, sec = cpu_sample(m_sample, "gemm")
+        if i >= args.warmup:
+            vals.append((gf, sec))
+    if not args.skip_gemv:
+        faithful, _ = cpu_sample(2048, "gemv")
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([s for _, s in vals])) * 1e3
+    sample = (f"{m_sample} of {c['m']} rows (same n, k, p, it, spectrum); one GEMM per product (best-case CPU); "
+              f"oracle = scipy LAPACK ?geqp3/?orgqr/?gesdd on OpenBLAS")
+    line = {"impl": "reference", "metric": "rsvd_f64_algorithmic_gflops", "value": value, "unit": "GFLOP/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample,
+                             "reference_faithful_gemv_route_gflops": faithful},
+            "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus):
+    c = CFG
+    return {"workload": f"configs[1]: rank-{c['k']} (+{c['p']}) randomized SVD, f64, {c['m']}x{c['n']} per GPU, "
+                        f"sigma_j = 10^(-j/{c['decade_every']:g}), {c['it']} power iterations (as executed by the reference)",
+            "m_per_gpu": c["m"], "n": c["n"], "k": c["k"], "p": c["p"], "it_count": c["it"],
+            "global_rows": c["m"] * n_gpus, "parallelism": f"row-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
+            "l2_policy": "inputs (4 GiB per pass) exceed the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------- CUDA arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--m", type=int, default=None, help="rows per GPU (default: config)")
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-gemv", action="store_true")
+    args = ap.parse_args()
+    if args.m:
+        CFG["m"] = args.m
+    if args.n:
+        CFG["n"] = args.n
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from rusty_compression_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    ctx = api.Context(device=local)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+
+    c = CFG
+    m, n, k, p, it = c["m"], c["n"], c["k"], c["p"], c["it"]
+    l = k + p
+    # ---- synthetic input, generated on device (same construction as oracle/inputs.py)
+    a_dev = api.decaying_spectrum_matrix((m, n), np.float64, c["seed"], r0=c["r0"], decade_every=c["decade_every"],
+                                         row_offset=rank * m, ctx=ctx)
+    if world > 1:
+        a_dev.set_shard(world * m, rank * m)
+    ctx.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        q = api.sample_range_power_iteration(a_dev, k, p, it, seed=c["omega_seed"], ctx=ctx, device=True)
+        svd = api.SVD.compute_from_range_estimate(q, a_dev)
+        return q, svd
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.reset_counters()
+    launches_before = ctx.counter("kernel_launches")
+    ms_step = timed(step_device, args.steps, args.warmup)
+    launches = (ctx.counter("kernel_launches") - launches_before) // (args.steps + args.warmup) * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    flops_rank = algorithmic_flops(m, n, k, p, it)
+    value = world * flops_rank / (ms_step * 1e-3) / 1e9
+    hbm_gbs = world * algorithmic_bytes(m, n, k, p, it) / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (dmma_gemm_kernel, NN: Y = A Omega), timed alone, live
+    omega_dev = api.DeviceMatrix.random_gaussian((n, l), np.float64, c["omega_seed"], ctx=ctx)
+    ms_nn = timed(lambda: a_dev.matmat(omega_dev), 10, 3)
+    y_dev = a_dev.matmat(omega_dev)
+    ms_tn = timed(lambda: a_dev.conj_matmat(y_dev), 10, 3)
+    hbm_peak, peak_src = measured_peaks()
+    roofline = None
+    if rank == 0:
+        peaks = own_fp64_peaks()
+        gemm_flops = 2.0 * m * n * l
+        ach = gemm_flops / (ms_nn * 1e-3) / 1e12
+        peak = peaks.get("dmma_tflops") or 37.0
+        prof = {}
+        pj = os.path.join(ROOT, "profiles", "dominant_kernel.json")
+        if os.path.exists(pj):
+            prof = json.load(open(pj))
+        roofline = {"bound": "tensor", "kernel": "dmma_gemm_kernel<80,false> (FP64 tensor pipe, DMMA.8x8x4, TMA-fed)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "peak_source": "own-measured DMMA microbenchmark (rc_peaks); MEASURED_PEAKS.json has no FP64 figure",
+                    "own_measured_peaks": peaks, "traffic": prof.get("dram_bytes_per_launch"),
+                    "algorithmic_bytes_per_launch": m * n * 8 + (n + m) * l * 8,
+                    "hbm_gbs_of_this_kernel": (m * n * 8 + (n + m) * l * 8) / (ms_nn * 1e-3) / 1e9,
+                    "hbm_frac_of_measured": (m * n * 8 + (n + m) * l * 8) / (ms_nn * 1e-3) / 1e9 / hbm_peak,
+                    "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src,
+                    "ms_per_launch": ms_nn,
+                    "tn_kernel": {"kernel": "dmma_gemm_kernel<80,true> + split-K reduce (Z = A^T Y)",
+                                  "ms_per_launch": ms_tn, "achieved": gemm_flops / (ms_tn * 1e-3) / 1e12,
+                                  "frac": gemm_flops / (ms_tn * 1e-3) / 1e12 / peak}}
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D of A, D2H of U, s, Vt
+    e2e = None
+    if not args.skip_e2e:
+        a_host = torch.empty((m, n), dtype=torch.float64, pin_memory=True)
+        a_np = a_host.numpy()
+        ctx.check(ctx.lib.rc_matrix_to_host(ctx.h, a_dev.h, a_np.ctypes.data))
+        u_host = torch.empty((m, k), dtype=torch.float64, pin_memory=True).numpy()
+        vt_host = torch.empty((k, n), dtype=torch.float64, pin_memory=True).numpy()
+        a_dev.free()                                  # the e2e step owns its own upload
+
+        def step_e2e():
+            op = api.DeviceMatrix.from_numpy(a_np, ctx=ctx)
+            if world > 1:
+                op.set_shard(world * m, rank * m)
+            q = api.sample_range_power_iteration(op, k, p, it, seed=c["omega_seed"], ctx=ctx, device=True)
+            svd = api.SVD.compute_from_range_estimate(q, op)
+            ctx.check(ctx.lib.rc_matrix_to_host(ctx.h, ctx.lib.rc_svd_get_u(svd.h), u_host.ctypes.data))
+            ctx.check(ctx.lib.rc_matrix_to_host(ctx.h, ctx.lib.rc_svd_get_vt(svd.h), vt_host.ctypes.data))
+            s = svd.s_f64()
+            op.free()
+            return s
+
+        ms_e2e = timed(step_e2e, max(2, min(args.steps, 3)), 1)
+        e2e = {"value": world * flops_rank / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": m * n * 8, "d2h_bytes_per_step": (m * k + k + k * n) * 8,
+               "ms_per_step": ms_e2e, "api": "rc_matrix_from_host -> rc_sample_range_power_iteration -> "
+                                           "rc_svd_compute_from_range_estimate -> rc_matrix_to_host (pinned host buffers)"}
+
+    if rank == 0:
+        cpu = None
+        if not args.skip_cpu:
+            m_sample = 8192
+            gf, sec = cpu_sample(m_sample, "gemm")
+            gv, _ = cpu_sample(2048, "gemv")
+            cpu = {"value": gf, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"oracle pipeline on {m_sample} of {m} rows, one GEMM per product (best-case CPU), {sec:.1f} s",
+                   "reference_faithful_gemv_route_gflops": gv}
+        line = {"metric": "rsvd_f64_algorithmic_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu,
+                "hbm_gbs_algorithmic": hbm_gbs, "algorithmic_flops_per_step_per_gpu": flops_rank}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,1335 @@
+// C ABI (include/rc_api.h) and the host-side orchestration of the reference's algorithms over
+// the CUDA kernels.  Each routine cites the reference lines whose behaviour it reproduces
+// (paths relative to /root/reference).  There is no CPU fallback anywhere in this file: every
+// numerical step is a kernel launch on the context stream.
+#include <type_traits>
+#include "host_linalg.cuh"
+
+// ============================================================================ handles
+struct rc_qr { rc_matrix* q = nullptr; rc_matrix* r = nullptr; std::vector<uint64_t> ind; };
+struct rc_lq { rc_matrix* l = nullptr; rc_matrix* q = nullptr; std::vector<uint64_t> ind; };
+struct rc_svd { rc_matrix* u = nullptr; rc_matrix* vt = nullptr; std::vector<double> s; };
+struct rc_column_id { rc_matrix* c = nullptr; rc_matrix* z = nullptr; std::vector<uint64_t> col_ind; };
+struct rc_row_id { rc_matrix* x = nullptr; rc_matrix* r = nullptr; std::vector<uint64_t> row_ind; };
+struct rc_two_sided_id {
+    rc_matrix* c = nullptr; rc_matrix* x = nullptr; rc_matrix* r = nullptr;
+    std::vector<uint64_t> row_ind, col_ind;
+};
+
+namespace {
+
+template <class F>
+rc_status guard(rc_ctx* ctx, F&& f) {
+    try {
+        f();
+        return RC_OK;
+    } catch (const RcError& e) {
+        if (ctx) ctx->err = e.msg;
+        return e.status;
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->err = "host allocation failed";
+        return RC_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->err = e.what();
+        return RC_INVALID_ARGUMENT;
+    } catch (...) {
+        if (ctx) ctx->err = "unknown error";
+        return RC_INVALID_ARGUMENT;
+    }
+}
+
+#define RC_DISPATCH(dt, ...)                                                      \
+    switch (dt) {                                                                 \
+        case RC_F32: { using T = float; __VA_ARGS__; } break;                     \
+        case RC_F64: { using T = double; __VA_ARGS__; } break;                    \
+        case RC_C32: { using T = c32; __VA_ARGS__; } break;                       \
+        case RC_C64: { using T = c64; __VA_ARGS__; } break;                       \
+        default: RC_THROW(RC_INVALID_ARGUMENT, "bad dtype %d", (int)(dt));        \
+    }
+
+void check_same(const rc_matrix* a, const rc_matrix* b) {
+    RC_REQUIRE(a && b, "null matrix handle");
+    RC_REQUIRE(a->dtype == b->dtype, "scalar types differ");
+}
+
+double dev_scalar(rc_ctx* c, const double* d) {
+    double h = 0.0;
+    RC_CUDA(cudaMemcpyAsync(&h, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    return h;
+}
+
+}  // namespace
+
+// ============================================================================ GEMM dispatch
+// Replaces ndarray `.dot` (reference N5).  f64/c64 contractions with a plain or (conj-)transposed
+// left operand go to the TMA-fed DMMA kernels; everything else to the generic SIMT tiles.
+template <class T>
+void gemm(rc_ctx* c, RcOp opa, RcOp opb, int64_t M, int64_t N, int64_t K, const T* A, int64_t lda,
+          const T* B, int64_t ldb, T* C, int64_t ldc, T alpha, T beta) {
+    if (M == 0 || N == 0) return;
+    if (K == 0) {
+        RC_REQUIRE(rc_real(beta) == RealOf<T>(0) && rc_imag(beta) == RealOf<T>(0), "gemm: K == 0 with beta != 0");
+        k_fill<T>(c, C, M, N, ldc, rc_zero<T>());
+        return;
+    }
+    bool plain = (rc_real(alpha) == RealOf<T>(1) && rc_imag(alpha) == RealOf<T>(0) &&
+                  rc_real(beta) == RealOf<T>(0) && rc_imag(beta) == RealOf<T>(0));
+    bool big = (double)M * (double)N * (double)K >= 4.0e6;
+    if (plain && big && c->gemm_impl == 0 && opb == RC_OP_N) {
+        if constexpr (std::is_same<T, double>::value) {
+            if (gemm_dmma_f64(c, opa != RC_OP_N, M, N, K, A, lda, B, ldb, C, ldc)) return;
+        } else if constexpr (std::is_same<T, c64>::value) {
+            if (opa == RC_OP_N || opa == RC_OP_H)
+                if (gemm_dmma_c64(c, opa == RC_OP_H, M, N, K, A, lda, B, ldb, C, ldc)) return;
+        }
+    }
+    gemm_generic<T>(c, opa, opb, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+    c->gemm_flops += (ScalarTraits<T>::is_complex ? 8 : 2) * M * N * K;
+}
+
+// ============================================================================ pivoted QR
+namespace {
+
+// TSQR of a (possibly row-sharded) tall panel, with the extra all-gather level across ranks.
+template <class T>
+struct DistTsqr {
+    rc_ctx* c;
+    bool sharded;
+    int64_t w;
+    TsqrFactor<T> local, top;
+    DevBuf<T> stack;
+    const T* r() const { return sharded ? top.r : local.r; }
+    void factor(rc_ctx* ctx, T* y, int64_t ld, int64_t m, int64_t width, bool is_sharded) {
+        c = ctx; w = width; sharded = is_sharded && ctx->nranks > 1;
+        tsqr_factor<T>(c, y, ld, m, w, local);
+        if (sharded) {
+            // all-gather of the w x w R factors; every rank factors the stack redundantly
+            stack.alloc(c, (size_t)c->nranks * w * w);
+            comm_allgather(c, local.r, stack.p, (size_t)w * w * sizeof(T));
+            tsqr_factor<T>(c, stack.p, w, (int64_t)c->nranks * w, w, top);
+        }
+    }
+    // out (m x nc) = Q [ctop ; 0]
+    void apply(const T* ctop, int64_t ldc, int64_t nc, T* out, int64_t ldo) {
+        if (!sharded) { tsqr_apply_q<T>(c, local, ctop, ldc, nc, out, ldo); return; }
+        DevBuf<T> mid(c, (size_t)c->nranks * w * nc);
+        tsqr_apply_q<T>(c, top, ctop, ldc, nc, mid.p, nc);
+        tsqr_apply_q<T>(c, local, mid.p + (size_t)c->rank * w * nc, nc, nc, out, ldo);
+    }
+};
+
+void download_ind(rc_ctx* c, const int* dind, int64_t n, std::vector<uint64_t>& ind) {
+    std::vector<int> h((size_t)n);
+    RC_CUDA(cudaMemcpyAsync(h.data(), dind, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    ind.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (h[i] < 0 || h[i] >= n) RC_THROW(RC_PIVOTED_QR_ERROR, "pivoted QR produced an invalid permutation");
+        ind[i] = (uint64_t)h[i];
+    }
+}
+
+// Tall-skinny route: Y = Q0 R0 by (distributed) Householder TSQR, pivoting on R0, Q = Q0 Q1.
+// Panels wider than the shared-memory limit are orthogonalised block by block against the
+// previous panels (two projection passes) before their own TSQR.
+template <class T>
+void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, bool sharded, int dtype, QrParts& out) {
+    const int64_t wmax = tsqr_max_width(c, dtype);
+    DevBuf<T> r0(c, (size_t)w * w);
+    DevBuf<T> wc(c, (size_t)w * w), vbuf(c, (size_t)w * w), tau(c, (size_t)w);
+    DevBuf<int> dind(c, (size_t)w);
+    MatPtr r(mat_new(c, dtype, w, w));
+    MatPtr q(mat_new(c, dtype, m, ncq));
+    DevBuf<T> q1(c, (size_t)w * ncq);
+
+    if (w <= wmax) {
+        DistTsqr<T> ts;
+        ts.factor(c, y, ldy, m, w, sharded);
+        // column-major copy of R0 = transpose of the row-major factor
+        k_transpose<T>(c, wc.p, w, ts.r(), w, w, w, false);
+        pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
+        pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1.p, ncq);
+        ts.apply(q1.p, ncq, ncq, P<T>(q.get()), q->ld);
+    } else {
+        int64_t npan = (w + wmax - 1) / wmax;
+        int64_t wp = (w + npan - 1) / npan;
+        DevBuf<T> qfull(c, (size_t)m * w);
+        k_fill<T>(c, r0.p, w, w, w, rc_zero<T>());
+        for (int64_t c0 = 0; c0 < w; c0 += wp) {
+            int64_t cw = std::min(wp, w - c0);
+            T* yp = y + c0;
+            if (c0 > 0) {
+                // block classical Gram-Schmidt against the previous panels, twice ("twice is enough")
+                DevBuf<T> t(c, (size_t)c0 * cw);
+                for (int pass = 0; pass < 2; ++pass) {
+                    gemm<T>(c, RC_OP_H, RC_OP_N, c0, cw, m, qfull.p, w, yp, ldy, t.p, cw, rc_one<T>(), rc_zero<T>());
+                    if (sharded) comm_allreduce_sum(c, t.p, (size_t)c0 * cw, dtype);
+                    gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, c0, qfull.p, w, t.p, cw, yp, ldy, rc_make<T>(-1.0, 0.0), rc_one<T>());
+                    k_add<T>(c, r0.p + c0, w, r0.p + c0, w, t.p, cw, c0, cw);     // R0[0:c0, c0:c0+cw] += t
+                }
+            }
+            DistTsqr<T> ts;
+            ts.factor(c, yp, ldy, m, cw, sharded);
+            k_copy<T>(c, r0.p + c0 * w + c0, w, ts.r(), cw, cw, cw);
+            DevBuf<T> eye(c, (size_t)cw * cw);
+            k_eye<T>(c, eye.p, cw, cw, cw);
+            ts.apply(eye.p, cw, cw, qfull.p + c0, w);
+        }
+        k_transpose<T>(c, wc.p, w, r0.p, w, w, w, false);
+        pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
+        pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1.p, ncq);
+        gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, qfull.p, w, q1.p, ncq, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
+    }
+    download_ind(c, dind.p, w, out.ind);
+    out.q.reset(q.release());
+    out.r.reset(r.release());
+}
+
+}  // namespace
+
+// PivotedQR::pivoted_qr (src/pivoted_qr.rs:25-31, 81-119): arr[:, ind] = q r.
+// input_is_conj_transposed: `arr` holds S (n x p row-major) and the matrix factored is M = S^H
+// (p x n) -- the access pattern of pivoted_lq / LQ::compute_from (src/pivoted_qr.rs:32-41,
+// src/qr.rs:354-362) and of b = (A^H Q)^H (src/qr.rs:315), without materialising the transpose.
+template <class T>
+void pivoted_qr_impl(rc_ctx* c, const rc_matrix* arr, bool input_is_conj_transposed, int64_t ncq,
+                     bool may_destroy, QrParts& out) {
+    const int dtype = arr->dtype;
+    const int64_t p = input_is_conj_transposed ? arr->cols : arr->rows;   // rows of M
+    const int64_t n = input_is_conj_transposed ? arr->rows : arr->cols;   // cols of M
+    RC_REQUIRE(p > 0 && n > 0, "pivoted_qr: empty matrix");
+    const int64_t kk = std::min(p, n);
+    if (ncq < 0 || ncq > kk) ncq = kk;
+    const bool sharded = !input_is_conj_transposed && mat_sharded(arr);
+    const int64_t p_global = sharded ? arr->global_rows : p;
+
+    if (p_global >= n && (p >= n || sharded)) {
+        // ---- tall: TSQR route (destroys its input, so work on a copy unless allowed)
+        MatPtr work;
+        T* y; int64_t ldy;
+        if (input_is_conj_transposed) {
+            work.reset(mat_conj_transpose<T>(c, arr));
+            y = P<T>(work.get()); ldy = work->ld;
+        } else if (may_destroy) {
+            y = P<T>(arr); ldy = arr->ld;
+        } else {
+            work.reset(mat_clone<T>(c, arr));
+            y = P<T>(work.get()); ldy = work->ld;
+        }
+        pqr_tall<T>(c, y, ldy, p, n, ncq, sharded, dtype, out);
+        if (sharded) inherit_shard(out.q.get(), arr);
+        return;
+    }
+    RC_REQUIRE(!sharded, "pivoted_qr: a row-sharded matrix must be tall (rows >= cols)");
+    // ---- general / short-wide: cooperative pivoted Householder on a column-major copy
+    DevBuf<T> wc(c, (size_t)p * n);
+    if (input_is_conj_transposed) {
+        // column j of M = conj(row j of S): conj copy of S is already column-major M
+        k_copy<T>(c, wc.p, p, P<T>(arr), arr->ld, n, p);
+        k_conj_inplace<T>(c, wc.p, n, p, p);
+    } else {
+        k_transpose<T>(c, wc.p, p, P<T>(arr), arr->ld, p, n, false);
+    }
+    DevBuf<T> vbuf(c, (size_t)p * kk), tau(c, (size_t)kk);
+    DevBuf<int> dind(c, (size_t)n);
+    MatPtr r(mat_new(c, dtype, kk, n));
+    pivqr_factor<T>(c, wc.p, p, p, n, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
+    MatPtr q(mat_new(c, dtype, p, ncq));
+    pivqr_form_q<T>(c, vbuf.p, tau.p, p, kk, ncq, P<T>(q.get()), q->ld);
+    download_ind(c, dind.p, n, out.ind);
+    out.q.reset(q.release());
+    out.r.reset(r.release());
+}
+
+// ============================================================================ SVD
+// ComputeSVD::compute_svd (src/compute_svd.rs:14-30): thin SVD, s descending.
+// Tall (or conj-transposed short-wide) input is reduced by TSQR to a w x w triangle, which a
+// one-sided Jacobi kernel diagonalises: arr = (Q0 Ur) diag(s) W^H.
+template <class T>
+void svd_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int dtype, bool sharded,
+              MatPtr& u, std::vector<double>& s, MatPtr& wmat) {
+    DevBuf<double> ds(c, (size_t)w);
+    MatPtr um(mat_new(c, dtype, m, w)), wm(mat_new(c, dtype, w, w));
+    const int64_t wmax = tsqr_max_width(c, dtype);
+    if (w <= wmax && m >= w) {
+        DistTsqr<T> ts;
+        ts.factor(c, y, ldy, m, w, sharded);
+        DevBuf<T> ur(c, (size_t)w * w);
+        jacobi_svd<T>(c, ts.r(), w, w, w, ur.p, w, ds.p, P<T>(wm.get()), wm->ld);
+        ts.apply(ur.p, w, w, P<T>(um.get()), um->ld);
+    } else {
+        RC_REQUIRE(!sharded, "svd: row-sharded input must be tall-skinny");
+        jacobi_svd<T>(c, y, ldy, m, w, P<T>(um.get()), um->ld, ds.p, P<T>(wm.get()), wm->ld);
+    }
+    s.resize((size_t)w);
+    RC_CUDA(cudaMemcpyAsync(s.data(), ds.p, sizeof(double) * w, cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    u.reset(um.release());
+    wmat.reset(wm.release());
+}
+
+template <class T>
+void svd_impl(rc_ctx* c, const rc_matrix* arr, bool input_is_conj_transposed, SvdParts& out) {
+    const int dtype = arr->dtype;
+    const int64_t m = input_is_conj_transposed ? arr->cols : arr->rows;
+    const int64_t n = input_is_conj_transposed ? arr->rows : arr->cols;
+    RC_REQUIRE(m > 0 && n > 0, "svd: empty matrix");
+    const bool sharded = !input_is_conj_transposed && mat_sharded(arr);
+    MatPtr uu, ww;
+    if (m >= n) {
+        // M = U S W^H directly
+        MatPtr work(input_is_conj_transposed ? mat_conj_transpose<T>(c, arr) : mat_clone<T>(c, arr));
+        svd_tall<T>(c, P<T>(work.get()), work->ld, m, n, dtype, sharded, uu, out.s, ww);
+        out.u.reset(uu.release());
+        if (sharded) inherit_shard(out.u.get(), arr);
+        out.vt.reset(mat_conj_transpose<T>(c, ww.get()));
+    } else {
+        // M^H (n x m, tall) = Ub S Wb^H  =>  M = Wb S Ub^H : u = Wb, vt = Ub^H
+        MatPtr work(input_is_conj_transposed ? mat_clone<T>(c, arr) : mat_conj_transpose<T>(c, arr));
+        svd_tall<T>(c, P<T>(work.get()), work->ld, n, m, dtype, false, uu, out.s, ww);
+        out.u.reset(ww.release());
+        out.vt.reset(mat_conj_transpose<T>(c, uu.get()));
+    }
+}
+
+// ============================================================================ algorithms
+namespace {
+
+template <class T>
+rc_matrix* gaussian_new(rc_ctx* c, int dtype, int64_t rows, int64_t cols, uint64_t seed, uint32_t stream, int64_t row_offset) {
+    MatPtr o(mat_new(c, dtype, rows, cols));
+    k_gaussian<T>(c, P<T>(o.get()), rows, cols, o->ld, seed, stream, row_offset);
+    return o.release();
+}
+
+// MatMat::matmat (src/types.rs:58-71)
+template <class T>
+rc_matrix* matmat_impl(rc_ctx* c, const rc_matrix* a, const rc_matrix* x) {
+    RC_REQUIRE(a->cols == x->rows, "matmat: operator has %lld columns, X has %lld rows", (long long)a->cols, (long long)x->rows);
+    MatPtr y(mat_mul<T>(c, RC_OP_N, a, RC_OP_N, x));
+    inherit_shard(y.get(), a);
+    return y.release();
+}
+// ConjMatMat::conj_matmat (src/types.rs:88-101, 129-131); partial sums across row shards.
+template <class T>
+rc_matrix* conj_matmat_impl(rc_ctx* c, const rc_matrix* a, const rc_matrix* x) {
+    RC_REQUIRE(a->rows == x->rows, "conj_matmat: operator has %lld rows, X has %lld rows", (long long)a->rows, (long long)x->rows);
+    MatPtr z(mat_mul<T>(c, RC_OP_H, a, RC_OP_N, x));
+    if (mat_sharded(a)) {
+        // reduce the dense payload row by row when padded; ld == cols for the common case
+        if (z->ld == z->cols) comm_allreduce_sum(c, z->data, (size_t)z->rows * z->cols, z->dtype);
+        else for (int64_t i = 0; i < z->rows; ++i)
+            comm_allreduce_sum(c, (char*)z->data + (size_t)i * z->ld * rc_dtype_size(z->dtype), (size_t)z->cols, z->dtype);
+    }
+    return z.release();
+}
+
+// MaxColNorm::max_col_norm (src/random_sampling.rs:175-199)
+template <class T>
+double max_col_norm_impl(rc_ctx* c, const rc_matrix* m) {
+    if (m->cols == 0) return 0.0;
+    DevBuf<double> n2(c, (size_t)m->cols);
+    k_col_norms2<T>(c, P<T>(m), m->ld, m->rows, m->cols, n2.p);
+    if (mat_sharded(m)) comm_allreduce_sum(c, n2.p, (size_t)m->cols, RC_F64);
+    std::vector<double> h((size_t)m->cols);
+    RC_CUDA(cudaMemcpyAsync(h.data(), n2.p, sizeof(double) * m->cols, cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    double best = 0.0;
+    for (double v : h) best = std::max(best, v);
+    return std::sqrt(best);
+}
+
+// SampleRange::sample_range_by_rank (src/random_sampling.rs:103-118)
+template <class T>
+rc_matrix* sample_by_rank_impl(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p, const rc_matrix* omega, uint64_t seed) {
+    const int64_t n = a->cols, l = k + p;
+    RC_REQUIRE(k > 0 && p >= 0, "sample_range_by_rank: need k > 0, p >= 0");
+    MatPtr gen;
+    if (!omega) { gen.reset(gaussian_new<T>(c, a->dtype, n, l, seed, 0, 0)); omega = gen.get(); }
+    RC_REQUIRE(omega->rows == n && omega->cols == l, "omega must be %lld x %lld", (long long)n, (long long)l);
+    MatPtr y(matmat_impl<T>(c, a, omega));                       // :111-112
+    QrParts qr;
+    int64_t kk = std::min<int64_t>(mat_sharded(a) ? a->global_rows : a->rows, l);
+    pivoted_qr_impl<T>(c, y.get(), false, std::min(k, kk), true, qr);   // :114-115 compress(RANK(k))
+    return qr.q.release();
+}
+
+// SampleRangePowerIteration::sample_range_power_iteration (src/random_sampling.rs:131-160).
+// Reference semantics (quirk Q1): `op_omega` inside the loop is a fresh binding, so every trip
+// restarts from Y0 = A Omega and the result equals the it_count = 1 result; every trip is
+// executed as the reference executes it.  Option "true_power_iteration" advances Y instead.
+template <class T>
+rc_matrix* sample_power_impl(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p, int64_t it_count,
+                             const rc_matrix* omega, uint64_t seed) {
+    const int64_t n = a->cols, l = k + p;
+    RC_REQUIRE(k > 0 && p >= 0 && it_count >= 0, "sample_range_power_iteration: bad arguments");
+    MatPtr gen;
+    if (!omega) { gen.reset(gaussian_new<T>(c, a->dtype, n, l, seed, 0, 0)); omega = gen.get(); }
+    RC_REQUIRE(omega->rows == n && omega->cols == l, "omega must be %lld x %lld", (long long)n, (long long)l);
+    MatPtr y0(matmat_impl<T>(c, a, omega));                      // :140-141
+    MatPtr res;                                                  // :142 (res = y0 unless a trip replaces it)
+    MatPtr cur;                                                  // only for true_power_iteration
+    for (int64_t index = 0; index < it_count; ++index) {
+        const rc_matrix* start = (c->true_power_iteration && cur.get()) ? cur.get() : y0.get();
+        QrParts q1;
+        pivoted_qr_impl<T>(c, start, false, -1, false, q1);      // :145-146 (all columns of Q)
+        MatPtr z(conj_matmat_impl<T>(c, a, q1.q.get()));          // :148
+        QrParts q2;
+        pivoted_qr_impl<T>(c, z.get(), false, -1, true, q2);     // :148-149
+        MatPtr ynew(matmat_impl<T>(c, a, q2.q.get()));            // :150
+        if (c->true_power_iteration) { cur.reset(ynew.release()); if (index == it_count - 1) res.reset(cur.release()); }
+        else if (index == it_count - 1) res.reset(ynew.release());   // :151-153
+    }
+    const rc_matrix* fin = res.get() ? res.get() : y0.get();
+    QrParts qr;
+    int64_t kk = std::min<int64_t>(mat_sharded(a) ? a->global_rows : a->rows, l);
+    pivoted_qr_impl<T>(c, fin, false, std::min(k, kk), true, qr);   // :156-159
+    return qr.q.release();
+}
+
+// AdaptiveSampling::sample_range_adaptive (src/random_sampling.rs:223-274).  Q and B live in
+// pre-allocated device buffers with a column / row cursor instead of the crate's re-concatenation.
+template <class T>
+rc_matrix* sample_adaptive_impl(rc_ctx* c, const rc_matrix* a, double rel_tol_in, int64_t s, const rc_matrix* omega_blocks,
+                                uint64_t seed, int64_t max_rank, std::vector<uint64_t>& hist_rank, std::vector<double>& hist_res) {
+    using R = RealOf<T>;
+    const int64_t m = a->rows, n = a->cols;
+    const int64_t m_glob = mat_sharded(a) ? a->global_rows : m;
+    RC_REQUIRE(s > 0, "sample_range_adaptive: sample_size must be positive");
+    if (max_rank <= 0) max_rank = std::min(m_glob, n);
+    const int64_t cap = (max_rank + s - 1) / s * s + s;
+    const R tol_factor = (R)(10.0 * std::sqrt(2.0 / 3.14159265358979323846));   // :229-232
+    const R rel_tol = (R)rel_tol_in;
+    uint32_t draw = 0;
+    auto next_omega = [&](MatPtr& holder) -> const rc_matrix* {
+        if (omega_blocks) {
+            RC_REQUIRE((int64_t)(draw + 1) * s <= omega_blocks->cols, "omega_blocks exhausted after %u draws", draw);
+            holder.reset(mat_slice<T>(c, omega_blocks, 0, n, (int64_t)draw * s, (int64_t)(draw + 1) * s));
+        } else {
+            holder.reset(gaussian_new<T>(c, a->dtype, n, s, seed, draw, 0));
+        }
+        ++draw;
+        return holder.get();
+    };
+    if (omega_blocks) RC_REQUIRE(omega_blocks->rows == n, "omega_blocks must have %lld rows", (long long)n);
+    MatPtr om;
+    const rc_matrix* omega = next_omega(om);                                     // :238
+    MatPtr y(matmat_impl<T>(c, a, omega));                                       // :239
+    const R operator_norm = (R)max_col_norm_impl<T>(c, y.get()) * tol_factor;    // :241
+    R max_norm = operator_norm;
+    MatPtr qbuf(mat_new(c, a->dtype, m, cap)), bbuf(mat_new(c, a->dtype, cap, n));
+    int64_t r = 0;
+    while (max_norm / operator_norm >= rel_tol) {                                // :248
+        if (r + s > max_rank) RC_THROW(RC_COMPRESSION_ERROR, "adaptive sampler exceeded max_rank %lld", (long long)max_rank);
+        if (r > 0) {                                                             // :250-252
+            DevBuf<T> t(c, (size_t)r * s);
+            gemm<T>(c, RC_OP_H, RC_OP_N, r, s, m, P<T>(qbuf.get()), qbuf->ld, P<T>(y.get()), y->ld, t.p, s, rc_one<T>(), rc_zero<T>());
+            if (mat_sharded(a)) comm_allreduce_sum(c, t.p, (size_t)r * s, a->dtype);
+            gemm<T>(c, RC_OP_N, RC_OP_N, m, s, r, P<T>(qbuf.get()), qbuf->ld, t.p, s, P<T>(y.get()), y->ld, rc_make<T>(-1.0, 0.0), rc_one<T>());
+        }
+        QrParts qq;
+        pivoted_qr_impl<T>(c, y.get(), false, -1, true, qq);                     // :254
+        const int64_t sq = qq.q->cols;
+        MatPtr z(conj_matmat_impl<T>(c, a, qq.q.get()));                          // :256-260  (A^H q)
+        k_transpose<T>(c, P<T>(bbuf.get()) + r * bbuf->ld, bbuf->ld, P<T>(z.get()), z->ld, n, sq, true);
+        k_copy<T>(c, P<T>(qbuf.get()) + r, qbuf->ld, P<T>(qq.q.get()), qq.q->ld, m, sq);   // :262
+        r += sq;
+        omega = next_omega(om);                                                  // :265
+        y.reset(matmat_impl<T>(c, a, omega));                                    // :266  A Omega
+        {
+            DevBuf<T> t(c, (size_t)r * s);
+            gemm<T>(c, RC_OP_N, RC_OP_N, r, s, n, P<T>(bbuf.get()), bbuf->ld, P<T>(omega), omega->ld, t.p, s, rc_one<T>(), rc_zero<T>());
+            gemm<T>(c, RC_OP_N, RC_OP_N, m, s, r, P<T>(qbuf.get()), qbuf->ld, t.p, s, P<T>(y.get()), y->ld, rc_make<T>(-1.0, 0.0), rc_one<T>());
+        }
+        max_norm = (R)max_col_norm_impl<T>(c, y.get()) * tol_factor;             // :269
+        hist_rank.push_back((uint64_t)r);
+        hist_res.push_back((double)(max_norm / operator_norm));                  // :270
+    }
+    MatPtr q(mat_slice<T>(c, qbuf.get(), 0, m, 0, r));
+    inherit_shard(q.get(), a);
+    return q.release();
+}
+
+// QRTraits::compute_from_range_estimate (src/qr.rs:311-323)
+template <class T>
+void qr_from_range_impl(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, QrParts& out) {
+    RC_REQUIRE(range->rows == op->rows, "range estimate and operator row counts differ");
+    MatPtr z(conj_matmat_impl<T>(c, op, range));                 // A^H Q  (n x k)
+    QrParts qb;
+    pivoted_qr_impl<T>(c, z.get(), true, -1, false, qb);         // pivoted QR of b = (A^H Q)^H, :315-316
+    out.q.reset(mat_mul<T>(c, RC_OP_N, range, RC_OP_N, qb.q.get()));   // :319
+    inherit_shard(out.q.get(), range);
+    out.r.reset(qb.r.release());
+    out.ind = qb.ind;
+}
+
+// SVDTraits::compute_from_range_estimate (src/svd.rs:171-183)
+template <class T>
+void svd_from_range_impl(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, SvdParts& out) {
+    RC_REQUIRE(range->rows == op->rows, "range estimate and operator row counts differ");
+    MatPtr z(conj_matmat_impl<T>(c, op, range));                 // A^H Q = b^H  (n x k)
+    SvdParts sb;
+    svd_impl<T>(c, z.get(), true, sb);                           // SVD of b, :175-176
+    out.u.reset(mat_mul<T>(c, RC_OP_N, range, RC_OP_N, sb.u.get()));   // :179
+    inherit_shard(out.u.get(), range);
+    out.vt.reset(sb.vt.release());
+    out.s = sb.s;
+}
+
+template <class T>
+rc_matrix* permute_impl(rc_ctx* c, const rc_matrix* m, const std::vector<uint64_t>& idx, int mode) {
+    // src/permutation.rs:84-144
+    const bool cols = (mode == RC_PERM_COL || mode == RC_PERM_COLINV);
+    RC_REQUIRE((int64_t)idx.size() == (cols ? m->cols : m->rows),
+               cols ? "Length of index array and number of columns differ." : "Length of index array and number of rows differ.");
+    std::vector<uint64_t> use = (mode == RC_PERM_COLINV || mode == RC_PERM_ROWINV) ? invert_perm(idx) : idx;
+    for (uint64_t v : use) RC_REQUIRE(v < use.size(), "index out of range in permutation");
+    DevIndex di(c, use);
+    MatPtr o(mat_new(c, m->dtype, m->rows, m->cols));
+    if (cols) k_gather_cols<T>(c, P<T>(o.get()), o->ld, P<T>(m), m->ld, m->rows, m->cols, di.d.p);
+    else k_gather_rows<T>(c, P<T>(o.get()), o->ld, P<T>(m), m->ld, m->rows, m->cols, di.d.p);
+    return o.release();
+}
+
+// QRTraits::column_id (src/qr.rs:270-309)
+template <class T>
+void column_id_impl(rc_ctx* c, const rc_matrix* q, const rc_matrix* r, const std::vector<uint64_t>& ind, rc_column_id* out) {
+    const int64_t rank = q->cols, ncols = r->cols;
+    MatPtr cm, z(mat_new(c, q->dtype, rank, ncols));
+    if (rank == ncols) {
+        cm.reset(mat_mul<T>(c, RC_OP_N, q, RC_OP_N, r));                         // :277
+        k_eye<T>(c, P<T>(z.get()), rank, ncols, z->ld);
+    } else {
+        MatPtr r11(mat_slice<T>(c, r, 0, rank, 0, rank));                        // :286
+        cm.reset(mat_mul<T>(c, RC_OP_N, q, RC_OP_N, r11.get()));                 // :287
+        k_eye<T>(c, P<T>(z.get()), rank, ncols, z->ld);                          // [I | .]
+        // all n - k triangular solves at once (:290-301)
+        trsm_upper<T>(c, P<T>(r11.get()), r11->ld, false, rank, P<T>(r) + rank, r->ld, ncols - rank,
+                      P<T>(z.get()) + rank, z->ld);
+    }
+    MatPtr zp(permute_impl<T>(c, z.get(), ind, RC_PERM_COLINV));                 // :278, :305
+    inherit_shard(cm.get(), q);
+    out->c = cm.release();
+    out->z = zp.release();
+    out->col_ind = ind;
+}
+
+// LQTraits::row_id (src/qr.rs:363-403)
+template <class T>
+void row_id_impl(rc_ctx* c, const rc_matrix* l, const rc_matrix* q, const std::vector<uint64_t>& ind, rc_row_id* out) {
+    const int64_t rank = q->rows, nrows = l->rows;
+    MatPtr rm, x(mat_new(c, l->dtype, nrows, rank));
+    if (rank == nrows) {
+        rm.reset(mat_mul<T>(c, RC_OP_N, l, RC_OP_N, q));                         // :371
+        k_eye<T>(c, P<T>(x.get()), nrows, rank, x->ld);
+    } else {
+        MatPtr l11(mat_slice<T>(c, l, 0, rank, 0, rank));                        // :379
+        rm.reset(mat_mul<T>(c, RC_OP_N, l11.get(), RC_OP_N, q));                 // :380
+        k_eye<T>(c, P<T>(x.get()), nrows, rank, x->ld);
+        // X2 L11 = L21  <=>  L11^T X2^T = L21^T : upper solve with the plain transpose (:383-395)
+        const int64_t nr = nrows - rank;
+        DevBuf<T> bt(c, (size_t)rank * nr), xt(c, (size_t)rank * nr);
+        k_transpose<T>(c, bt.p, nr, P<T>(l) + rank * l->ld, l->ld, nr, rank, false);
+        trsm_upper<T>(c, P<T>(l11.get()), l11->ld, true, rank, bt.p, nr, nr, xt.p, nr);
+        k_transpose<T>(c, P<T>(x.get()) + rank * x->ld, x->ld, xt.p, nr, rank, nr, false);
+    }
+    MatPtr xp(permute_impl<T>(c, x.get(), ind, RC_PERM_ROWINV));                 // :369, :399
+    out->x = xp.release();
+    out->r = rm.release();
+    out->row_ind = ind;
+}
+
+template <class T>
+double rel_diff_impl(rc_ctx* c, const rc_matrix* first, const rc_matrix* second) {
+    // src/types.rs:182-188, 190-196
+    RC_REQUIRE(first->rows == second->rows && first->cols == second->cols, "rel_diff: shapes differ");
+    DevBuf<double> d(c, 2);
+    k_diff_fro2<T>(c, P<T>(first), first->ld, P<T>(second), second->ld, first->rows, first->cols, d.p);
+    k_fro2<T>(c, P<T>(second), second->ld, second->rows, second->cols, d.p + 1);
+    if (mat_sharded(second)) comm_allreduce_sum(c, d.p, 2, RC_F64);
+    double h[2];
+    RC_CUDA(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    return std::sqrt(h[0]) / std::sqrt(h[1]);
+}
+
+// RandomMatrix::random_orthogonal_matrix (src/random_matrix.rs:35-56): left singular vectors of a Gaussian.
+template <class T>
+rc_matrix* random_orthogonal_impl(rc_ctx* c, int dtype, int64_t rows, int64_t cols, uint64_t seed, uint32_t stream) {
+    int64_t m = rows, n = cols;
+    const bool swap = cols > rows;
+    if (swap) std::swap(m, n);
+    MatPtr g(gaussian_new<T>(c, dtype, m, n, seed, stream, 0));
+    SvdParts sv;
+    svd_impl<T>(c, g.get(), false, sv);
+    if (swap) return mat_conj_transpose<T>(c, sv.u.get());
+    return sv.u.release();
+}
+
+template <class T>
+rc_matrix* low_rank_from_factors(rc_ctx* c, const rc_matrix* u, const std::vector<double>& sig, const rc_matrix* vt) {
+    using R = RealOf<T>;
+    std::vector<R> hs(sig.size());
+    for (size_t i = 0; i < sig.size(); ++i) hs[i] = (R)sig[i];
+    DevBuf<R> ds(c, hs.size());
+    RC_CUDA(cudaMemcpyAsync(ds.p, hs.data(), sizeof(R) * hs.size(), cudaMemcpyHostToDevice, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    MatPtr sv(mat_clone<T>(c, vt));
+    k_scale_rows<T>(c, P<T>(sv.get()), sv->rows, sv->cols, sv->ld, ds.p);
+    return mat_mul<T>(c, RC_OP_N, u, RC_OP_N, sv.get());
+}
+
+std::vector<uint64_t> vec_from(const uint64_t* p, size_t n) {
+    RC_REQUIRE(p || n == 0, "null index array");
+    return std::vector<uint64_t>(p, p + n);
+}
+void copy_ind(const std::vector<uint64_t>& v, uint64_t* out, size_t n) {
+    RC_REQUIRE(out && n >= v.size(), "index output buffer too small (%zu < %zu)", n, v.size());
+    memcpy(out, v.data(), v.size() * sizeof(uint64_t));
+}
+
+}  // namespace
+
+template <class T>
+static rc_matrix* scaled_vt(rc_ctx* c, const rc_svd* svd) {
+    using R = RealOf<T>;
+    std::vector<R> hs(svd->s.size());
+    for (size_t i = 0; i < hs.size(); ++i) hs[i] = (R)svd->s[i];
+    DevBuf<R> ds(c, std::max<size_t>(hs.size(), 1));
+    if (!hs.empty()) {
+        RC_CUDA(cudaMemcpyAsync(ds.p, hs.data(), sizeof(R) * hs.size(), cudaMemcpyHostToDevice, c->stream));
+        RC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    MatPtr sv(mat_clone<T>(c, svd->vt));
+    k_scale_rows<T>(c, P<T>(sv.get()), sv->rows, sv->cols, sv->ld, ds.p);
+    return sv.release();
+}
+template <class T>
+static rc_matrix* chain_apply(rc_ctx* c, std::initializer_list<const rc_matrix*> factors, const rc_matrix* rhs) {
+    // right-to-left: f0 (f1 (... rhs))   (src/col_interp_decomp.rs:141, src/two_sided_interp_decomp.rs:160)
+    MatPtr cur;
+    const rc_matrix* x = rhs;
+    std::vector<const rc_matrix*> fs(factors);
+    for (size_t i = fs.size(); i-- > 0;) {
+        MatPtr nxt(mat_mul<T>(c, RC_OP_N, fs[i], RC_OP_N, x));
+        cur.reset(nxt.release());
+        x = cur.get();
+    }
+    return cur.release();
+}
+
+// ============================================================================ extern "C"
+extern "C" {
+
+int rc_version(void) { return 100; }
+
+rc_status rc_ctx_create(int device, rc_ctx** out) {
+    if (!out) return RC_INVALID_ARGUMENT;
+    *out = nullptr;
+    rc_ctx* c = new rc_ctx();
+    rc_status st = guard(c, [&] {
+        int ndev = 0;
+        RC_CUDA(cudaGetDeviceCount(&ndev));
+        RC_REQUIRE(device >= 0 && device < ndev, "device %d not available (%d visible)", device, ndev);
+        RC_CUDA(cudaSetDevice(device));
+        c->device = device;
+        cudaDeviceProp prop;
+        RC_CUDA(cudaGetDeviceProperties(&prop, device));
+        RC_REQUIRE(prop.major == 10, "this library is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
+        c->sm_count = prop.multiProcessorCount;
+        c->smem_optin = prop.sharedMemPerBlockOptin;
+        RC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+        // keep freed blocks in the stream-ordered pool: workspaces are re-used every call
+        cudaMemPool_t pool;
+        RC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thresh = ~0ull;
+        RC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    });
+    if (st != RC_OK) { fprintf(stderr, "rc_ctx_create: %s\n", c->err.c_str()); delete c; return st; }
+    *out = c;
+    return RC_OK;
+}
+
+rc_status rc_ctx_destroy(rc_ctx* c) {
+    if (!c) return RC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    try { comm_destroy(c); } catch (...) {}
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RC_OK;
+}
+
+rc_status rc_ctx_set_stream(rc_ctx* c, void* s) {
+    if (!c) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->own_stream) RC_CUDA(cudaStreamDestroy(c->stream));
+        c->stream = (cudaStream_t)s;
+        c->own_stream = false;
+    });
+}
+rc_status rc_ctx_synchronize(rc_ctx* c) {
+    if (!c) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { RC_CUDA(cudaStreamSynchronize(c->stream)); });
+}
+const char* rc_last_error_string(rc_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
+    if (!c || !key) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        if (!strcmp(key, "gemm_impl")) c->gemm_impl = (int)v;
+        else if (!strcmp(key, "true_power_iteration")) c->true_power_iteration = (int)v;
+        else RC_THROW(RC_INVALID_ARGUMENT, "unknown option '%s'", key);
+    });
+}
+rc_status rc_ctx_get_counter(rc_ctx* c, const char* key, int64_t* out) {
+    if (!c || !key || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        if (!strcmp(key, "kernel_launches")) *out = c->launches;
+        else if (!strcmp(key, "gemm_flops")) *out = c->gemm_flops;
+        else if (!strcmp(key, "h2d_bytes")) *out = c->h2d_bytes;
+        else if (!strcmp(key, "d2h_bytes")) *out = c->d2h_bytes;
+        else RC_THROW(RC_INVALID_ARGUMENT, "unknown counter '%s'", key);
+    });
+}
+rc_status rc_ctx_reset_counters(rc_ctx* c) {
+    if (!c) return RC_INVALID_ARGUMENT;
+    c->launches = c->gemm_flops = c->h2d_bytes = c->d2h_bytes = 0;
+    return RC_OK;
+}
+
+rc_status rc_comm_get_unique_id(void* out) {
+    if (!out) return RC_INVALID_ARGUMENT;
+    return guard(nullptr, [&] { comm_get_unique_id(out); });
+}
+rc_status rc_ctx_comm_init(rc_ctx* c, const void* id, int rank, int nranks) {
+    if (!c || !id) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { comm_init(c, id, rank, nranks); });
+}
+rc_status rc_ctx_comm_info(rc_ctx* c, int* rank, int* nranks) {
+    if (!c) return RC_INVALID_ARGUMENT;
+    if (rank) *rank = c->rank;
+    if (nranks) *nranks = c->nranks;
+    return RC_OK;
+}
+
+// ---------------------------------------------------------------- matrices
+rc_status rc_matrix_create(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t cols, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(dt >= 0 && dt <= 3, "bad dtype");
+        *out = mat_new(c, dt, rows, cols);
+    });
+}
+rc_status rc_matrix_from_host(rc_ctx* c, rc_dtype dt, const void* host, int64_t rows, int64_t cols,
+                              int64_t rs, int64_t cs, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(dt >= 0 && dt <= 3, "bad dtype");
+        RC_REQUIRE(host || rows * cols == 0, "null host pointer");
+        RC_REQUIRE(rows >= 0 && cols >= 0, "negative dimension");
+        MatPtr m(mat_new(c, dt, rows, cols));
+        const size_t es = rc_dtype_size(dt);
+        if (rows * cols > 0) {
+            if (cs == 1 && rs >= cols) {
+                RC_CUDA(cudaMemcpy2DAsync(m->data, m->ld * es, host, rs * es, cols * es, rows, cudaMemcpyHostToDevice, c->stream));
+            } else {
+                // general strided view (e.g. a transposed ndarray view): stage the spanned host
+                // range, then gather on device
+                RC_REQUIRE(rs >= 0 && cs >= 0, "negative strides are not supported");   // LayoutError analogue
+                size_t span = (size_t)((rows - 1) * rs + (cols - 1) * cs + 1);
+                DevBuf<char> stage(c, span * es);
+                RC_CUDA(cudaMemcpyAsync(stage.p, host, span * es, cudaMemcpyHostToDevice, c->stream));
+                RC_DISPATCH(dt, k_strided_to_dense<T>(c, P<T>(m.get()), m->ld, reinterpret_cast<const T*>(stage.p), rs, cs, rows, cols));
+            }
+            RC_CUDA(cudaStreamSynchronize(c->stream));   // host buffer is not retained
+            c->h2d_bytes += rows * cols * (int64_t)es;
+        }
+        *out = m.release();
+    });
+}
+rc_status rc_matrix_wrap_device(rc_ctx* c, rc_dtype dt, void* dptr, int64_t rows, int64_t cols, int64_t ld, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(dt >= 0 && dt <= 3 && dptr && rows >= 0 && cols >= 0 && ld >= cols, "bad arguments");
+        rc_matrix* m = new rc_matrix();
+        m->ctx = c; m->dtype = dt; m->rows = rows; m->cols = cols; m->ld = ld; m->data = dptr; m->owns = false;
+        *out = m;
+    });
+}
+rc_status rc_matrix_to_host(rc_ctx* c, const rc_matrix* m, void* host) {
+    if (!c || !m) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        if (m->rows * m->cols == 0) return;
+        RC_REQUIRE(host, "null host pointer");
+        const size_t es = rc_dtype_size(m->dtype);
+        RC_CUDA(cudaMemcpy2DAsync(host, m->cols * es, m->data, m->ld * es, m->cols * es, m->rows, cudaMemcpyDeviceToHost, c->stream));
+        RC_CUDA(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += m->rows * m->cols * (int64_t)es;
+    });
+}
+rc_status rc_matrix_to_device(rc_ctx* c, const rc_matrix* m, void* dptr) {
+    if (!c || !m) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        if (m->rows * m->cols == 0) return;
+        RC_REQUIRE(dptr, "null device pointer");
+        const size_t es = rc_dtype_size(m->dtype);
+        RC_CUDA(cudaMemcpy2DAsync(dptr, m->cols * es, m->data, m->ld * es, m->cols * es, m->rows, cudaMemcpyDeviceToDevice, c->stream));
+    });
+}
+rc_status rc_matrix_free(rc_matrix* m) { mat_free(m); return RC_OK; }
+int64_t rc_matrix_rows(const rc_matrix* m) { return m ? m->rows : -1; }
+int64_t rc_matrix_cols(const rc_matrix* m) { return m ? m->cols : -1; }
+int64_t rc_matrix_ld(const rc_matrix* m) { return m ? m->ld : -1; }
+int rc_matrix_dtype(const rc_matrix* m) { return m ? m->dtype : -1; }
+void* rc_matrix_device_ptr(const rc_matrix* m) { return m ? m->data : nullptr; }
+rc_status rc_matrix_set_shard(rc_matrix* m, int64_t global_rows, int64_t row_offset) {
+    if (!m) return RC_INVALID_ARGUMENT;
+    return guard(m->ctx, [&] {
+        RC_REQUIRE(global_rows >= m->rows && row_offset >= 0 && row_offset + m->rows <= global_rows, "bad shard description");
+        m->global_rows = global_rows; m->row_offset = row_offset;
+    });
+}
+
+rc_status rc_matmat(rc_ctx* c, const rc_matrix* a, const rc_matrix* x, rc_matrix** y) {
+    if (!c || !a || !x || !y) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { check_same(a, x); RC_DISPATCH(a->dtype, *y = matmat_impl<T>(c, a, x)); });
+}
+rc_status rc_conj_matmat(rc_ctx* c, const rc_matrix* a, const rc_matrix* x, rc_matrix** z) {
+    if (!c || !a || !x || !z) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { check_same(a, x); RC_DISPATCH(a->dtype, *z = conj_matmat_impl<T>(c, a, x)); });
+}
+
+rc_status rc_random_gaussian(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t cols, uint64_t seed, uint32_t stream,
+                             int64_t row_offset, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { RC_DISPATCH(dt, *out = gaussian_new<T>(c, dt, rows, cols, seed, stream, row_offset)); });
+}
+rc_status rc_random_orthogonal_matrix(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t cols, uint64_t seed, uint32_t stream, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(rows > 0 && cols > 0, "empty matrix");
+        RC_DISPATCH(dt, *out = random_orthogonal_impl<T>(c, dt, rows, cols, seed, stream));
+    });
+}
+rc_status rc_random_approximate_low_rank_matrix(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t cols, double smax, double smin,
+                                                uint64_t seed, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(smin < smax, "`sigma_min` must be smaller than `sigma_max`");     // src/random_matrix.rs:78-82
+        RC_REQUIRE(smin > 0.0, "`sigma_min` must be positive.");
+        RC_REQUIRE(rows > 0 && cols > 0, "empty matrix");
+        const int64_t md = std::min(rows, cols);
+        std::vector<double> sig((size_t)md);
+        for (int64_t i = 0; i < md; ++i)      // geomspace(sigma_min, sigma_max): ascending (quirk Q4)
+            sig[i] = (md == 1) ? smin : smin * std::pow(smax / smin, (double)i / (double)(md - 1));
+        RC_DISPATCH(dt, {
+            MatPtr u(random_orthogonal_impl<T>(c, dt, rows, md, seed, 101));
+            MatPtr vt(random_orthogonal_impl<T>(c, dt, md, cols, seed, 102));
+            *out = low_rank_from_factors<T>(c, u.get(), sig, vt.get());
+        });
+    });
+}
+rc_status rc_decaying_spectrum_matrix(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t cols, int64_t r0, double decade_every,
+                                      uint64_t seed, int64_t row_offset, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(rows > 0 && cols > 0 && r0 > 0 && decade_every > 0, "bad arguments");
+        r0 = std::min(r0, std::min(rows, cols));
+        std::vector<double> sig((size_t)r0);
+        for (int64_t j = 0; j < r0; ++j) sig[j] = std::pow(10.0, -(double)j / decade_every);
+        RC_DISPATCH(dt, {
+            // orthonormal factors: Q of the TSQR of seeded Gaussians
+            auto ortho = [&](int64_t m, uint32_t stream, int64_t off) -> rc_matrix* {
+                MatPtr g(gaussian_new<T>(c, dt, m, r0, seed, stream, off));
+                QrParts qr;
+                pivoted_qr_impl<T>(c, g.get(), false, -1, true, qr);
+                return qr.q.release();
+            };
+            MatPtr u(ortho(rows, 201, row_offset)), v(ortho(cols, 202, 0));
+            MatPtr vt(mat_conj_transpose<T>(c, v.get()));
+            *out = low_rank_from_factors<T>(c, u.get(), sig, vt.get());
+        });
+    });
+}
+
+rc_status rc_rel_diff_fro(rc_ctx* c, const rc_matrix* a, const rc_matrix* b, double* out) {
+    if (!c || !a || !b || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { check_same(a, b); RC_DISPATCH(a->dtype, *out = rel_diff_impl<T>(c, a, b)); });
+}
+rc_status rc_rel_diff_l2(rc_ctx* c, const rc_matrix* a, const rc_matrix* b, double* out) {
+    return rc_rel_diff_fro(c, a, b, out);   // same arithmetic on a 1 x n / n x 1 matrix
+}
+rc_status rc_max_col_norm(rc_ctx* c, const rc_matrix* m, double* out) {
+    if (!c || !m || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { RC_DISPATCH(m->dtype, *out = max_col_norm_impl<T>(c, m)); });
+}
+
+// ---------------------------------------------------------------- permutations
+rc_status rc_invert_permutation_vector(const uint64_t* perm, size_t n, uint64_t* inverse) {
+    if ((!perm || !inverse) && n) return RC_INVALID_ARGUMENT;
+    for (size_t i = 0; i < n; ++i) if (perm[i] >= n) return RC_INVALID_ARGUMENT;
+    for (size_t i = 0; i < n; ++i) inverse[perm[i]] = i;     // src/permutation.rs:33-35
+    return RC_OK;
+}
+rc_status rc_apply_permutation_matrix(rc_ctx* c, const rc_matrix* m, const uint64_t* idx, size_t n, rc_perm_mode mode, rc_matrix** out) {
+    if (!c || !m || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(mode >= 0 && mode <= 3, "bad permutation mode");
+        std::vector<uint64_t> v = vec_from(idx, n);
+        RC_DISPATCH(m->dtype, *out = permute_impl<T>(c, m, v, mode));
+    });
+}
+rc_status rc_apply_permutation_vector(rc_ctx* c, const rc_matrix* v, const uint64_t* idx, size_t n, rc_vperm_mode mode, rc_matrix** out) {
+    if (!c || !v || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(v->rows == 1 || v->cols == 1, "vector permutation expects a 1 x n or n x 1 matrix");
+        RC_REQUIRE((int64_t)n == v->rows * v->cols, "The input vector and the index array must have the same length");   // :161-164
+        std::vector<uint64_t> iv = vec_from(idx, n);
+        int mm = (v->rows == 1) ? (mode == RC_VPERM_INV ? RC_PERM_COLINV : RC_PERM_COL)
+                                : (mode == RC_VPERM_INV ? RC_PERM_ROWINV : RC_PERM_ROW);
+        RC_DISPATCH(v->dtype, *out = permute_impl<T>(c, v, iv, mm));
+    });
+}
+
+// ---------------------------------------------------------------- samplers
+rc_status rc_sample_range_by_rank(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p, const rc_matrix* omega, uint64_t seed, rc_matrix** q) {
+    if (!c || !a || !q) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        if (omega) check_same(a, omega);
+        RC_DISPATCH(a->dtype, *q = sample_by_rank_impl<T>(c, a, k, p, omega, seed));
+    });
+}
+rc_status rc_sample_range_power_iteration(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p, int64_t it, const rc_matrix* omega,
+                                          uint64_t seed, rc_matrix** q) {
+    if (!c || !a || !q) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        if (omega) check_same(a, omega);
+        RC_DISPATCH(a->dtype, *q = sample_power_impl<T>(c, a, k, p, it, omega, seed));
+    });
+}
+rc_status rc_sample_range_adaptive(rc_ctx* c, const rc_matrix* a, double rel_tol, int64_t s, const rc_matrix* omega_blocks, uint64_t seed,
+                                   int64_t max_rank, rc_matrix** q, uint64_t* hist_rank, double* hist_res, size_t hist_cap, size_t* hist_len) {
+    if (!c || !a || !q) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        if (omega_blocks) check_same(a, omega_blocks);
+        std::vector<uint64_t> hr; std::vector<double> hv;
+        MatPtr res;
+        RC_DISPATCH(a->dtype, res.reset(sample_adaptive_impl<T>(c, a, rel_tol, s, omega_blocks, seed, max_rank, hr, hv)));
+        if (hist_len) *hist_len = hr.size();
+        size_t ncopy = std::min(hist_cap, hr.size());
+        if (hist_rank) for (size_t i = 0; i < ncopy; ++i) hist_rank[i] = hr[i];
+        if (hist_res) for (size_t i = 0; i < ncopy; ++i) hist_res[i] = hv[i];
+        *q = res.release();
+    });
+}
+
+// ---------------------------------------------------------------- QR / LQ
+static rc_qr* qr_from_parts(QrParts& p) {
+    rc_qr* h = new rc_qr();
+    h->q = p.q.release(); h->r = p.r.release(); h->ind = std::move(p.ind);
+    return h;
+}
+rc_status rc_qr_compute_from(rc_ctx* c, const rc_matrix* arr, rc_qr** out) {
+    if (!c || !arr || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        QrParts p;
+        RC_DISPATCH(arr->dtype, pivoted_qr_impl<T>(c, arr, false, -1, false, p));
+        *out = qr_from_parts(p);
+    });
+}
+rc_status rc_qr_compute_from_range_estimate(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, rc_qr** out) {
+    if (!c || !range || !op || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        check_same(range, op);
+        QrParts p;
+        RC_DISPATCH(op->dtype, qr_from_range_impl<T>(c, range, op, p));
+        *out = qr_from_parts(p);
+    });
+}
+rc_status rc_qr_compress_rank(rc_ctx* c, const rc_qr* qr, int64_t max_rank, rc_qr** out) {
+    if (!c || !qr || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(max_rank >= 0, "negative rank");
+        max_rank = std::min(max_rank, qr->q->cols);                              // src/qr.rs:172-174
+        std::unique_ptr<rc_qr> h(new rc_qr());
+        RC_DISPATCH(qr->q->dtype, {
+            MatPtr q(mat_slice<T>(c, qr->q, 0, qr->q->rows, 0, max_rank));
+            MatPtr r(mat_slice<T>(c, qr->r, 0, max_rank, 0, qr->r->cols));
+            h->q = q.release(); h->r = r.release();
+        });
+        h->ind = qr->ind;                                                        // full length (quirk Q8)
+        *out = h.release();
+    });
+}
+static int64_t first_below(rc_ctx* c, const rc_matrix* tri, double tol) {
+    // first i with |d_ii / d_00| < tol, ratio formed in the scalar type, compared in f64 (src/qr.rs:190-194)
+    int64_t nd = std::min(tri->rows, tri->cols);
+    const size_t es = rc_dtype_size(tri->dtype);
+    std::vector<char> diag((size_t)nd * es);
+    RC_CUDA(cudaMemcpy2DAsync(diag.data(), es, tri->data, (tri->ld + 1) * es, es, nd, cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    auto ratio = [&](int64_t i) -> double {
+        switch (tri->dtype) {
+            case RC_F32: { const float* d = (const float*)diag.data(); return (double)std::fabs(d[i] / d[0]); }
+            case RC_F64: { const double* d = (const double*)diag.data(); return std::fabs(d[i] / d[0]); }
+            case RC_C32: { const c32* d = (const c32*)diag.data(); c32 q = d[i] / d[0]; return (double)std::hypot(q.re, q.im); }
+            default: { const c64* d = (const c64*)diag.data(); c64 q = d[i] / d[0]; return std::hypot(q.re, q.im); }
+        }
+    };
+    for (int64_t i = 0; i < nd; ++i) if (ratio(i) < tol) return i;
+    return -1;
+}
+rc_status rc_qr_compress_tolerance(rc_ctx* c, const rc_qr* qr, double tol, rc_qr** out) {
+    if (!c || !qr || !out) return RC_INVALID_ARGUMENT;
+    int64_t pos = -1;
+    rc_status st = guard(c, [&] {
+        RC_REQUIRE((tol < 1.0) && (0.0 <= tol), "Require 0 <= tol < 1.0");      // src/qr.rs:188
+        pos = first_below(c, qr->r, tol);
+        if (pos < 0) RC_THROW(RC_COMPRESSION_ERROR, "Could not compress to desired tolerance");   // quirk Q3
+    });
+    if (st != RC_OK) return st;
+    return rc_qr_compress_rank(c, qr, pos, out);
+}
+rc_status rc_qr_to_mat(rc_ctx* c, const rc_qr* qr, rc_matrix** out) {
+    if (!c || !qr || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_DISPATCH(qr->q->dtype, {
+            MatPtr rp(permute_impl<T>(c, qr->r, qr->ind, RC_PERM_COLINV));       // src/qr.rs:160-166
+            *out = mat_mul<T>(c, RC_OP_N, qr->q, RC_OP_N, rp.get());
+            inherit_shard(*out, qr->q);
+        });
+    });
+}
+rc_status rc_qr_column_id(rc_ctx* c, const rc_qr* qr, rc_column_id** out) {
+    if (!c || !qr || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        std::unique_ptr<rc_column_id> h(new rc_column_id());
+        RC_DISPATCH(qr->q->dtype, column_id_impl<T>(c, qr->q, qr->r, qr->ind, h.get()));
+        *out = h.release();
+    });
+}
+const rc_matrix* rc_qr_get_q(const rc_qr* qr) { return qr ? qr->q : nullptr; }
+const rc_matrix* rc_qr_get_r(const rc_qr* qr) { return qr ? qr->r : nullptr; }
+int64_t rc_qr_rank(const rc_qr* qr) { return qr ? qr->q->cols : -1; }
+int64_t rc_qr_nrows(const rc_qr* qr) { return qr ? qr->q->rows : -1; }
+int64_t rc_qr_ncols(const rc_qr* qr) { return qr ? qr->r->cols : -1; }
+rc_status rc_qr_get_ind(const rc_qr* qr, uint64_t* out, size_t n) {
+    if (!qr) return RC_INVALID_ARGUMENT;
+    return guard(qr->q->ctx, [&] { copy_ind(qr->ind, out, n); });
+}
+rc_status rc_qr_free(rc_qr* qr) {
+    if (qr) { mat_free(qr->q); mat_free(qr->r); delete qr; }
+    return RC_OK;
+}
+
+rc_status rc_lq_compute_from(rc_ctx* c, const rc_matrix* arr, rc_lq** out) {
+    if (!c || !arr || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        // pivoted QR of arr^H, transposed back (src/qr.rs:354-362)
+        QrParts p;
+        std::unique_ptr<rc_lq> h(new rc_lq());
+        RC_DISPATCH(arr->dtype, {
+            pivoted_qr_impl<T>(c, arr, true, -1, false, p);
+            MatPtr l(mat_conj_transpose<T>(c, p.r.get()));
+            MatPtr q(mat_conj_transpose<T>(c, p.q.get()));
+            h->l = l.release(); h->q = q.release();
+        });
+        h->ind = std::move(p.ind);
+        *out = h.release();
+    });
+}
+rc_status rc_lq_compress_rank(rc_ctx* c, const rc_lq* lq, int64_t max_rank, rc_lq** out) {
+    if (!c || !lq || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(max_rank >= 0, "negative rank");
+        max_rank = std::min(max_rank, lq->q->rows);                              // src/qr.rs:84-86
+        std::unique_ptr<rc_lq> h(new rc_lq());
+        RC_DISPATCH(lq->q->dtype, {
+            MatPtr q(mat_slice<T>(c, lq->q, 0, max_rank, 0, lq->q->cols));
+            MatPtr l(mat_slice<T>(c, lq->l, 0, lq->l->rows, 0, max_rank));
+            h->q = q.release(); h->l = l.release();
+        });
+        h->ind = lq->ind;
+        *out = h.release();
+    });
+}
+rc_status rc_lq_compress_tolerance(rc_ctx* c, const rc_lq* lq, double tol, rc_lq** out) {
+    if (!c || !lq || !out) return RC_INVALID_ARGUMENT;
+    int64_t pos = -1;
+    rc_status st = guard(c, [&] {
+        RC_REQUIRE((tol < 1.0) && (0.0 <= tol), "Require 0 <= tol < 1.0");      // src/qr.rs:99
+        pos = first_below(c, lq->l, tol);
+        if (pos < 0) RC_THROW(RC_COMPRESSION_ERROR, "Could not compress to desired tolerance");
+    });
+    if (st != RC_OK) return st;
+    return rc_lq_compress_rank(c, lq, pos, out);
+}
+rc_status rc_lq_to_mat(rc_ctx* c, const rc_lq* lq, rc_matrix** out) {
+    if (!c || !lq || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_DISPATCH(lq->q->dtype, {
+            MatPtr lp(permute_impl<T>(c, lq->l, lq->ind, RC_PERM_ROWINV));       // src/qr.rs:73-78
+            *out = mat_mul<T>(c, RC_OP_N, lp.get(), RC_OP_N, lq->q);
+        });
+    });
+}
+rc_status rc_lq_row_id(rc_ctx* c, const rc_lq* lq, rc_row_id** out) {
+    if (!c || !lq || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        std::unique_ptr<rc_row_id> h(new rc_row_id());
+        RC_DISPATCH(lq->q->dtype, row_id_impl<T>(c, lq->l, lq->q, lq->ind, h.get()));
+        *out = h.release();
+    });
+}
+const rc_matrix* rc_lq_get_l(const rc_lq* lq) { return lq ? lq->l : nullptr; }
+const rc_matrix* rc_lq_get_q(const rc_lq* lq) { return lq ? lq->q : nullptr; }
+int64_t rc_lq_rank(const rc_lq* lq) { return lq ? lq->q->rows : -1; }
+int64_t rc_lq_nrows(const rc_lq* lq) { return lq ? lq->l->rows : -1; }
+int64_t rc_lq_ncols(const rc_lq* lq) { return lq ? lq->q->cols : -1; }
+rc_status rc_lq_get_ind(const rc_lq* lq, uint64_t* out, size_t n) {
+    if (!lq) return RC_INVALID_ARGUMENT;
+    return guard(lq->q->ctx, [&] { copy_ind(lq->ind, out, n); });
+}
+rc_status rc_lq_free(rc_lq* lq) {
+    if (lq) { mat_free(lq->l); mat_free(lq->q); delete lq; }
+    return RC_OK;
+}
+
+// ---------------------------------------------------------------- SVD
+static rc_svd* svd_from_parts(SvdParts& p) {
+    rc_svd* h = new rc_svd();
+    h->u = p.u.release(); h->vt = p.vt.release(); h->s = std::move(p.s);
+    return h;
+}
+rc_status rc_svd_compute_from(rc_ctx* c, const rc_matrix* arr, rc_svd** out) {
+    if (!c || !arr || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        SvdParts p;
+        RC_DISPATCH(arr->dtype, svd_impl<T>(c, arr, false, p));
+        *out = svd_from_parts(p);
+    });
+}
+rc_status rc_svd_compute_from_range_estimate(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, rc_svd** out) {
+    if (!c || !range || !op || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        check_same(range, op);
+        SvdParts p;
+        RC_DISPATCH(op->dtype, svd_from_range_impl<T>(c, range, op, p));
+        *out = svd_from_parts(p);
+    });
+}
+rc_status rc_svd_compress_rank(rc_ctx* c, const rc_svd* svd, int64_t max_rank, rc_svd** out) {
+    if (!c || !svd || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(max_rank >= 0, "negative rank");
+        max_rank = std::min<int64_t>(max_rank, (int64_t)svd->s.size());          // src/svd.rs:71-73
+        std::unique_ptr<rc_svd> h(new rc_svd());
+        RC_DISPATCH(svd->u->dtype, {
+            MatPtr u(mat_slice<T>(c, svd->u, 0, svd->u->rows, 0, max_rank));
+            MatPtr vt(mat_slice<T>(c, svd->vt, 0, max_rank, 0, svd->vt->cols));
+            h->u = u.release(); h->vt = vt.release();
+        });
+        h->s.assign(svd->s.begin(), svd->s.begin() + max_rank);
+        *out = h.release();
+    });
+}
+rc_status rc_svd_compress_tolerance(rc_ctx* c, const rc_svd* svd, double tol, rc_svd** out) {
+    if (!c || !svd || !out) return RC_INVALID_ARGUMENT;
+    int64_t pos = -1;
+    rc_status st = guard(c, [&] {
+        RC_REQUIRE((tol < 1.0) && (0.0 <= tol), "Require 0 <= tol < 1.0");      // src/svd.rs:88
+        RC_REQUIRE(!svd->s.empty(), "empty SVD");
+        const bool single = (svd->u->dtype == RC_F32 || svd->u->dtype == RC_C32);
+        for (size_t i = 0; i < svd->s.size(); ++i) {                             // src/svd.rs:92-95
+            double ratio = single ? (double)((float)svd->s[i] / (float)svd->s[0]) : svd->s[i] / svd->s[0];
+            if (ratio < tol) { pos = (int64_t)i; break; }
+        }
+        if (pos < 0) RC_THROW(RC_COMPRESSION_ERROR, "Could not compress to desired tolerance");
+    });
+    if (st != RC_OK) return st;
+    return rc_svd_compress_rank(c, svd, pos, out);
+}
+rc_status rc_svd_to_mat(rc_ctx* c, const rc_svd* svd, rc_matrix** out) {
+    if (!c || !svd || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_DISPATCH(svd->u->dtype, {
+            MatPtr sv(scaled_vt<T>(c, svd));                                     // src/svd.rs:42-54
+            *out = mat_mul<T>(c, RC_OP_N, svd->u, RC_OP_N, sv.get());
+            inherit_shard(*out, svd->u);
+        });
+    });
+}
+rc_status rc_svd_to_qr(rc_ctx* c, const rc_svd* svd, rc_qr** out) {
+    if (!c || !svd || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        QrParts p;
+        RC_DISPATCH(svd->u->dtype, {
+            MatPtr sv(scaled_vt<T>(c, svd));                                     // src/svd.rs:150-163
+            pivoted_qr_impl<T>(c, sv.get(), false, -1, true, p);
+            MatPtr q(mat_mul<T>(c, RC_OP_N, svd->u, RC_OP_N, p.q.get()));
+            inherit_shard(q.get(), svd->u);
+            p.q.reset(q.release());
+        });
+        *out = qr_from_parts(p);
+    });
+}
+const rc_matrix* rc_svd_get_u(const rc_svd* svd) { return svd ? svd->u : nullptr; }
+const rc_matrix* rc_svd_get_vt(const rc_svd* svd) { return svd ? svd->vt : nullptr; }
+int64_t rc_svd_rank(const rc_svd* svd) { return svd ? (int64_t)svd->s.size() : -1; }
+rc_status rc_svd_get_s(const rc_svd* svd, double* out, size_t n) {
+    if (!svd || (!out && n)) return RC_INVALID_ARGUMENT;
+    if (n < svd->s.size()) return RC_INVALID_ARGUMENT;
+    memcpy(out, svd->s.data(), svd->s.size() * sizeof(double));
+    return RC_OK;
+}
+rc_status rc_svd_free(rc_svd* svd) {
+    if (svd) { mat_free(svd->u); mat_free(svd->vt); delete svd; }
+    return RC_OK;
+}
+
+// ---------------------------------------------------------------- interpolative decompositions
+rc_status rc_column_id_new(rc_ctx* c, const rc_matrix* cm, const rc_matrix* z, const uint64_t* col_ind, size_t n, rc_column_id** out) {
+    if (!c || !cm || !z || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        check_same(cm, z);
+        std::unique_ptr<rc_column_id> h(new rc_column_id());
+        h->col_ind = vec_from(col_ind, n);
+        RC_DISPATCH(cm->dtype, { MatPtr a(mat_clone<T>(c, cm)); MatPtr b(mat_clone<T>(c, z)); h->c = a.release(); h->z = b.release(); });
+        *out = h.release();
+    });
+}
+const rc_matrix* rc_column_id_get_c(const rc_column_id* id) { return id ? id->c : nullptr; }
+const rc_matrix* rc_column_id_get_z(const rc_column_id* id) { return id ? id->z : nullptr; }
+rc_status rc_column_id_get_col_ind(const rc_column_id* id, uint64_t* out, size_t n) {
+    if (!id) return RC_INVALID_ARGUMENT;
+    return guard(id->c->ctx, [&] { copy_ind(id->col_ind, out, n); });
+}
+rc_status rc_column_id_to_mat(rc_ctx* c, const rc_column_id* id, rc_matrix** out) {
+    if (!c || !id || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { RC_DISPATCH(id->c->dtype, *out = mat_mul<T>(c, RC_OP_N, id->c, RC_OP_N, id->z)); });   // :64
+}
+rc_status rc_column_id_apply(rc_ctx* c, const rc_column_id* id, const rc_matrix* rhs, rc_matrix** out) {
+    if (!c || !id || !rhs || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { check_same(id->c, rhs); RC_DISPATCH(id->c->dtype, *out = chain_apply<T>(c, {id->c, id->z}, rhs)); });
+}
+rc_status rc_column_id_two_sided_id(rc_ctx* c, const rc_column_id* id, rc_two_sided_id** out) {
+    if (!c || !id || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        // LQ::compute_from(C).row_id() (src/col_interp_decomp.rs:116-125; quirk Q10: uncompressed)
+        std::unique_ptr<rc_two_sided_id> h(new rc_two_sided_id());
+        RC_DISPATCH(id->c->dtype, {
+            QrParts p;
+            pivoted_qr_impl<T>(c, id->c, true, -1, false, p);
+            MatPtr l(mat_conj_transpose<T>(c, p.r.get()));
+            MatPtr q(mat_conj_transpose<T>(c, p.q.get()));
+            rc_row_id rid;
+            row_id_impl<T>(c, l.get(), q.get(), p.ind, &rid);
+            h->c = rid.x; h->x = rid.r; h->row_ind = rid.row_ind;
+            MatPtr zc(mat_clone<T>(c, id->z));
+            h->r = zc.release();
+        });
+        h->col_ind = id->col_ind;
+        *out = h.release();
+    });
+}
+rc_status rc_column_id_free(rc_column_id* id) {
+    if (id) { mat_free(id->c); mat_free(id->z); delete id; }
+    return RC_OK;
+}
+
+rc_status rc_row_id_new(rc_ctx* c, const rc_matrix* x, const rc_matrix* r, const uint64_t* row_ind, size_t n, rc_row_id** out) {
+    if (!c || !x || !r || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        check_same(x, r);
+        std::unique_ptr<rc_row_id> h(new rc_row_id());
+        h->row_ind = vec_from(row_ind, n);
+        RC_DISPATCH(x->dtype, { MatPtr a(mat_clone<T>(c, x)); MatPtr b(mat_clone<T>(c, r)); h->x = a.release(); h->r = b.release(); });
+        *out = h.release();
+    });
+}
+const rc_matrix* rc_row_id_get_x(const rc_row_id* id) { return id ? id->x : nullptr; }
+const rc_matrix* rc_row_id_get_r(const rc_row_id* id) { return id ? id->r : nullptr; }
+rc_status rc_row_id_get_row_ind(const rc_row_id* id, uint64_t* out, size_t n) {
+    if (!id) return RC_INVALID_ARGUMENT;
+    return guard(id->x->ctx, [&] { copy_ind(id->row_ind, out, n); });
+}
+rc_status rc_row_id_to_mat(rc_ctx* c, const rc_row_id* id, rc_matrix** out) {
+    if (!c || !id || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { RC_DISPATCH(id->x->dtype, *out = mat_mul<T>(c, RC_OP_N, id->x, RC_OP_N, id->r)); });   // :66
+}
+rc_status rc_row_id_apply(rc_ctx* c, const rc_row_id* id, const rc_matrix* rhs, rc_matrix** out) {
+    if (!c || !id || !rhs || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { check_same(id->x, rhs); RC_DISPATCH(id->x->dtype, *out = chain_apply<T>(c, {id->x, id->r}, rhs)); });
+}
+rc_status rc_row_id_two_sided_id(rc_ctx* c, const rc_row_id* id, rc_two_sided_id** out) {
+    if (!c || !id || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        // QR::compute_from(R).column_id() (src/row_interp_decomp.rs:120-130)
+        std::unique_ptr<rc_two_sided_id> h(new rc_two_sided_id());
+        RC_DISPATCH(id->x->dtype, {
+            QrParts p;
+            pivoted_qr_impl<T>(c, id->r, false, -1, false, p);
+            rc_column_id cid;
+            column_id_impl<T>(c, p.q.get(), p.r.get(), p.ind, &cid);
+            h->x = cid.c; h->r = cid.z; h->col_ind = cid.col_ind;
+            MatPtr xc(mat_clone<T>(c, id->x));
+            h->c = xc.release();
+        });
+        h->row_ind = id->row_ind;
+        *out = h.release();
+    });
+}
+rc_status rc_row_id_free(rc_row_id* id) {
+    if (id) { mat_free(id->x); mat_free(id->r); delete id; }
+    return RC_OK;
+}
+
+rc_status rc_two_sided_id_new(rc_ctx* c, const rc_matrix* x, const rc_matrix* r, const rc_matrix* cm, const uint64_t* col_ind, size_t n_col,
+                              const uint64_t* row_ind, size_t n_row, rc_two_sided_id** out) {
+    if (!c || !x || !r || !cm || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        check_same(x, r); check_same(x, cm);
+        std::unique_ptr<rc_two_sided_id> h(new rc_two_sided_id());
+        h->col_ind = vec_from(col_ind, n_col);
+        h->row_ind = vec_from(row_ind, n_row);
+        RC_DISPATCH(x->dtype, {
+            MatPtr a(mat_clone<T>(c, cm)); MatPtr b(mat_clone<T>(c, x)); MatPtr d(mat_clone<T>(c, r));
+            h->c = a.release(); h->x = b.release(); h->r = d.release();
+        });
+        *out = h.release();
+    });
+}
+const rc_matrix* rc_two_sided_id_get_c(const rc_two_sided_id* id) { return id ? id->c : nullptr; }
+const rc_matrix* rc_two_sided_id_get_x(const rc_two_sided_id* id) { return id ? id->x : nullptr; }
+const rc_matrix* rc_two_sided_id_get_r(const rc_two_sided_id* id) { return id ? id->r : nullptr; }
+rc_status rc_two_sided_id_get_row_ind(const rc_two_sided_id* id, uint64_t* out, size_t n) {
+    if (!id) return RC_INVALID_ARGUMENT;
+    return guard(id->c->ctx, [&] { copy_ind(id->row_ind, out, n); });
+}
+rc_status rc_two_sided_id_get_col_ind(const rc_two_sided_id* id, uint64_t* out, size_t n) {
+    if (!id) return RC_INVALID_ARGUMENT;
+    return guard(id->c->ctx, [&] { copy_ind(id->col_ind, out, n); });
+}
+rc_status rc_two_sided_id_to_mat(rc_ctx* c, const rc_two_sided_id* id, rc_matrix** out) {
+    if (!c || !id || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_DISPATCH(id->c->dtype, {
+            MatPtr xr(mat_mul<T>(c, RC_OP_N, id->x, RC_OP_N, id->r));            // c . (x . r)  (:62-64)
+            *out = mat_mul<T>(c, RC_OP_N, id->c, RC_OP_N, xr.get());
+        });
+    });
+}
+rc_status rc_two_sided_id_apply(rc_ctx* c, const rc_two_sided_id* id, const rc_matrix* rhs, rc_matrix** out) {
+    if (!c || !id || !rhs || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { check_same(id->c, rhs); RC_DISPATCH(id->c->dtype, *out = chain_apply<T>(c, {id->c, id->x, id->r}, rhs)); });
+}
+rc_status rc_two_sided_id_free(rc_two_sided_id* id) {
+    if (id) { mat_free(id->c); mat_free(id->x); mat_free(id->r); delete id; }
+    return RC_OK;
+}
+
+}  // extern "C"

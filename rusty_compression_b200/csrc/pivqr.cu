@@ -1,0 +1,282 @@
+// Column-pivoted Householder QR: the B200 replacement for LAPACK ?geqp3 + ?orgqr/?ungqr as the
+// crate calls them (reference N1/N2: src/pivoted_qr.rs:104-111, 139-173).
+//
+// One persistent cooperative kernel runs all min(p, n) steps with ONE grid-wide sync per step:
+//   argmax of the partial column norms (first maximum wins, like ?geqp3's idamax) ->
+//   Householder reflector of the pivot column (LAPACK ?larfg) -> rank-1 update of the trailing
+//   columns (?larf), each warp owning a fixed set of columns.
+// Columns are never physically swapped; a logical position per physical column stands for
+// ?geqp3's swaps, which reproduces its pivot order including tie-breaks.  Partial norms are
+// recomputed exactly (in double) in the same pass that updates a column, instead of ?geqp3's
+// downdate-with-safeguard: the two agree wherever the pivot gap exceeds sqrt(eps) effects, and
+// the exact norm costs nothing extra here because the column is being touched anyway.
+#include <cooperative_groups.h>
+#include "rc_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int NW = NT / 32;
+
+struct Cand {
+    double val;
+    int lpos;   // logical position (tie-break: smaller wins)
+    int phys;
+};
+__device__ __forceinline__ bool better(const Cand& a, const Cand& b) {
+    // a better than b ?
+    if (a.phys < 0) return false;
+    if (b.phys < 0) return true;
+    if (a.val != b.val) return a.val > b.val;
+    return a.lpos < b.lpos;
+}
+__device__ __forceinline__ Cand warp_best(Cand c) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        Cand o;
+        o.val = __shfl_xor_sync(0xffffffffu, c.val, m);
+        o.lpos = __shfl_xor_sync(0xffffffffu, c.lpos, m);
+        o.phys = __shfl_xor_sync(0xffffffffu, c.phys, m);
+        if (better(o, c)) c = o;
+    }
+    return c;
+}
+
+template <class T>
+__device__ __forceinline__ void larfg_dev(T alpha, double xnorm2, T& tau, T& scale, T& beta) {
+    double ar = (double)rc_real(alpha), ai = (double)rc_imag(alpha);
+    if (xnorm2 == 0.0 && ai == 0.0) {
+        tau = rc_zero<T>(); scale = rc_zero<T>(); beta = alpha;
+        return;
+    }
+    double b = -copysign(sqrt(ar * ar + ai * ai + xnorm2), ar);
+    double dr = ar - b, di = ai, den = dr * dr + di * di;
+    tau = rc_make<T>((b - ar) / b, -ai / b);
+    scale = rc_make<T>(dr / den, -di / den);
+    beta = rc_make<T>(b, 0.0);
+}
+
+// W: p x n column-major (ld = ldw).  Work arrays: vn (n doubles), lpos (n ints),
+// slots: 2 * gridDim.x Cand + 2 * gridDim.x ints (displaced column).
+template <class T>
+__global__ void __launch_bounds__(NT)
+pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __restrict__ vn,
+             int* __restrict__ lpos, int* __restrict__ ind, T* __restrict__ vbuf, T* __restrict__ tau_out,
+             T* __restrict__ diag, Cand* __restrict__ slots, int* __restrict__ slots_disp) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xs = reinterpret_cast<T*>(smem_raw);     // pivot column / reflector, p entries
+    __shared__ Cand s_cand[NW];
+    __shared__ int s_disp[NW];
+    __shared__ double s_red[NW];
+    __shared__ Cand s_win;
+    __shared__ int s_windisp;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gw = blockIdx.x * NW + warp, GW = gridDim.x * NW;
+
+    // initial norms and identity logical order
+    for (int c = gw; c < n; c += GW) {
+        const T* col = W + (int64_t)c * ldw;
+        double a = 0.0;
+        for (int r = lane; r < p; r += 32) a += rc_abs2(col[r]);
+        a = rc_warp_sum(a);
+        if (lane == 0) { vn[c] = sqrt(a); lpos[c] = c; }
+    }
+    __syncthreads();
+
+    for (int i = 0; i < kk; ++i) {
+        // (a) local candidates over owned, not yet pivoted columns
+        Cand best; best.val = -1.0; best.lpos = 0x7fffffff; best.phys = -1;
+        int disp = -1;
+        for (int c = gw + lane * GW; c < n; c += 32 * GW) {
+            int lp = lpos[c];
+            if (lp >= i) {
+                Cand cnd; cnd.val = vn[c]; cnd.lpos = lp; cnd.phys = c;
+                if (better(cnd, best)) best = cnd;
+                if (lp == i) disp = c;
+            }
+        }
+        best = warp_best(best);
+        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 16));
+        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 8));
+        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 4));
+        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 2));
+        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 1));
+        if (lane == 0) { s_cand[warp] = best; s_disp[warp] = disp; }
+        __syncthreads();
+        if (tid == 0) {
+            Cand b = s_cand[0]; int d = s_disp[0];
+            for (int w2 = 1; w2 < NW; ++w2) { if (better(s_cand[w2], b)) b = s_cand[w2]; d = max(d, s_disp[w2]); }
+            slots[(i & 1) * gridDim.x + blockIdx.x] = b;
+            slots_disp[(i & 1) * gridDim.x + blockIdx.x] = d;
+        }
+        // (b) one grid-wide sync per step
+        grid.sync();
+        // (c) global winner (every CTA reduces the same slots -> same answer)
+        if (warp == 0) {
+            Cand b; b.val = -1.0; b.lpos = 0x7fffffff; b.phys = -1;
+            int d = -1;
+            for (int s = lane; s < (int)gridDim.x; s += 32) {
+                Cand o = slots[(i & 1) * gridDim.x + s];
+                if (better(o, b)) b = o;
+                d = max(d, slots_disp[(i & 1) * gridDim.x + s]);
+            }
+            b = warp_best(b);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, m));
+            if (lane == 0) { s_win = b; s_windisp = d; }
+        }
+        __syncthreads();
+        const int pv = s_win.phys;          // physical pivot column
+        const int pv_lpos = s_win.lpos;     // where it sat logically
+        const int dc = s_windisp;           // physical column sitting at logical position i
+        // (d) logical swap, done by the owners
+        if (lane == 0) {
+            if (dc >= 0 && dc != pv && (dc % GW) == gw) lpos[dc] = pv_lpos;
+            if ((pv % GW) == gw) { lpos[pv] = i; }
+        }
+        if (blockIdx.x == 0 && tid == 0) ind[i] = pv;
+        // (e) reflector from the pivot column (rows i..p-1), redundantly per CTA
+        const T* pcol = W + (int64_t)pv * ldw;
+        double a = 0.0;
+        for (int r = i + tid; r < p; r += NT) {
+            T v = pcol[r];
+            xs[r] = v;
+            if (r > i) a += rc_abs2(v);
+        }
+        a = rc_warp_sum(a);
+        if (lane == 0) s_red[warp] = a;
+        __syncthreads();
+        double xnorm2 = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; ++w2) xnorm2 += s_red[w2];
+        T tau, scale, beta;
+        larfg_dev<T>(xs[i], xnorm2, tau, scale, beta);
+        __syncthreads();
+        for (int r = i + 1 + tid; r < p; r += NT) xs[r] = xs[r] * scale;
+        __syncthreads();
+        if (blockIdx.x == 0) {
+            T* vcol = vbuf + (int64_t)i * p;
+            for (int r = tid; r < p; r += NT) vcol[r] = (r < i) ? rc_zero<T>() : (r == i ? rc_one<T>() : xs[r]);
+            if (tid == 0) { tau_out[i] = tau; diag[i] = beta; }
+        }
+        // (f) trailing update of owned columns + exact partial norms
+        const T ctau = rc_conj(tau);
+        for (int c = gw; c < n; c += GW) {
+            if (lpos[c] <= i) continue;      // warp-uniform
+            T* col = W + (int64_t)c * ldw;
+            T part = rc_zero<T>();
+            for (int r = i + 1 + lane; r < p; r += 32) part = rc_cfma(xs[r], col[r], part);
+            part = rc_warp_sum(part);
+            T ci = col[i];
+            T f = ctau * (ci + part);
+            double nrm = 0.0;
+            for (int r = i + 1 + lane; r < p; r += 32) {
+                T v = col[r] - f * xs[r];
+                col[r] = v;
+                nrm += rc_abs2(v);
+            }
+            nrm = rc_warp_sum(nrm);
+            if (lane == 0) { col[i] = ci - f; vn[c] = sqrt(nrm); }
+        }
+        __syncthreads();   // xs is rewritten next step; lpos/vn written by lane 0 are read by the warp
+    }
+    // final logical order for the never-pivoted columns (n > p)
+    for (int c = gw + lane * GW; c < n; c += 32 * GW) {
+        int lp = lpos[c];
+        if (lp >= kk) ind[lp] = c;
+    }
+}
+
+// r (kk x n row-major) from the factored column-major W, logical order `ind`.
+template <class T>
+__global__ void gather_r_kernel(const T* __restrict__ W, int64_t ldw, int kk, int n, const int* __restrict__ ind,
+                                const T* __restrict__ diag, T* __restrict__ r, int64_t ldr) {
+    int64_t total = (int64_t)kk * n;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int row = (int)(e / n), j = (int)(e - (int64_t)row * n);
+        T v;
+        if (row > j) v = rc_zero<T>();
+        else if (row == j) v = diag[row];
+        else v = W[(int64_t)ind[j] * ldw + row];
+        r[(int64_t)row * ldr + j] = v;
+    }
+}
+
+// qc (p x nc column-major) = H_0 ... H_{kk-1} I[:, :nc] ; one warp per output column.
+template <class T>
+__global__ void form_q_kernel(const T* __restrict__ vbuf, const T* __restrict__ tau, int p, int kk, int nc,
+                              T* __restrict__ qc) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= nc) return;
+    T* col = qc + (int64_t)c * p;
+    for (int r = lane; r < p; r += 32) col[r] = (r == c) ? rc_one<T>() : rc_zero<T>();
+    __syncwarp();
+    // e_c is untouched by reflectors j > c (their v has zeros above j and e_c is zero from j on)
+    int jstart = (c < kk - 1) ? c : kk - 1;
+    for (int j = jstart; j >= 0; --j) {
+        const T* v = vbuf + (int64_t)j * p;
+        T part = rc_zero<T>();
+        for (int r = j + lane; r < p; r += 32) part = rc_cfma(v[r], col[r], part);
+        part = rc_warp_sum(part);
+        T f = tau[j] * part;
+        for (int r = j + lane; r < p; r += 32) col[r] = col[r] - f * v[r];
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+template <class T>
+void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int64_t ldr, int* ind,
+                  T* vbuf, T* tau) {
+    int kk = (int)std::min(p, n);
+    RC_REQUIRE(p > 0 && n > 0, "pivoted_qr: empty matrix");
+    size_t smem = (size_t)p * sizeof(T);
+    size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
+    RC_REQUIRE(smem + 4096 <= lim, "pivoted_qr: %lld rows exceed the shared-memory column buffer", (long long)p);
+    RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pivqr_kernel<T>, NT, smem));
+    RC_REQUIRE(per_sm >= 1, "pivoted_qr: kernel does not fit on an SM");
+    int64_t max_grid = (int64_t)per_sm * c->sm_count;
+    int64_t want = (n + NW * 4 - 1) / (NW * 4);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(max_grid, c->sm_count)));
+    DevBuf<double> vn(c, (size_t)n);
+    DevBuf<int> lpos(c, (size_t)n);
+    DevBuf<T> diag(c, (size_t)kk);
+    DevBuf<Cand> slots(c, (size_t)2 * grid);
+    DevBuf<int> slots_disp(c, (size_t)2 * grid);
+    int pi = (int)p, ni = (int)n;
+    void* args[] = {&wc, &ldw, &pi, &ni, &kk, &vn.p, &lpos.p, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p};
+    RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T>, dim3(grid), dim3(NT), args, smem, c->stream));
+    RC_COUNT_LAUNCH(c);
+    int64_t total = (int64_t)kk * n;
+    int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+    gather_r_kernel<T><<<nb, 256, 0, c->stream>>>(wc, ldw, kk, ni, ind, diag.p, r, ldr);
+    RC_CHECK_LAUNCH(c);
+}
+
+template <class T>
+void pivqr_form_q(rc_ctx* c, const T* vbuf, const T* tau, int64_t p, int64_t kk, int64_t nc, T* q, int64_t ldq) {
+    if (nc == 0) return;
+    DevBuf<T> qc(c, (size_t)p * nc);
+    int warps = 4;
+    int nb = (int)((nc + warps - 1) / warps);
+    form_q_kernel<T><<<nb, warps * 32, 0, c->stream>>>(vbuf, tau, (int)p, (int)kk, (int)nc, qc.p);
+    RC_CHECK_LAUNCH(c);
+    // column-major p x nc  ==  row-major nc x p  -> transpose to row-major p x nc
+    k_transpose<T>(c, q, ldq, qc.p, p, nc, p, false);
+}
+
+#define INST(T)                                                                                         \
+    template void pivqr_factor<T>(rc_ctx*, T*, int64_t, int64_t, int64_t, T*, int64_t, int*, T*, T*);    \
+    template void pivqr_form_q<T>(rc_ctx*, const T*, const T*, int64_t, int64_t, int64_t, T*, int64_t);
+INST(float)
+INST(double)
+INST(c32)
+INST(c64)

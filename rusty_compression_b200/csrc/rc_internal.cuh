@@ -1,0 +1,209 @@
+// Internal declarations shared by the kernels and the host orchestration.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+#include "../../include/rc_api.h"
+#include "rc_scalar.cuh"
+
+struct RcError {
+    rc_status status;
+    std::string msg;
+};
+
+#define RC_THROW(st, ...)                                                     \
+    do {                                                                      \
+        char _buf[512];                                                       \
+        snprintf(_buf, sizeof(_buf), __VA_ARGS__);                            \
+        throw RcError{st, std::string(_buf)};                                 \
+    } while (0)
+
+#define RC_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            rc_status _st = (_e == cudaErrorMemoryAllocation) ? RC_OUT_OF_MEMORY : RC_CUDA_ERROR; \
+            RC_THROW(_st, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,             \
+                     cudaGetErrorString(_e));                                              \
+        }                                                                                  \
+    } while (0)
+
+#define RC_REQUIRE(cond, ...)                                    \
+    do {                                                         \
+        if (!(cond)) RC_THROW(RC_INVALID_ARGUMENT, __VA_ARGS__); \
+    } while (0)
+
+struct rc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    // options
+    int gemm_impl = 0;            // 0 auto, 1 generic only
+    int true_power_iteration = 0;
+    // counters
+    int64_t launches = 0, gemm_flops = 0, h2d_bytes = 0, d2h_bytes = 0;
+    // communicator (row-sharded multi-GPU)
+    void* comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+struct rc_matrix {
+    rc_ctx* ctx = nullptr;
+    int dtype = RC_F64;
+    int64_t rows = 0, cols = 0, ld = 0;
+    void* data = nullptr;
+    bool owns = false;
+    // row sharding: this handle holds rows [row_offset, row_offset + rows) of a
+    // global_rows x cols matrix (global_rows == 0: not sharded)
+    int64_t global_rows = 0, row_offset = 0;
+};
+
+inline size_t rc_dtype_size(int dt) {
+    static const size_t s[4] = {4, 8, 8, 16};
+    return s[dt];
+}
+inline int rc_real_dtype(int dt) { return dt & 1; }
+
+// Stream-ordered device buffer.
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    rc_ctx* c = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(rc_ctx* ctx, size_t count) { alloc(ctx, count); }
+    void alloc(rc_ctx* ctx, size_t count) {
+        release();
+        c = ctx;
+        n = count;
+        if (count) RC_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), ctx->stream));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, c->stream);
+        p = nullptr;
+    }
+    ~DevBuf() { release(); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    T* take() { T* r = p; p = nullptr; return r; }
+};
+
+#define RC_COUNT_LAUNCH(ctx) ((ctx)->launches++)
+#define RC_CHECK_LAUNCH(ctx)                  \
+    do {                                      \
+        RC_COUNT_LAUNCH(ctx);                 \
+        RC_CUDA(cudaGetLastError());          \
+    } while (0)
+
+enum RcOp { RC_OP_N = 0, RC_OP_T = 1, RC_OP_H = 2 };
+
+// ------------------------------------------------------------------ kernels_basic.cu
+template <class T> void k_fill(rc_ctx*, T* p, int64_t rows, int64_t cols, int64_t ld, T v);
+template <class T> void k_eye(rc_ctx*, T* p, int64_t rows, int64_t cols, int64_t ld);
+// dst (rows x cols, ldd) = src (rows x cols, lds)
+template <class T> void k_copy(rc_ctx*, T* dst, int64_t ldd, const T* src, int64_t lds, int64_t rows, int64_t cols);
+// dst (cols x rows) = op(src (rows x cols)), op = T or H
+template <class T> void k_transpose(rc_ctx*, T* dst, int64_t ldd, const T* src, int64_t lds, int64_t rows, int64_t cols, bool conj);
+template <class T> void k_conj_inplace(rc_ctx*, T* p, int64_t rows, int64_t cols, int64_t ld);
+// strided (element strides) -> dense row-major
+template <class T> void k_strided_to_dense(rc_ctx*, T* dst, int64_t ldd, const T* src, int64_t rs, int64_t cs, int64_t rows, int64_t cols);
+// out[:, j] = in[:, idx[j]]  (cols) ; out[i, :] = in[idx[i], :] (rows)
+template <class T> void k_gather_cols(rc_ctx*, T* dst, int64_t ldd, const T* src, int64_t lds, int64_t rows, int64_t cols, const int* idx);
+template <class T> void k_gather_rows(rc_ctx*, T* dst, int64_t ldd, const T* src, int64_t lds, int64_t rows, int64_t cols, const int* idx);
+// zero strictly-lower part of a rows x cols matrix
+template <class T> void k_triu(rc_ctx*, T* p, int64_t rows, int64_t cols, int64_t ld);
+// rows scaled by real s[i]
+template <class T> void k_scale_rows(rc_ctx*, T* p, int64_t rows, int64_t cols, int64_t ld, const RealOf<T>* s);
+// dst = a - b
+template <class T> void k_sub(rc_ctx*, T* dst, int64_t ldd, const T* a, int64_t lda, const T* b, int64_t ldb, int64_t rows, int64_t cols);
+template <class T> void k_add(rc_ctx*, T* dst, int64_t ldd, const T* a, int64_t lda, const T* b, int64_t ldb, int64_t rows, int64_t cols);
+// Philox Gaussian fill (row-major, element index = (row_offset + i) * cols + j)
+template <class T> void k_gaussian(rc_ctx*, T* p, int64_t rows, int64_t cols, int64_t ld, uint64_t seed, uint32_t stream, int64_t row_offset);
+// squared column norms (double), one per column: out[j] = sum_i |a_ij|^2
+template <class T> void k_col_norms2(rc_ctx*, const T* a, int64_t lda, int64_t rows, int64_t cols, double* out);
+// sum of |a_ij|^2 ; and sum of |a_ij - b_ij|^2 (double, device scalars)
+template <class T> void k_fro2(rc_ctx*, const T* a, int64_t lda, int64_t rows, int64_t cols, double* out);
+template <class T> void k_diff_fro2(rc_ctx*, const T* a, int64_t lda, const T* b, int64_t ldb, int64_t rows, int64_t cols, double* out);
+// complex real-expansion helpers for the DMMA path (c64 only)
+void k_expand_rhs_c64(rc_ctx*, double* dst, int64_t ldd, const c64* x, int64_t ldx, int64_t rows, int64_t cols);
+// real <-> T conversions of device vectors (singular values)
+template <class T> void k_convert_real(rc_ctx*, RealOf<T>* dst, const double* src, int64_t n);
+
+// ------------------------------------------------------------------ gemm_generic.cu / gemm_dmma.cu
+// C (M x N, ldc) = alpha * op(A) * op(B) + beta * C ; all row-major.
+template <class T>
+void gemm(rc_ctx*, RcOp opa, RcOp opb, int64_t M, int64_t N, int64_t K, const T* A, int64_t lda,
+          const T* B, int64_t ldb, T* C, int64_t ldc, T alpha, T beta);
+template <class T>
+void gemm_generic(rc_ctx*, RcOp opa, RcOp opb, int64_t M, int64_t N, int64_t K, const T* A, int64_t lda,
+                  const T* B, int64_t ldb, T* C, int64_t ldc, T alpha, T beta);
+// f64 tensor-pipe (DMMA) + TMA kernels; return false if the shape/alignment is not supported.
+bool gemm_dmma_f64(rc_ctx*, bool a_transposed, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda,
+                   const double* B, int64_t ldb, double* C, int64_t ldc);
+bool gemm_dmma_c64(rc_ctx*, bool a_conj_transposed, int64_t M, int64_t N, int64_t K, const c64* A, int64_t lda,
+                   const c64* B, int64_t ldb, c64* C, int64_t ldc);
+
+// ------------------------------------------------------------------ tsqr.cu
+// Unpivoted Householder TSQR of a tall matrix Y (m x w, row-major ld), destroying Y (it is
+// overwritten by the leaf Householder vectors).  Keeps the reflector tree so Q can be applied.
+template <class T>
+struct TsqrFactor {
+    rc_ctx* ctx = nullptr;
+    int64_t m = 0, w = 0;
+    struct Level {
+        T* v = nullptr;        // (rows x w) reflectors, row-major, ld = ldv
+        int64_t ldv = 0;
+        int64_t rows = 0;      // rows of this level's input
+        int64_t block = 0;     // rows per block
+        int64_t nblocks = 0;
+        RealOf<T>* dummy = nullptr;
+        T* tau = nullptr;      // nblocks x w
+        bool owns_v = false;
+    };
+    std::vector<Level> levels;
+    T* r = nullptr;            // final w x w upper-triangular R (row-major, ld = w)
+    ~TsqrFactor();
+};
+template <class T> void tsqr_factor(rc_ctx*, T* y, int64_t ld, int64_t m, int64_t w, TsqrFactor<T>& f);
+// out (m x nc, ldo) = Q * [ctop (w x nc, ldc) ; 0]
+template <class T> void tsqr_apply_q(rc_ctx*, const TsqrFactor<T>& f, const T* ctop, int64_t ldc, int64_t nc, T* out, int64_t ldo);
+int64_t tsqr_max_width(rc_ctx*, int dtype);
+
+// ------------------------------------------------------------------ pivqr.cu
+// Column-pivoted Householder QR (LAPACK ?geqp3 / ?laqp2 pivot rule) of a p x n matrix held
+// COLUMN-major in wc (ld = ldw >= p), in place.  Outputs: r (kk x n row-major, ldr), ind (n),
+// and the reflectors (vbuf p x kk column-major ld = p, tau kk) for forming Q.  kk = min(p, n).
+template <class T>
+void pivqr_factor(rc_ctx*, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int64_t ldr, int* ind,
+                  T* vbuf, T* tau);
+// q (p x nc row-major, ldq) = H_0 ... H_{kk-1} * I[:, :nc]
+template <class T>
+void pivqr_form_q(rc_ctx*, const T* vbuf, const T* tau, int64_t p, int64_t kk, int64_t nc, T* q, int64_t ldq);
+
+// ------------------------------------------------------------------ jacobi.cu
+// One-sided Jacobi SVD of a small rows x n matrix G (row-major, ld; rows >= n): G = U diag(s) W^H.
+// On exit u (rows x n row-major), s (n, descending, double), w (n x n row-major).
+template <class T>
+void jacobi_svd(rc_ctx*, const T* g, int64_t ldg, int64_t rows, int64_t n, T* u, int64_t ldu, double* s, T* w, int64_t ldw);
+
+// ------------------------------------------------------------------ trsm.cu
+// X (k x nrhs, ldx) = U^{-1} B (k x nrhs, ldb), U k x k upper triangular (row-major ldu);
+// if u_transposed, U[i][j] is read from u[j*ldu + i] (i.e. the stored matrix is lower).
+template <class T>
+void trsm_upper(rc_ctx*, const T* u, int64_t ldu, bool u_transposed, int64_t k, const T* b, int64_t ldb,
+                int64_t nrhs, T* x, int64_t ldx);
+
+// ------------------------------------------------------------------ comm.cu
+void comm_get_unique_id(void* out128);
+void comm_init(rc_ctx*, const void* id128, int rank, int nranks);
+void comm_destroy(rc_ctx*);
+void comm_allreduce_sum(rc_ctx*, void* buf, size_t count, int dtype);   // in place
+void comm_allreduce_max_f64(rc_ctx*, double* buf, size_t count);
+void comm_allgather(rc_ctx*, const void* send, void* recv, size_t bytes_per_rank);

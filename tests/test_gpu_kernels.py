@@ -1,0 +1,162 @@
+"""Kernel-level parity through the C ABI: every CUDA building block against numpy / the oracle."""
+import numpy as np
+import pytest
+
+from oracle import reference_path as ref
+from oracle.philox import random_gaussian as oracle_gaussian
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float32, np.float64, np.complex64, np.complex128]
+TOL = {np.float32: 2e-5, np.float64: 1e-13, np.complex64: 2e-5, np.complex128: 1e-13}
+
+
+def rnd(shape, dtype, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal(shape)
+    if np.dtype(dtype).kind == "c":
+        a = a + 1j * rng.standard_normal(shape)
+    return a.astype(dtype)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from rusty_compression_b200 import api as a
+    return a
+
+
+def relerr(x, y):
+    return np.linalg.norm(x.astype(np.complex128) - y.astype(np.complex128)) / max(np.linalg.norm(y), 1e-300)
+
+
+def test_library_loaded_and_counts_launches(api):
+    ctx = api.default_context()
+    ctx.reset_counters()
+    api.DeviceMatrix.from_numpy(np.eye(4)).matmat(np.eye(4)).to_numpy()
+    assert ctx.counter("kernel_launches") >= 1
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gaussian_matches_oracle_philox(api, dtype):
+    want = oracle_gaussian((257, 33), dtype, seed=42, stream=3, row_offset=11)
+    got = api.random_gaussian((257, 33), dtype, seed=42, stream=3, row_offset=11)
+    assert got.dtype == want.dtype
+    tol = 1e-6 if np.dtype(dtype).itemsize in (4, 8) and np.dtype(dtype).kind != "f" or dtype == np.float32 else 1e-13
+    assert np.max(np.abs(got - want)) < (1e-6 if dtype in (np.float32, np.complex64) else 1e-13)
+
+
+def test_permutation_known_answers(api):
+    """src/permutation.rs:192-239 verbatim, through the device gather kernels."""
+    mat = np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0], [7.0, 8.0, 9.0]])
+    perm = np.array([2, 0, 1])
+    assert np.array_equal(api.apply_permutation_matrix(mat, perm, "COL"), [[3, 1, 2], [6, 4, 5], [9, 7, 8]])
+    assert np.array_equal(api.apply_permutation_matrix(mat, perm, "COLINV"), [[2, 3, 1], [5, 6, 4], [8, 9, 7]])
+    assert np.array_equal(api.apply_permutation_matrix(mat, perm, "ROW"), [[7, 8, 9], [1, 2, 3], [4, 5, 6]])
+    assert np.array_equal(api.apply_permutation_matrix(mat, perm, "ROWINV"), [[4, 5, 6], [7, 8, 9], [1, 2, 3]])
+    vec = np.array([1.0, 2.0, 3.0])
+    assert np.array_equal(api.apply_permutation_vector(vec, perm, "NOINV"), [3, 1, 2])
+    assert np.array_equal(api.apply_permutation_vector(vec, perm, "INV"), [2, 3, 1])
+    assert np.array_equal(api.invert_permutation_vector(perm), [1, 2, 0])
+    with pytest.raises(AssertionError):
+        api.apply_permutation_matrix(mat, np.array([0, 1]), "COL")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(300, 130, 17), (64, 64, 64), (1000, 257, 5), (33, 2100, 9)])
+def test_matmat_and_conj_matmat(api, dtype, shape):
+    m, n, l = shape
+    a = rnd((m, n), dtype, 1)
+    x = rnd((n, l), dtype, 2)
+    y = rnd((m, l), dtype, 3)
+    op = api.DeviceMatrix.from_numpy(a)
+    assert relerr(op.matmat(x).to_numpy(), a.dot(x)) < TOL[dtype] * 10
+    assert relerr(op.conj_matmat(y).to_numpy(), np.conj(a.T).dot(y)) < TOL[dtype] * 10
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("shape", [(4096, 1024, 74), (1000, 514, 10), (777, 1030, 138), (2048, 512, 96), (130, 4096, 20)])
+def test_dmma_tma_gemm_matches_generic_and_numpy(api, dtype, shape):
+    """The TMA + DMMA tensor-pipe kernels (gemm_dmma.cu) against numpy and the SIMT kernel."""
+    m, n, l = shape
+    a = rnd((m, n), dtype, 4)
+    x = rnd((n, l), dtype, 5)
+    y = rnd((m, l), dtype, 6)
+    ctx = api.default_context()
+    op = api.DeviceMatrix.from_numpy(a)
+    ctx.set_option("gemm_impl", 0)
+    y_fast = op.matmat(x).to_numpy()
+    z_fast = op.conj_matmat(y).to_numpy()
+    ctx.set_option("gemm_impl", 1)
+    y_gen = op.matmat(x).to_numpy()
+    z_gen = op.conj_matmat(y).to_numpy()
+    ctx.set_option("gemm_impl", 0)
+    assert relerr(y_fast, a.dot(x)) < 1e-13 and relerr(y_gen, a.dot(x)) < 1e-13
+    assert relerr(z_fast, np.conj(a.T).dot(y)) < 1e-13 and relerr(z_gen, np.conj(a.T).dot(y)) < 1e-13
+
+
+def test_strided_views_upload(api):
+    a = rnd((40, 30), np.float64, 7)
+    assert np.array_equal(api.DeviceMatrix.from_numpy(a.T).to_numpy(), a.T)
+    assert np.array_equal(api.DeviceMatrix.from_numpy(a[::2, ::3]).to_numpy(), a[::2, ::3])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_norms_and_rel_diff(api, dtype):
+    a = rnd((500, 37), dtype, 8)
+    b = a + 1e-3 * rnd((500, 37), dtype, 9)
+    assert abs(api.rel_diff_fro(a, b) - ref.rel_diff_fro(a, b)) < 1e-6 * ref.rel_diff_fro(a, b) + 1e-12
+    assert abs(api.max_col_norm(a) - ref.max_col_norm(a)) < 1e-5 * ref.max_col_norm(a)
+    assert abs(api.rel_diff_l2(a[:, 0], b[:, 0]) - ref.rel_diff_l2(a[:, 0], b[:, 0])) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2000, 40), (300, 74), (5000, 7), (64, 64), (150, 100)])
+def test_tall_pivoted_qr_matches_lapack(api, dtype, shape):
+    """TSQR + pivot-on-R against ?geqp3/?orgqr: same pivots, |R| equal, Q equal up to phases."""
+    a = ref.random_approximate_low_rank_matrix(shape, 1.0, 1e-4, dtype, seed=5)
+    q, r, ind = api.pivoted_qr(a)
+    q0, r0, ind0 = ref.pivoted_qr(a)
+    tol = 2e-4 if dtype in (np.float32, np.complex64) else 1e-9
+    k = min(shape)
+    assert np.max(np.abs(np.conj(q.T).dot(q) - np.eye(k))) < (1e-5 if tol > 1e-6 else 1e-13)
+    assert relerr(q.dot(r), a[:, ind]) < (1e-5 if tol > 1e-6 else 1e-13)
+    gaps = ref.pivot_gaps(a, ind0)
+    first_bad = next((j for j in range(k) if ind[j] != ind0[j]), None)
+    if first_bad is not None:
+        assert gaps[first_bad] <= (1e-3 if tol > 1e-6 else 1e-6), (first_bad, gaps[first_bad])
+    else:
+        assert np.max(np.abs(np.abs(np.diagonal(r)) - np.abs(np.diagonal(r0))) / np.abs(r0[0, 0])) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(20, 700), (64, 3000), (50, 100)])
+def test_wide_pivoted_qr_matches_lapack(api, dtype, shape):
+    """Cooperative pivoted Householder kernel (short-wide k x n factor) against ?geqp3."""
+    a = ref.random_approximate_low_rank_matrix(shape, 1.0, 1e-3, dtype, seed=6)
+    q, r, ind = api.pivoted_qr(a)
+    q0, r0, ind0 = ref.pivoted_qr(a)
+    single = dtype in (np.float32, np.complex64)
+    k = min(shape)
+    assert sorted(ind.tolist()) == list(range(shape[1]))
+    assert np.max(np.abs(np.conj(q.T).dot(q) - np.eye(k))) < (1e-5 if single else 1e-13)
+    assert relerr(q.dot(r), a[:, ind]) < (1e-5 if single else 1e-13)
+    gaps = ref.pivot_gaps(a, ind0)
+    first_bad = next((j for j in range(k) if ind[j] != ind0[j]), None)
+    if first_bad is not None:
+        assert gaps[first_bad] <= (1e-3 if single else 1e-6), (first_bad, gaps[first_bad])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(64, 2000), (300, 40), (50, 50), (33, 7)])
+def test_svd_matches_gesdd(api, dtype, shape):
+    a = ref.random_approximate_low_rank_matrix(shape, 1.0, 1e-5, dtype, seed=7)
+    u, s, vt = api.compute_svd(a)
+    u0, s0, vt0 = ref.compute_svd(a)
+    single = dtype in (np.float32, np.complex64)
+    k = min(shape)
+    assert u.shape == u0.shape and vt.shape == vt0.shape and s.shape == s0.shape
+    assert np.all(np.diff(s) <= 0)
+    assert np.max(np.abs(s - s0)) / s0[0] < (1e-5 if single else 1e-13)
+    assert relerr((u * s).dot(vt), a) < (2e-5 if single else 1e-12)
+    assert np.max(np.abs(np.conj(u.T).dot(u) - np.eye(k))) < (2e-4 if single else 1e-10)
+    assert np.max(np.abs(vt.dot(np.conj(vt.T)) - np.eye(k))) < (2e-4 if single else 1e-10)
