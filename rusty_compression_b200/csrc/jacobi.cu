@@ -13,13 +13,20 @@ namespace {
 constexpr int JT = 1024;
 constexpr int JW = JT / 32;
 
-template <class T>
+template <class T, bool SMEM>
 __global__ void __launch_bounds__(JT)
-jacobi_kernel(T* __restrict__ G, T* __restrict__ V, int rows, int n, int max_sweeps, double tol,
+jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int max_sweeps, double tol,
               T* __restrict__ u, int64_t ldu, double* __restrict__ s_out, T* __restrict__ w, int64_t ldw,
               double* __restrict__ sig_scratch, int* __restrict__ info) {
     __shared__ int s_rot;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // SMEM: G (rows x n) and V (n x n) are resident in shared memory for the whole iteration
+    T* G = SMEM ? reinterpret_cast<T*>(smem_raw) : Gg;
+    T* V = SMEM ? G + (size_t)rows * n : Vg;
+    if (SMEM) {
+        for (int e = tid; e < rows * n; e += JT) G[e] = Gg[e];
+    }
     const int npad = n + (n & 1);
     const int half = npad / 2;
     // V = I
@@ -124,7 +131,14 @@ void jacobi_svd(rc_ctx* c, const T* g, int64_t ldg, int64_t rows, int64_t n, T* 
     k_transpose<T>(c, G.p, rows, g, ldg, rows, n, false);
     double eps = (sizeof(RealOf<T>) == 4) ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
     double tol = eps * sqrt((double)rows);
-    jacobi_kernel<T><<<1, JT, 0, c->stream>>>(G.p, V.p, (int)rows, (int)n, 60, tol, u, ldu, s, w, ldw, sig.p, info.p);
+    size_t smem = ((size_t)rows * n + (size_t)n * n) * sizeof(T);
+    size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
+    if (smem + 4096 <= lim) {
+        RC_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        jacobi_kernel<T, true><<<1, JT, smem, c->stream>>>(G.p, V.p, (int)rows, (int)n, 60, tol, u, ldu, s, w, ldw, sig.p, info.p);
+    } else {
+        jacobi_kernel<T, false><<<1, JT, 0, c->stream>>>(G.p, V.p, (int)rows, (int)n, 60, tol, u, ldu, s, w, ldw, sig.p, info.p);
+    }
     RC_CHECK_LAUNCH(c);
 }
 

@@ -17,8 +17,8 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int NT = 256;
-constexpr int NW = NT / 32;
+// NT threads per CTA: 256 for the multi-CTA (wide) case, 1024 when one CTA holds the whole
+// matrix in shared memory (small factors such as the w x w R of a sketch).
 
 struct Cand {
     double val;
@@ -60,19 +60,31 @@ __device__ __forceinline__ void larfg_dev(T alpha, double xnorm2, T& tau, T& sca
 
 // W: p x n column-major (ld = ldw).  Work arrays: vn (n doubles), lpos (n ints),
 // slots: 2 * gridDim.x Cand + 2 * gridDim.x ints (displaced column).
-template <class T>
+template <class T, int NT, bool SMEM>
 __global__ void __launch_bounds__(NT)
-pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __restrict__ vn,
-             int* __restrict__ lpos, int* __restrict__ ind, T* __restrict__ vbuf, T* __restrict__ tau_out,
+pivqr_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, double* __restrict__ vn_g,
+             int* __restrict__ lpos_g, int* __restrict__ ind, T* __restrict__ vbuf, T* __restrict__ tau_out,
              T* __restrict__ diag, Cand* __restrict__ slots, int* __restrict__ slots_disp) {
+    constexpr int NW = NT / 32;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* xs = reinterpret_cast<T*>(smem_raw);     // pivot column / reflector, p entries
+    // SMEM: the whole (column-major) matrix lives in shared memory; single CTA, no grid sync
+    T* W = SMEM ? xs + p : Wg;
+    const int64_t ldw = SMEM ? p : ldwg;
+    // SMEM: the norm / logical-position tables live in shared memory too (no global round trips)
+    double* vn = SMEM ? reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(W + (size_t)p * n) + 7) & ~(uintptr_t)7) : vn_g;
+    int* lpos = SMEM ? reinterpret_cast<int*>(vn + n) : lpos_g;
+    if (SMEM) {
+        for (int e = threadIdx.x; e < p * n; e += NT) { int c = e / p, r = e - c * p; W[e] = Wg[(int64_t)c * ldwg + r]; }
+        __syncthreads();
+    }
     __shared__ Cand s_cand[NW];
     __shared__ int s_disp[NW];
     __shared__ double s_red[NW];
     __shared__ Cand s_win;
     __shared__ int s_windisp;
+    __shared__ T s_hs[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * NW + warp, GW = gridDim.x * NW;
@@ -107,22 +119,28 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
         disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 1));
         if (lane == 0) { s_cand[warp] = best; s_disp[warp] = disp; }
         __syncthreads();
-        if (tid == 0) {
-            Cand b = s_cand[0]; int d = s_disp[0];
-            for (int w2 = 1; w2 < NW; ++w2) { if (better(s_cand[w2], b)) b = s_cand[w2]; d = max(d, s_disp[w2]); }
-            slots[(i & 1) * gridDim.x + blockIdx.x] = b;
-            slots_disp[(i & 1) * gridDim.x + blockIdx.x] = d;
+        if (!SMEM) {
+            if (tid == 0) {
+                Cand b = s_cand[0]; int d = s_disp[0];
+                for (int w2 = 1; w2 < NW; ++w2) { if (better(s_cand[w2], b)) b = s_cand[w2]; d = max(d, s_disp[w2]); }
+                slots[(i & 1) * gridDim.x + blockIdx.x] = b;
+                slots_disp[(i & 1) * gridDim.x + blockIdx.x] = d;
+            }
+            // (b) one grid-wide sync per step
+            grid.sync();
         }
-        // (b) one grid-wide sync per step
-        grid.sync();
         // (c) global winner (every CTA reduces the same slots -> same answer)
         if (warp == 0) {
             Cand b; b.val = -1.0; b.lpos = 0x7fffffff; b.phys = -1;
             int d = -1;
-            for (int s = lane; s < (int)gridDim.x; s += 32) {
-                Cand o = slots[(i & 1) * gridDim.x + s];
-                if (better(o, b)) b = o;
-                d = max(d, slots_disp[(i & 1) * gridDim.x + s]);
+            if (SMEM) {
+                if (lane < NW) { b = s_cand[lane]; d = s_disp[lane]; }
+            } else {
+                for (int s = lane; s < (int)gridDim.x; s += 32) {
+                    Cand o = slots[(i & 1) * gridDim.x + s];
+                    if (better(o, b)) b = o;
+                    d = max(d, slots_disp[(i & 1) * gridDim.x + s]);
+                }
             }
             b = warp_best(b);
 #pragma unroll
@@ -150,12 +168,13 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
         a = rc_warp_sum(a);
         if (lane == 0) s_red[warp] = a;
         __syncthreads();
-        double xnorm2 = 0.0;
-#pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) xnorm2 += s_red[w2];
-        T tau, scale, beta;
-        larfg_dev<T>(xs[i], xnorm2, tau, scale, beta);
+        if (tid == 0) {      // one thread derives the reflector scalars (FP64 sqrt/div are long sequences)
+            double xnorm2 = 0.0;
+            for (int w2 = 0; w2 < NW; ++w2) xnorm2 += s_red[w2];
+            larfg_dev<T>(xs[i], xnorm2, s_hs[0], s_hs[1], s_hs[2]);
+        }
         __syncthreads();
+        const T tau = s_hs[0], scale = s_hs[1], beta = s_hs[2];
         for (int r = i + 1 + tid; r < p; r += NT) xs[r] = xs[r] * scale;
         __syncthreads();
         if (blockIdx.x == 0) {
@@ -168,11 +187,12 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
         for (int c = gw; c < n; c += GW) {
             if (lpos[c] <= i) continue;      // warp-uniform
             T* col = W + (int64_t)c * ldw;
-            T part = rc_zero<T>();
-            for (int r = i + 1 + lane; r < p; r += 32) part = rc_cfma(xs[r], col[r], part);
+            using A = typename AccOf<T>::type;
+            A part = rc_zero<A>();
+            for (int r = i + 1 + lane; r < p; r += 32) part = rc_cfma(rc_widen(xs[r]), rc_widen(col[r]), part);
             part = rc_warp_sum(part);
             T ci = col[i];
-            T f = ctau * (ci + part);
+            T f = ctau * rc_narrow<T>(rc_widen(ci) + part);
             double nrm = 0.0;
             for (int r = i + 1 + lane; r < p; r += 32) {
                 T v = col[r] - f * xs[r];
@@ -188,6 +208,10 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
     for (int c = gw + lane * GW; c < n; c += 32 * GW) {
         int lp = lpos[c];
         if (lp >= kk) ind[lp] = c;
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < p * n; e += NT) { int c = e / p, r = e - c * p; Wg[(int64_t)c * ldwg + r] = W[e]; }
     }
 }
 
@@ -220,10 +244,11 @@ __global__ void form_q_kernel(const T* __restrict__ vbuf, const T* __restrict__ 
     int jstart = (c < kk - 1) ? c : kk - 1;
     for (int j = jstart; j >= 0; --j) {
         const T* v = vbuf + (int64_t)j * p;
-        T part = rc_zero<T>();
-        for (int r = j + lane; r < p; r += 32) part = rc_cfma(v[r], col[r], part);
+        using A = typename AccOf<T>::type;
+        A part = rc_zero<A>();
+        for (int r = j + lane; r < p; r += 32) part = rc_cfma(rc_widen(v[r]), rc_widen(col[r]), part);
         part = rc_warp_sum(part);
-        T f = tau[j] * part;
+        T f = tau[j] * rc_narrow<T>(part);
         for (int r = j + lane; r < p; r += 32) col[r] = col[r] - f * v[r];
         __syncwarp();
     }
@@ -236,25 +261,44 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
                   T* vbuf, T* tau) {
     int kk = (int)std::min(p, n);
     RC_REQUIRE(p > 0 && n > 0, "pivoted_qr: empty matrix");
-    size_t smem = (size_t)p * sizeof(T);
     size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
-    RC_REQUIRE(smem + 4096 <= lim, "pivoted_qr: %lld rows exceed the shared-memory column buffer", (long long)p);
-    RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pivqr_kernel<T>, NT, smem));
-    RC_REQUIRE(per_sm >= 1, "pivoted_qr: kernel does not fit on an SM");
-    int64_t max_grid = (int64_t)per_sm * c->sm_count;
-    int64_t want = (n + NW * 4 - 1) / (NW * 4);
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(max_grid, c->sm_count)));
     DevBuf<double> vn(c, (size_t)n);
     DevBuf<int> lpos(c, (size_t)n);
     DevBuf<T> diag(c, (size_t)kk);
-    DevBuf<Cand> slots(c, (size_t)2 * grid);
-    DevBuf<int> slots_disp(c, (size_t)2 * grid);
     int pi = (int)p, ni = (int)n;
-    void* args[] = {&wc, &ldw, &pi, &ni, &kk, &vn.p, &lpos.p, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p};
-    RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T>, dim3(grid), dim3(NT), args, smem, c->stream));
-    RC_COUNT_LAUNCH(c);
+    size_t smem_all = ((size_t)p + (size_t)p * n + 1) * sizeof(T) + (size_t)n * (sizeof(double) + sizeof(int)) + 16;
+    if (smem_all + 8192 <= lim && n <= 2048) {
+        // small factor: one CTA, matrix resident in shared memory; fewer warps when there are few
+        // columns (block barriers are the critical path of the 74-step chain)
+        DevBuf<Cand> slots(c, 2);
+        DevBuf<int> slots_disp(c, 2);
+        void* args[] = {&wc, &ldw, &pi, &ni, &kk, &vn.p, &lpos.p, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p};
+        if (n <= 0) {   // (256 threads measured slower than 1024 even for 74 columns)
+            RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
+            RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T, 256, true>, dim3(1), dim3(256), args, smem_all, c->stream));
+        } else {
+            RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
+            RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T, 1024, true>, dim3(1), dim3(1024), args, smem_all, c->stream));
+        }
+        RC_COUNT_LAUNCH(c);
+    } else {
+        constexpr int NT = 256;
+        constexpr int NW = NT / 32;
+        size_t smem = (size_t)p * sizeof(T);
+        RC_REQUIRE(smem + 4096 <= lim, "pivoted_qr: %lld rows exceed the shared-memory column buffer", (long long)p);
+        RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pivqr_kernel<T, NT, false>, NT, smem));
+        RC_REQUIRE(per_sm >= 1, "pivoted_qr: kernel does not fit on an SM");
+        int64_t max_grid = (int64_t)per_sm * c->sm_count;
+        int64_t want = (n + NW * 4 - 1) / (NW * 4);
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(max_grid, c->sm_count)));
+        DevBuf<Cand> slots(c, (size_t)2 * grid);
+        DevBuf<int> slots_disp(c, (size_t)2 * grid);
+        void* args[] = {&wc, &ldw, &pi, &ni, &kk, &vn.p, &lpos.p, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p};
+        RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T, NT, false>, dim3(grid), dim3(NT), args, smem, c->stream));
+        RC_COUNT_LAUNCH(c);
+    }
     int64_t total = (int64_t)kk * n;
     int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
     gather_r_kernel<T><<<nb, 256, 0, c->stream>>>(wc, ldw, kk, ni, ind, diag.p, r, ldr);

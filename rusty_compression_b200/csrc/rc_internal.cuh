@@ -163,9 +163,10 @@ struct TsqrFactor {
         int64_t rows = 0;      // rows of this level's input
         int64_t block = 0;     // rows per block
         int64_t nblocks = 0;
-        RealOf<T>* dummy = nullptr;
         T* tau = nullptr;      // nblocks x w
+        T* tpan = nullptr;     // nblocks x npanels x (8 x 8) compact-WY T factors
         bool owns_v = false;
+        bool tri = false;      // input is a stack of upper triangles (tree levels)
     };
     std::vector<Level> levels;
     T* r = nullptr;            // final w x w upper-triangular R (row-major, ld = w)

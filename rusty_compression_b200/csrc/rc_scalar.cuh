@@ -103,6 +103,17 @@ template <class R> RC_HD Cx<R> rc_cfma(Cx<R> a, Cx<R> b, Cx<R> c) {
     return Cx<R>(c.re + a.re * b.re + a.im * b.im, c.im + a.re * b.im - a.im * b.re);
 }
 
+// Accumulation type for inner products: single-precision data is accumulated in double so that
+// the Householder dots do not lose digits to the summation length.
+template <class T> struct AccOf { using type = T; };
+template <> struct AccOf<float> { using type = double; };
+template <> struct AccOf<c32> { using type = c64; };
+RC_HD double rc_widen(float a) { return (double)a; }
+RC_HD double rc_widen(double a) { return a; }
+RC_HD c64 rc_widen(c32 a) { return c64((double)a.re, (double)a.im); }
+RC_HD c64 rc_widen(c64 a) { return a; }
+template <class T> RC_HD T rc_narrow(typename AccOf<T>::type a) { return rc_make<T>((double)rc_real(a), (double)rc_imag(a)); }
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float  rc_shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ double rc_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
