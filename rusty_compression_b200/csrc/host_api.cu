@@ -657,6 +657,7 @@ rc_status rc_ctx_destroy(rc_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     try { comm_destroy(c); } catch (...) {}
+    if (c->tile_counter) cudaFree(c->tile_counter);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return RC_OK;

@@ -49,6 +49,7 @@ struct rc_ctx {
     int true_power_iteration = 0;
     // counters
     int64_t launches = 0, gemm_flops = 0, h2d_bytes = 0, d2h_bytes = 0;
+    int* tile_counter = nullptr;   // device scratch for the dynamic GEMM tile scheduler
     // communicator (row-sharded multi-GPU)
     void* comm = nullptr;
     int rank = 0, nranks = 1;

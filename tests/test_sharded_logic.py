@@ -1,0 +1,102 @@
+"""World-size-2 gloo test (CPU) of the row-sharded algorithm the C++ host code implements
+(csrc/host_api.cu: DistTsqr, conj_matmat_impl): local sketch, TSQR with an all-gather of the R
+factors, pivoting on the combined R, all-reduce of the A^H Q partials.  Each rank holds a row
+block of A; the local numerics are the oracle's numpy/LAPACK calls; the collectives are real
+torch.distributed (gloo) calls.  The sharded result must reproduce the unsharded oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import reference_path as ref
+from oracle.inputs import decaying_spectrum_matrix
+from oracle.philox import random_gaussian
+
+M, N, K, P = 600, 200, 24, 6
+
+
+def _allgather(x):
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    return [o.numpy() for o in outs]
+
+
+def _allreduce(x):
+    t = torch.from_numpy(np.ascontiguousarray(x).copy())
+    dist.all_reduce(t)
+    return t.numpy()
+
+
+def sharded_pivoted_qr(y_local, ncq):
+    """DistTsqr + pivot-on-R: local QR, all-gather R_i, QR of the stack (redundant on every rank),
+    pivoted QR of the combined R, Q_i = Q0_i * top-chunk_i * Q1."""
+    rank = dist.get_rank()
+    w = y_local.shape[1]
+    q0, r0 = np.linalg.qr(y_local)                      # local TSQR (Householder)
+    rs = _allgather(r0)
+    qs, r = np.linalg.qr(np.concatenate(rs, axis=0))    # top level on every rank
+    q1, rr, ind = ref.pivoted_qr(r)                     # pivoting on the small factor
+    top = qs[rank * w:(rank + 1) * w, :].dot(q1[:, :ncq])
+    return q0.dot(top), rr, ind
+
+
+def sharded_rsvd(a_local, omega, k, it_count):
+    y0 = a_local.dot(omega)
+    res = y0
+    for index in range(it_count):
+        q, _, _ = sharded_pivoted_qr(y0, y0.shape[1])                 # always y0 (quirk Q1)
+        z = _allreduce(np.conj(a_local.T).dot(q))                      # all-reduce of A^H Q partials
+        w, _, _ = ref.pivoted_qr(z)                                   # replicated n x l: plain pivoted QR
+        ynew = a_local.dot(w)
+        if index == it_count - 1:
+            res = ynew
+    q, _, ind = sharded_pivoted_qr(res, k)
+    b = np.conj(_allreduce(np.conj(a_local.T).dot(q)).T)              # b = Q^H A, replicated
+    ub, s, vt = ref.compute_svd(b)
+    return q.dot(ub), s, vt, ind
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, _ = decaying_spectrum_matrix(M, N, np.float64, seed=5, r0=64, decade_every=8.0)
+    omega = random_gaussian((N, K + P), np.float64, seed=42)           # same Philox seed on every rank
+    rows = M // world
+    a_local = a[rank * rows:(rank + 1) * rows]
+    u_local, s, vt, ind = sharded_rsvd(a_local, omega, K, it_count=2)
+    us = _allgather(u_local)
+    if rank == 0:
+        np.savez(out, u=np.concatenate(us, axis=0), s=s, vt=vt, ind=ind)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.timeout(300)
+def test_row_sharded_rsvd_matches_unsharded_oracle(tmp_path):
+    out = str(tmp_path / "sharded.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    a, _ = decaying_spectrum_matrix(M, N, np.float64, seed=5, r0=64, decade_every=8.0)
+    omega = random_gaussian((N, K + P), np.float64, seed=42)
+    q_ref = ref.sample_range_power_iteration(a, K, P, 2, ref.OmegaStream(np.float64, blocks=[omega]))
+    svd_ref = ref.SVD.compute_from_range_estimate(q_ref, a)
+    assert np.max(np.abs(got["s"] - svd_ref.s) / svd_ref.s) < 1e-10
+    u = got["u"]
+    assert np.max(np.abs(u.T.dot(u) - np.eye(K))) < 1e-12
+    rec = (u * got["s"]).dot(got["vt"])
+    assert abs(ref.rel_diff_fro(rec, a) - ref.rel_diff_fro(svd_ref.to_mat(), a)) < 1e-10
+    # pivots of the final sketch agree with the unsharded LAPACK path
+    y = a.dot(ref.pivoted_qr(np.conj(a.T).dot(ref.pivoted_qr(a.dot(omega))[0]))[0])
+    assert np.array_equal(got["ind"], ref.pivoted_qr(y)[2])
