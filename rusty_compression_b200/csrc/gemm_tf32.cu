@@ -1,0 +1,371 @@
+// f32 contraction Y = A X on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with the
+// 3-product split  A X ~= A_hi X_hi + A_lo X_hi + A_hi X_lo  (hi = value rounded to TF32, lo = the
+// exact f32 remainder), FP32 accumulation in TMEM.  This is what carries f32 parity (1e-4 in
+// north_star; measured ~1e-6) on the tensor pipe instead of the FP32 SIMT pipe.
+//
+// Reference role: MatMat::matmat for f32 operators (src/types.rs:58-71), the dominant cost of
+// configs 3 and 4.
+//
+// Structure (one CTA per SM, persistent over 128-row tiles of A):
+//   warp 0      TMA producer: raw f32 A tile [128 x 32] + pre-split X^T tiles (hi, lo) [N x 32],
+//               SWIZZLE_128B, 4-deep (N <= 96) mbarrier ring
+//   warps 2-5   splitter: A tile -> A_hi (in place) and A_lo (second buffer), element positions
+//               preserved so the TMA-written canonical K-major layout stays valid for UMMA;
+//               fence.proxy.async, then signal the MMA warp.  Splitting A on the fly avoids a
+//               pre-split copy that would double the HBM traffic of the pass.
+//   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma (3 products x 4 K-steps of 8)
+//               per stage, tcgen05.commit frees the stage; accumulator double-buffered in TMEM
+//   warps 6-9   epilogue: tcgen05.ld (32 lanes x 16 columns) -> registers -> global Y
+// X is tiny (n x l): it is transposed and split once by a prologue kernel so that both B operands
+// are K-major TMA tiles.
+#include <cuda.h>
+#include "rc_internal.cuh"
+
+namespace {
+
+constexpr int BM = 128;           // UMMA M (cta_group::1)
+constexpr int BK = 32;            // floats per stage = one 128-byte swizzle row
+constexpr int NTHREADS = 320;     // 10 warps
+constexpr int MAX_STAGES = 4;
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p)
+            RC_THROW(RC_CUDA_ERROR, "cuTensorMapEncodeTiled entry point not available");
+        fn = (EncodeFn)p;
+    }
+    return fn;
+}
+// Row-major [rows][cols] f32 matrix, box = 32 cols (128 B) x box_rows, SWIZZLE_128B.
+CUtensorMap make_map_f32(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RC_THROW(RC_CUDA_ERROR, "cuTensorMapEncodeTiled (f32) failed (%d)", (int)r);
+    return m;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 128-byte rows, 8-row atoms of 1024 B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);           // start address  [0,14)
+    d |= (uint64_t)0 << 16;                             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;                  // stride byte offset [32,46): 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                             // layout type: SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t n) {
+    uint32_t d = 0;
+    d |= 1u << 4;            // c_format = F32
+    d |= 2u << 7;            // a_format = TF32
+    d |= 2u << 10;           // b_format = TF32
+    d |= (n >> 3) << 17;     // n_dim
+    d |= (uint32_t)(BM >> 4) << 24;   // m_dim
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct Tf32Params {
+    float* y;
+    int64_t ldy;
+    int M, N, K;          // N = real number of columns
+    int npad;             // UMMA N (multiple of 16, <= 256)
+    int m_tiles;
+    uint32_t tmem_cols;   // power of two >= 2 * npad
+};
+
+// KC k-blocks (KC * 32 values of K) are accumulated inside the tensor core before the partial sum is
+// promoted to an FP32 register accumulator (round-to-nearest adds on the CUDA cores): the tensor
+// core's own FP32 accumulation truncates, which costs ~K * 2^-24 relative accuracy on long chains
+// (measured 2.9e-5 at K = 4096 without promotion).
+constexpr int KC = 8;
+
+template <int STAGES, int NPADC>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                   const __grid_constant__ CUtensorMap tmBlo, Tf32Params prm) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    __shared__ __align__(8) unsigned long long bars[3 * MAX_STAGES + 4];
+    __shared__ uint32_t tmem_base_smem;
+    const uint32_t full0 = smem_u32(&bars[0]);                   // TMA landed (raw A + B hi/lo)
+    const uint32_t split0 = smem_u32(&bars[MAX_STAGES]);         // A split into hi/lo
+    const uint32_t empty0 = smem_u32(&bars[2 * MAX_STAGES]);     // MMAs that read the stage are done
+    const uint32_t accf0 = smem_u32(&bars[3 * MAX_STAGES]);      // accumulator buffer full (2)
+    const uint32_t acce0 = smem_u32(&bars[3 * MAX_STAGES + 2]);  // accumulator buffer drained (2)
+
+    constexpr int npad = NPADC;
+    const uint32_t A_BYTES = BM * BK * 4;                        // 16 KB
+    const uint32_t B_BYTES = (uint32_t)npad * BK * 4;
+    const uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;      // A_hi(raw), A_lo, B_hi, B_lo
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(split0 + 8 * s, 4);        // one arrival per splitter warp
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {     // TMEM allocation (whole warp), address published through shared memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(prm.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int kblocks = (prm.K + BK - 1) / BK;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+                const int m0 = t * BM;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint32_t fb = full0 + 8 * stage;
+                    mbar_expect_tx(fb, A_BYTES + 2 * B_BYTES);
+                    tma_load_2d(sa, &tmA, kb * BK, m0, fb);
+                    tma_load_2d(sa + 2 * A_BYTES, &tmBhi, kb * BK, 0, fb);
+                    tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmBlo, kb * BK, 0, fb);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32((uint32_t)npad);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;                                              // counts K-chunks (TMEM buffer hand-offs)
+            for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+                for (int kc0 = 0; kc0 < kblocks; kc0 += KC, ++it) {
+                    const int buf = it & 1;
+                    const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+                    mbar_wait(acce0 + 8 * buf, acc_phase ^ 1u);      // epilogue drained this buffer
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * npad);
+                    const int kc1 = min(kblocks, kc0 + KC);
+                    for (int kb = kc0; kb < kc1; ++kb) {
+                        mbar_wait(split0 + 8 * stage, phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                        const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            const uint32_t koff = (uint32_t)k * 32u; // 8 floats along K inside the swizzle row
+                            const uint64_t dah = umma_desc_sw128(a_hi + koff), dal = umma_desc_sw128(a_lo + koff);
+                            const uint64_t dbh = umma_desc_sw128(b_hi + koff), dbl = umma_desc_sw128(b_lo + koff);
+                            // small terms first, then the dominant one
+                            umma_tf32(d_tmem, dal, dbh, idesc, (kb != kc0 || k != 0) ? 1u : 0u);
+                            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                            umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                        }
+                        umma_commit(empty0 + 8 * stage);             // frees the stage when the MMAs retire
+                        if (kb == kc1 - 1) umma_commit(accf0 + 8 * buf);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== splitter: A -> (A_hi in place, A_lo) =====================
+        const int st = tid - 64;                                     // 0..127
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(full0 + 8 * stage, phase);
+                unsigned char* base = smem_dyn + (smem_base - smem_u32(smem_dyn)) + (size_t)stage * STAGE_BYTES;
+                float4* raw = reinterpret_cast<float4*>(base);
+                float4* lo = reinterpret_cast<float4*>(base + A_BYTES);
+#pragma unroll
+                for (int i = 0; i < (int)(A_BYTES / 16 / 128); ++i) {
+                    const int idx = st + 128 * i;
+                    float4 v = raw[idx], h, l;
+                    uint32_t u;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+                    raw[idx] = h;
+                    lo[idx] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(split0 + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int lg = warp & 3;                                     // TMEM lane group this warp may access
+        int it = 0;
+        for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+            float acc[NPADC];
+#pragma unroll
+            for (int j = 0; j < NPADC; ++j) acc[j] = 0.f;
+            for (int kc0 = 0; kc0 < kblocks; kc0 += KC, ++it) {
+                const int buf = it & 1;
+                const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+                mbar_wait(accf0 + 8 * buf, acc_phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c0 = 0; c0 < NPADC; c0 += 16) {
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * npad + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+            }
+            const int row = t * BM + lg * 32 + lane;
+            if (row < prm.M) {
+                float* yrow = prm.y + (int64_t)row * prm.ldy;
+#pragma unroll
+                for (int j = 0; j < NPADC; ++j)
+                    if (j < prm.N) yrow[j] = acc[j];
+            }
+        }
+    }
+    // ---- teardown
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(prm.tmem_cols) : "memory");
+    }
+}
+
+// X (K x N row-major) -> XhiT, XloT (npad x K row-major, K contiguous), rows >= N zero.
+__global__ void split_transpose_kernel(const float* __restrict__ x, int64_t ldx, int K, int N, int npad,
+                                       float* __restrict__ hiT, float* __restrict__ loT, int64_t ldt) {
+    int64_t total = (int64_t)npad * K;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int j = (int)(e / K), k = (int)(e - (int64_t)j * K);
+        float v = (j < N) ? x[(int64_t)k * ldx + j] : 0.f;
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        float h = __uint_as_float(u);
+        hiT[(int64_t)j * ldt + k] = h;
+        loT[(int64_t)j * ldt + k] = v - h;
+    }
+}
+
+template <int STAGES, int NPADC>
+void launch_tf32(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
+                 const Tf32Params& prm) {
+    constexpr size_t stage_bytes = 2 * (size_t)BM * BK * 4 + 2 * (size_t)NPADC * BK * 4;
+    constexpr size_t smem = STAGES * stage_bytes + 1024;
+    RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<STAGES, NPADC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = std::min(prm.m_tiles, c->sm_count);
+    tf32x3_gemm_kernel<STAGES, NPADC><<<grid, NTHREADS, smem, c->stream>>>(tmA, tmBhi, tmBlo, prm);
+    RC_CHECK_LAUNCH(c);
+}
+
+}  // namespace
+
+// Y (M x N, ldy) = A (M x K, lda) * X (K x N, ldx), f32, 3xTF32 on tcgen05.  Returns false when the
+// shape / alignment is not supported (caller falls back to the SIMT kernel).
+bool gemm_tf32x3_f32(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                     const float* X, int64_t ldx, float* Y, int64_t ldy) {
+    if (M <= 0 || N <= 0 || K <= 0) return false;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3)) return false;      // TMA: 16-byte base and pitch
+    if (M > (1LL << 30) || K > (1LL << 30)) return false;
+    // columns are processed in chunks of at most 128 (the promoted FP32 accumulator of a row lives in
+    // the registers of one epilogue thread)
+    int64_t nchunks = (N + 127) / 128;
+    int64_t per = ((N + nchunks - 1) / nchunks + 31) / 32 * 32;
+    int64_t ldt = (K + 3) / 4 * 4;
+    for (int64_t n0 = 0; n0 < N; n0 += per) {
+        const int ncols = (int)std::min<int64_t>(per, N - n0);
+        const int npad = (ncols + 31) / 32 * 32;          // 32, 64, 96 or 128
+        DevBuf<float> hiT(c, (size_t)npad * ldt), loT(c, (size_t)npad * ldt);
+        {
+            int64_t total = (int64_t)npad * K;
+            int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+            split_transpose_kernel<<<nb, 256, 0, c->stream>>>(X + n0, ldx, (int)K, ncols, npad, hiT.p, loT.p, ldt);
+            RC_CHECK_LAUNCH(c);
+        }
+        CUtensorMap tmA = make_map_f32(A, M, K, lda, BM);
+        CUtensorMap tmBhi = make_map_f32(hiT.p, npad, K, ldt, npad);
+        CUtensorMap tmBlo = make_map_f32(loT.p, npad, K, ldt, npad);
+        Tf32Params prm;
+        prm.y = Y + n0; prm.ldy = ldy; prm.M = (int)M; prm.N = ncols; prm.K = (int)K; prm.npad = npad;
+        prm.m_tiles = (int)((M + BM - 1) / BM);
+        uint32_t cols = 32;
+        while (cols < (uint32_t)(2 * npad)) cols <<= 1;
+        prm.tmem_cols = cols;
+        switch (npad) {
+            case 32: launch_tf32<4, 32>(c, tmA, tmBhi, tmBlo, prm); break;
+            case 64: launch_tf32<4, 64>(c, tmA, tmBhi, tmBlo, prm); break;
+            case 96: launch_tf32<4, 96>(c, tmA, tmBhi, tmBlo, prm); break;
+            default: launch_tf32<3, 128>(c, tmA, tmBhi, tmBlo, prm); break;
+        }
+    }
+    c->gemm_flops += 2 * M * N * K;
+    return true;
+}

@@ -71,7 +71,7 @@ def main():
             qa_ref, hist_ref = ref.sample_range_adaptive(a, 1e-4, 16, ref.OmegaStream(dtype, seed=7))
             assert [r for r, _ in hist] == [r for r, _ in hist_ref], (hist, hist_ref)
             ra, ra_ref = ref.range_residual(a, qa_full), ref.range_residual(a, qa_ref)
-            assert abs(ra - ra_ref) <= max(tol, 1e-8) * ra_ref, (dtype, ra, ra_ref)
+            assert abs(ra - ra_ref) <= max(tol, 1e-8) * ra_ref + (5e-7 if tol > 1e-6 else 0.0), (dtype, ra, ra_ref)
             print(f"[multi-gpu x{world}] {np.dtype(dtype).name}: sv err {err_s:.2e}, rec {rec:.3e} (ref {rec_ref:.3e}), "
                   f"id err {e:.3e} (ref {e_ref:.3e}), adaptive rank {hist[-1][0]}", flush=True)
     dist.barrier()

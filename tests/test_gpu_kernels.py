@@ -94,6 +94,26 @@ def test_dmma_tma_gemm_matches_generic_and_numpy(api, dtype, shape):
     assert relerr(z_fast, np.conj(a.T).dot(y)) < 1e-13 and relerr(z_gen, np.conj(a.T).dot(y)) < 1e-13
 
 
+@pytest.mark.parametrize("shape", [(4096, 1024, 74), (1000, 516, 10), (777, 1028, 138), (2048, 512, 266), (130, 4096, 20)])
+def test_tcgen05_tf32x3_gemm_matches_f64_reference(api, shape):
+    """f32 Y = A X on tcgen05 (kind::tf32, 3-product split, TMEM accumulators; gemm_tf32.cu) against a
+    float64 reference and against the SIMT kernel: f32-level accuracy, far inside the 1e-4 of north_star."""
+    m, n, l = shape
+    a = rnd((m, n), np.float32, 14)
+    x = rnd((n, l), np.float32, 15)
+    want = a.astype(np.float64).dot(x.astype(np.float64))
+    ctx = api.default_context()
+    op = api.DeviceMatrix.from_numpy(a)
+    ctx.set_option("gemm_impl", 0)
+    y_tc = op.matmat(x).to_numpy()
+    ctx.set_option("gemm_impl", 1)
+    y_simt = op.matmat(x).to_numpy()
+    ctx.set_option("gemm_impl", 0)
+    e_tc, e_simt = relerr(y_tc, want), relerr(y_simt, want)
+    assert e_simt < 2e-6
+    assert e_tc < 5e-6, (e_tc, e_simt)
+
+
 def test_strided_views_upload(api):
     a = rnd((40, 30), np.float64, 7)
     assert np.array_equal(api.DeviceMatrix.from_numpy(a.T).to_numpy(), a.T)

@@ -1,0 +1,24 @@
+"""Times the tcgen05 TF32x3 contraction Y = A X (f32) at the config-3 / config-4 shapes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from rusty_compression_b200 import api
+ctx = api.default_context()
+stream = torch.cuda.Stream(); ctx.set_stream(stream.cuda_stream)
+for (m, n, l) in [(32768, 32768, 64), (65536, 8192, 266), (65536, 8192, 74)]:
+    a = api.DeviceMatrix.random_gaussian((m, n), np.float32, 1)
+    x = api.DeviceMatrix.random_gaussian((n, l), np.float32, 2)
+    for impl in (0, 1):
+        ctx.set_option("gemm_impl", impl)
+        for _ in range(2): y = a.matmat(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        reps = 5
+        for _ in range(reps): y = a.matmat(x)
+        e1.record(stream); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        print(f"{m}x{n}x{l} f32 impl={'tcgen05-tf32x3' if impl == 0 else 'simt'}: {ms:.3f} ms  {2*m*n*l/ms/1e9:.1f} TFLOP/s  {m*n*4/ms/1e6:.0f} GB/s", flush=True)
+    ctx.set_option("gemm_impl", 0)
+    del a, x, y
