@@ -8,7 +8,7 @@
 //
 // Structure (one CTA per SM, persistent over 128-row tiles of A):
 //   warp 0      TMA producer: raw f32 A tile [128 x 32] + pre-split X^T tiles (hi, lo) [N x 32],
-//               SWIZZLE_128B, 4-deep (N <= 96) mbarrier ring
+//               SWIZZLE_128B, 2-4-deep mbarrier ring
 //   warps 2-5   splitter: A tile -> A_hi (in place) and A_lo (second buffer), element positions
 //               preserved so the TMA-written canonical K-major layout stays valid for UMMA;
 //               fence.proxy.async, then signal the MMA warp.  Splitting A on the fly avoids a
@@ -18,7 +18,13 @@
 //   warps 6-9   epilogue: tcgen05.ld (32 lanes x 16 columns) -> registers -> global Y
 // X is tiny (n x l): it is transposed and split once by a prologue kernel so that both B operands
 // are K-major TMA tiles.
+//
+// TRANS mode (Z = A^T Y, reduction over the rows of A, split-K with a fixed-order reduction): the
+// raw tile arrives as four [32 k][32 i] boxes and the splitter transposes it while splitting, so
+// the MMA still sees K-major operands (an MN-major descriptor variant produced all-zero products
+// on this toolchain and was dropped).
 #include <cuda.h>
+#include <cstdlib>
 #include "rc_internal.cuh"
 
 namespace {
@@ -45,6 +51,7 @@ EncodeFn get_encode() {
 }
 // Row-major [rows][cols] f32 matrix, box = 32 cols (128 B) x box_rows, SWIZZLE_128B.
 CUtensorMap make_map_f32(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    RC_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map box rows out of range");
     CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
@@ -93,7 +100,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                             // layout type: SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n
+// instruction descriptor: D = F32, A = B = TF32 (both K-major), M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t n) {
     uint32_t d = 0;
     d |= 1u << 4;            // c_format = F32
@@ -122,6 +129,9 @@ struct Tf32Params {
     int npad;             // UMMA N (multiple of 16, <= 256)
     int m_tiles;
     uint32_t tmem_cols;   // power of two >= 2 * npad
+    // TRANS (Z = A^T Y): split-K over the rows of A; partial results at y + split * part_stride
+    int splits, kb_per_split;
+    int64_t part_stride;
 };
 
 // KC k-blocks (KC * 32 values of K) are accumulated inside the tensor core before the partial sum is
@@ -130,7 +140,7 @@ struct Tf32Params {
 // (measured 2.9e-5 at K = 4096 without promotion).
 constexpr int KC = 8;
 
-template <int STAGES, int NPADC>
+template <int STAGES, int NPADC, bool TRANS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, Tf32Params prm) {
@@ -147,7 +157,9 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     constexpr int npad = NPADC;
     const uint32_t A_BYTES = BM * BK * 4;                        // 16 KB
     const uint32_t B_BYTES = (uint32_t)npad * BK * 4;
-    const uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;      // A_hi(raw), A_lo, B_hi, B_lo
+    // stage layout: [raw A (TRANS only)] [A_hi] [A_lo] [B_hi] [B_lo]; in NN mode the raw tile is split in place
+    const uint32_t RAW_BYTES = TRANS ? A_BYTES : 0u;
+    const uint32_t STAGE_BYTES = RAW_BYTES + 2 * A_BYTES + 2 * B_BYTES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -169,22 +181,36 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
 
-    const int kblocks = (prm.K + BK - 1) / BK;
+    const int kblocks_all = (prm.K + BK - 1) / BK;
+    const int total_items = prm.m_tiles * prm.splits;      // NN: splits == 1
+    // work item -> (tile along M, k-block range)
+#define RC_ITEM(t)                                                                         \
+    const int mt_ = (t) % prm.m_tiles, sp_ = (t) / prm.m_tiles;                            \
+    const int kb0_ = sp_ * prm.kb_per_split;                                               \
+    const int kb1_ = min(kblocks_all, kb0_ + prm.kb_per_split);                            \
+    const int kblocks = kb1_ - kb0_;                                                       \
+    (void)mt_; (void)sp_; (void)kblocks;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
-                const int m0 = t * BM;
-                for (int kb = 0; kb < kblocks; ++kb) {
+            for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+                RC_ITEM(t)
+                const int m0 = mt_ * BM;
+                for (int kb = kb0_; kb < kb1_; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1u);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     const uint32_t fb = full0 + 8 * stage;
                     mbar_expect_tx(fb, A_BYTES + 2 * B_BYTES);
-                    tma_load_2d(sa, &tmA, kb * BK, m0, fb);
-                    tma_load_2d(sa + 2 * A_BYTES, &tmBhi, kb * BK, 0, fb);
-                    tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmBlo, kb * BK, 0, fb);
+                    if (!TRANS) {
+                        tma_load_2d(sa, &tmA, kb * BK, m0, fb);                                   // [128 rows][32 k]
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < BM / 32; ++b) tma_load_2d(sa + b * 4096, &tmA, m0 + 32 * b, kb * BK, fb);   // raw [32 k][32 i] x 4
+                    }
+                    tma_load_2d(sa + RAW_BYTES + 2 * A_BYTES, &tmBhi, kb * BK, 0, fb);            // [npad rows][32 k]
+                    tma_load_2d(sa + RAW_BYTES + 2 * A_BYTES + B_BYTES, &tmBlo, kb * BK, 0, fb);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -195,7 +221,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t idesc = umma_idesc_tf32((uint32_t)npad);
             int stage = 0; uint32_t phase = 0;
             int it = 0;                                              // counts K-chunks (TMEM buffer hand-offs)
-            for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+                RC_ITEM(t)
                 for (int kc0 = 0; kc0 < kblocks; kc0 += KC, ++it) {
                     const int buf = it & 1;
                     const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
@@ -207,10 +234,11 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         mbar_wait(split0 + 8 * stage, phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                        const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+                        const uint32_t a_hi = sa + RAW_BYTES, a_lo = a_hi + A_BYTES, b_hi = a_lo + A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {
-                            const uint32_t koff = (uint32_t)k * 32u; // 8 floats along K inside the swizzle row
+                            // K-major: 8 floats along K inside the swizzle row; MN-major: next group of 8 k-rows
+                            const uint32_t koff = (uint32_t)k * 32u;
                             const uint64_t dah = umma_desc_sw128(a_hi + koff), dal = umma_desc_sw128(a_lo + koff);
                             const uint64_t dbh = umma_desc_sw128(b_hi + koff), dbl = umma_desc_sw128(b_lo + koff);
                             // small terms first, then the dominant one
@@ -229,23 +257,51 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ===================== splitter: A -> (A_hi in place, A_lo) =====================
         const int st = tid - 64;                                     // 0..127
         int stage = 0; uint32_t phase = 0;
-        for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+            RC_ITEM(t)
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(full0 + 8 * stage, phase);
                 unsigned char* base = smem_dyn + (smem_base - smem_u32(smem_dyn)) + (size_t)stage * STAGE_BYTES;
-                float4* raw = reinterpret_cast<float4*>(base);
-                float4* lo = reinterpret_cast<float4*>(base + A_BYTES);
+                if (!TRANS) {
+                    float4* raw = reinterpret_cast<float4*>(base);
+                    float4* lo = reinterpret_cast<float4*>(base + A_BYTES);
 #pragma unroll
-                for (int i = 0; i < (int)(A_BYTES / 16 / 128); ++i) {
-                    const int idx = st + 128 * i;
-                    float4 v = raw[idx], h, l;
-                    uint32_t u;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
-                    raw[idx] = h;
-                    lo[idx] = l;
+                    for (int i = 0; i < (int)(A_BYTES / 16 / 128); ++i) {
+                        const int idx = st + 128 * i;
+                        float4 v = raw[idx], h, l;
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+                        raw[idx] = h;
+                        lo[idx] = l;
+                    }
+                } else {
+                    // Transposing split: the raw tile is 4 boxes of [32 k][32 i] (the contraction index is the
+                    // row index of A).  Thread `st` owns output row i = st of the K-major [128 i][32 k] tiles:
+                    // 32 conflict-free LDS.32 (a warp reads one 128-byte row per k), split, then 2 x 8 STS.128
+                    // into the SWIZZLE_128B positions UMMA expects for a K-major operand.
+                    const int bx = st >> 5, ci = st & 31;
+                    const unsigned char* rawb = base + bx * 4096;
+                    float4* hi = reinterpret_cast<float4*>(base + A_BYTES);
+                    float4* lo = reinterpret_cast<float4*>(base + 2 * A_BYTES);
+                    float vals[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        vals[k] = *reinterpret_cast<const float*>(rawb + k * 128 + ((((ci >> 2) ^ (k & 7)) << 4) | ((ci & 3) << 2)));
+#pragma unroll
+                    for (int cch = 0; cch < 8; ++cch) {
+                        float4 h, l;
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[4 * cch + 0])); h.x = __uint_as_float(u); l.x = vals[4 * cch + 0] - h.x;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[4 * cch + 1])); h.y = __uint_as_float(u); l.y = vals[4 * cch + 1] - h.y;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[4 * cch + 2])); h.z = __uint_as_float(u); l.z = vals[4 * cch + 2] - h.z;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[4 * cch + 3])); h.w = __uint_as_float(u); l.w = vals[4 * cch + 3] - h.w;
+                        const int dst = st * 8 + (cch ^ (st & 7));       // float4 index: row st, swizzled 16-byte chunk
+                        hi[dst] = h;
+                        lo[dst] = l;
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
                 __syncwarp();
@@ -257,7 +313,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ===================== epilogue: TMEM -> registers -> global =====================
         const int lg = warp & 3;                                     // TMEM lane group this warp may access
         int it = 0;
-        for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+            RC_ITEM(t)
             float acc[NPADC];
 #pragma unroll
             for (int j = 0; j < NPADC; ++j) acc[j] = 0.f;
@@ -283,15 +340,16 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acce0 + 8 * buf);
             }
-            const int row = t * BM + lg * 32 + lane;
+            const int row = mt_ * BM + lg * 32 + lane;
             if (row < prm.M) {
-                float* yrow = prm.y + (int64_t)row * prm.ldy;
+                float* yrow = prm.y + (int64_t)sp_ * prm.part_stride + (int64_t)row * prm.ldy;
 #pragma unroll
                 for (int j = 0; j < NPADC; ++j)
                     if (j < prm.N) yrow[j] = acc[j];
             }
         }
     }
+#undef RC_ITEM
     // ---- teardown
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -315,15 +373,37 @@ __global__ void split_transpose_kernel(const float* __restrict__ x, int64_t ldx,
     }
 }
 
-template <int STAGES, int NPADC>
+template <int STAGES, int NPADC, bool TRANS>
 void launch_tf32(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
                  const Tf32Params& prm) {
-    constexpr size_t stage_bytes = 2 * (size_t)BM * BK * 4 + 2 * (size_t)NPADC * BK * 4;
+    constexpr size_t stage_bytes = (TRANS ? 3 : 2) * (size_t)BM * BK * 4 + 2 * (size_t)NPADC * BK * 4;
     constexpr size_t smem = STAGES * stage_bytes + 1024;
-    RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<STAGES, NPADC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = std::min(prm.m_tiles, c->sm_count);
-    tf32x3_gemm_kernel<STAGES, NPADC><<<grid, NTHREADS, smem, c->stream>>>(tmA, tmBhi, tmBlo, prm);
+    static_assert(smem <= 227 * 1024, "stage configuration exceeds shared memory");
+    RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<STAGES, NPADC, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = std::min(prm.m_tiles * prm.splits, c->sm_count);
+    tf32x3_gemm_kernel<STAGES, NPADC, TRANS><<<grid, NTHREADS, smem, c->stream>>>(tmA, tmBhi, tmBlo, prm);
     RC_CHECK_LAUNCH(c);
+}
+template <bool TRANS>
+void dispatch_tf32(rc_ctx* c, int npad, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
+                   const Tf32Params& prm) {
+    switch (npad) {
+        case 32: launch_tf32<(TRANS ? 3 : 4), 32, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;
+        case 64: launch_tf32<(TRANS ? 3 : 4), 64, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;
+        case 96: launch_tf32<(TRANS ? 3 : 4), 96, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;
+        default: launch_tf32<(TRANS ? 2 : 3), 128, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;
+    }
+}
+
+__global__ void tf32_reduce_kernel(int64_t M, int N, int splits, const float* __restrict__ part, int64_t ldp, int64_t part_stride,
+                                   float* __restrict__ z, int64_t ldz) {
+    int64_t n = M * N;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = e / N; int j = (int)(e - i * N);
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += part[(int64_t)sp * part_stride + i * ldp + j];   // fixed order
+        z[i * ldz + j] = s;
+    }
 }
 
 }  // namespace
@@ -359,11 +439,64 @@ bool gemm_tf32x3_f32(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float* A,
         uint32_t cols = 32;
         while (cols < (uint32_t)(2 * npad)) cols <<= 1;
         prm.tmem_cols = cols;
-        switch (npad) {
-            case 32: launch_tf32<4, 32>(c, tmA, tmBhi, tmBlo, prm); break;
-            case 64: launch_tf32<4, 64>(c, tmA, tmBhi, tmBlo, prm); break;
-            case 96: launch_tf32<4, 96>(c, tmA, tmBhi, tmBlo, prm); break;
-            default: launch_tf32<3, 128>(c, tmA, tmBhi, tmBlo, prm); break;
+        prm.splits = 1; prm.kb_per_split = (int)((K + BK - 1) / BK); prm.part_stride = 0;
+        dispatch_tf32<false>(c, npad, tmA, tmBhi, tmBlo, prm);
+    }
+    c->gemm_flops += 2 * M * N * K;
+    return true;
+}
+
+// Z (M x N, ldz) = A^T Y with A stored K x M (row-major, lda) and Y stored K x N (row-major, ldy): the
+// reduction runs over the ROWS of both (MN-major UMMA operands), split-K over the rows, partials
+// reduced in a fixed order.  f32, 3xTF32 on tcgen05.  Returns false when unsupported.
+bool gemm_tf32x3_f32_tn(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                        const float* Y, int64_t ldy, float* Z, int64_t ldz) {
+    if (M <= 0 || N <= 0 || K <= 0) return false;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3)) return false;
+    if (M > (1LL << 30) || K > (1LL << 30)) return false;
+    int64_t nchunks = (N + 127) / 128;
+    int64_t per = ((N + nchunks - 1) / nchunks + 31) / 32 * 32;
+    const int64_t kblocks = (K + BK - 1) / BK;
+    for (int64_t n0 = 0; n0 < N; n0 += per) {
+        const int ncols = (int)std::min<int64_t>(per, N - n0);
+        const int npad = (ncols + 31) / 32 * 32;
+        // B operand K-major: Y^T split into hi / lo once (Y is the small m x l matrix)
+        const int64_t ldt = (K + 3) / 4 * 4;
+        DevBuf<float> hi(c, (size_t)npad * ldt), lo(c, (size_t)npad * ldt);
+        {
+            int64_t total = (int64_t)npad * K;
+            int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+            split_transpose_kernel<<<nb, 256, 0, c->stream>>>(Y + n0, ldy, (int)K, ncols, npad, hi.p, lo.p, ldt);
+            RC_CHECK_LAUNCH(c);
+        }
+        CUtensorMap tmA = make_map_f32(A, K, M, lda, 32);           // boxes [32 k rows][32 cols]
+        CUtensorMap tmBhi = make_map_f32(hi.p, npad, K, ldt, npad);
+        CUtensorMap tmBlo = make_map_f32(lo.p, npad, K, ldt, npad);
+        Tf32Params prm;
+        prm.M = (int)M; prm.N = ncols; prm.K = (int)K; prm.npad = npad;
+        prm.m_tiles = (int)((M + BM - 1) / BM);
+        uint32_t cols = 32;
+        while (cols < (uint32_t)(2 * npad)) cols <<= 1;
+        prm.tmem_cols = cols;
+        // split-K: about 2 work items per SM, each at least KC k-blocks
+        int64_t want = std::max<int64_t>(1, (2LL * c->sm_count + prm.m_tiles - 1) / prm.m_tiles);
+        int64_t maxs = std::max<int64_t>(1, kblocks / KC);
+        int splits = (int)std::min(want, maxs);
+        int64_t kbps = ((kblocks + splits - 1) / splits + KC - 1) / KC * KC;
+        splits = (int)((kblocks + kbps - 1) / kbps);
+        prm.splits = splits; prm.kb_per_split = (int)kbps;
+        DevBuf<float> part;
+        if (splits == 1) { prm.y = Z + n0; prm.ldy = ldz; prm.part_stride = 0; }
+        else {
+            part.alloc(c, (size_t)splits * M * npad);
+            prm.y = part.p; prm.ldy = npad; prm.part_stride = M * (int64_t)npad;
+        }
+        dispatch_tf32<true>(c, npad, tmA, tmBhi, tmBlo, prm);
+        if (splits > 1) {
+            int64_t n = M * (int64_t)ncols;
+            int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+            tf32_reduce_kernel<<<nb, 256, 0, c->stream>>>(M, ncols, splits, part.p, npad, prm.part_stride, Z + n0, ldz);
+            RC_CHECK_LAUNCH(c);
         }
     }
     c->gemm_flops += 2 * M * N * K;

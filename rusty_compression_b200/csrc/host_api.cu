@@ -83,8 +83,11 @@ void gemm(rc_ctx* c, RcOp opa, RcOp opb, int64_t M, int64_t N, int64_t K, const 
             if (opa == RC_OP_N || opa == RC_OP_H)
                 if (gemm_dmma_c64(c, opa == RC_OP_H, M, N, K, A, lda, B, ldb, C, ldc)) return;
         } else if constexpr (std::is_same<T, float>::value) {
-            if (opa == RC_OP_N && M >= 128)
+            if (opa == RC_OP_N && M >= 128) {
                 if (gemm_tf32x3_f32(c, M, N, K, A, lda, B, ldb, C, ldc)) return;
+            } else if (opa != RC_OP_N && M >= 128 && K >= 256) {
+                if (gemm_tf32x3_f32_tn(c, M, N, K, A, lda, B, ldb, C, ldc)) return;
+            }
         }
     }
     gemm_generic<T>(c, opa, opb, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);

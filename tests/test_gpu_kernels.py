@@ -112,6 +112,15 @@ def test_tcgen05_tf32x3_gemm_matches_f64_reference(api, shape):
     e_tc, e_simt = relerr(y_tc, want), relerr(y_simt, want)
     assert e_simt < 2e-6
     assert e_tc < 5e-6, (e_tc, e_simt)
+    # Z = A^T Y: MN-major UMMA operands, split-K over the rows of A
+    yy = rnd((m, l), np.float32, 16)
+    want_t = a.astype(np.float64).T.dot(yy.astype(np.float64))
+    z_tc = op.conj_matmat(yy).to_numpy()
+    ctx.set_option("gemm_impl", 1)
+    z_simt = op.conj_matmat(yy).to_numpy()
+    ctx.set_option("gemm_impl", 0)
+    assert relerr(z_simt, want_t) < 2e-6
+    assert relerr(z_tc, want_t) < 5e-6, relerr(z_tc, want_t)
 
 
 def test_strided_views_upload(api):

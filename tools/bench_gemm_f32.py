@@ -19,6 +19,14 @@ for (m, n, l) in [(32768, 32768, 64), (65536, 8192, 266), (65536, 8192, 74)]:
         for _ in range(reps): y = a.matmat(x)
         e1.record(stream); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        yy = y
+        for _ in range(2): z = a.conj_matmat(yy)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(reps): z = a.conj_matmat(yy)
+        e1.record(stream); torch.cuda.synchronize()
+        ms_t = e0.elapsed_time(e1) / reps
+        print(f"   A^T Y: {ms_t:.3f} ms  {2*m*n*l/ms_t/1e9:.1f} TFLOP/s  {m*n*4/ms_t/1e6:.0f} GB/s", flush=True)
         print(f"{m}x{n}x{l} f32 impl={'tcgen05-tf32x3' if impl == 0 else 'simt'}: {ms:.3f} ms  {2*m*n*l/ms/1e9:.1f} TFLOP/s  {m*n*4/ms/1e6:.0f} GB/s", flush=True)
     ctx.set_option("gemm_impl", 0)
     del a, x, y
