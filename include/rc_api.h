@@ -79,10 +79,12 @@ rc_status rc_ctx_set_stream(rc_ctx* ctx, void* cuda_stream);
 rc_status rc_ctx_synchronize(rc_ctx* ctx);
 const char* rc_last_error_string(rc_ctx* ctx);
 /* Tuning / test knobs.  Keys: "gemm_impl" (0 auto, 1 generic SIMT tiles only),
- * "true_power_iteration" (0 = reference semantics incl. quirk Q1, 1 = textbook iteration). */
+ * "true_power_iteration" (0 = reference semantics incl. quirk Q1, 1 = textbook iteration),
+ * "qr_mode" (0 = Cholesky-QR2 fast path for well-conditioned tall panels with automatic
+ * fallback to Householder TSQR, 1 = Householder TSQR always). */
 rc_status rc_ctx_set_option(rc_ctx* ctx, const char* key, int64_t value);
 /* Counters: "kernel_launches" (own kernels launched so far), "gemm_flops", "h2d_bytes",
- * "d2h_bytes".  rc_ctx_reset_counters zeroes them. */
+ * "d2h_bytes", "cholqr_used", "cholqr_fallbacks".  rc_ctx_reset_counters zeroes them. */
 rc_status rc_ctx_get_counter(rc_ctx* ctx, const char* key, int64_t* out);
 rc_status rc_ctx_reset_counters(rc_ctx* ctx);
 

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librc_b200.so")
 SOURCES = ["kernels_basic.cu", "gemm_generic.cu", "gemm_dmma.cu", "gemm_tf32.cu", "tsqr.cu", "pivqr.cu", "jacobi.cu",
-           "trsm.cu", "comm.cu", "host_api.cu"]
+           "trsm.cu", "chol.cu", "comm.cu", "host_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-diag-suppress", "177"]

@@ -136,6 +136,46 @@ void download_ind(rc_ctx* c, const int* dind, int64_t n, std::vector<uint64_t>& 
     }
 }
 
+
+// Cholesky-QR2 fast path for a tall, numerically full-rank panel (Y = Q R with Q = q1 * rinv2):
+// two rounds of Gram matrix (one TN GEMM + all-reduce across row shards) -> small Cholesky -> Y R^{-1}.
+// All the work is GEMM-shaped, so it runs at tensor-pipe speed instead of the latency-bound
+// reflector chain of the Householder TSQR.  It is only taken when the panel is well conditioned
+// (diag(R) ratio below 1/sqrt(eps)-ish, second Gram matrix close to I); otherwise -- or when the
+// Cholesky breaks down -- the caller falls back to the unconditionally stable Householder TSQR
+// with Y untouched.  Backward error and orthogonality are O(eps) in the accepted regime
+// (Yamamoto et al. 2015), the same class as Householder, which is what pivot parity needs.
+template <class T>
+bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, int dtype,
+             DevBuf<T>& q1, DevBuf<T>& rinv2, DevBuf<T>& rfac, int64_t& lds) {
+    if (c->qr_mode == 1) return false;
+    const int64_t m_all = m;    // (local rows; the Gram matrices are summed across shards)
+    if ((!sharded && m_all < 4 * w) || w > chol_max_width(c, dtype) || w < 2) return false;
+    lds = rc_pad_ld(dtype, w);
+    DevBuf<T> g(c, (size_t)w * lds), r1(c, (size_t)w * lds), rinv1(c, (size_t)w * lds), r2(c, (size_t)w * lds);
+    DevBuf<double> status(c, 8);
+    double h[4];
+    const bool single = (dtype == RC_F32 || dtype == RC_C32);
+    const double max_ratio = single ? 2.0e2 : 1.0e6;
+    auto gram_chol = [&](const T* x, int64_t ldx, T* rr, T* ri) -> bool {
+        gemm<T>(c, RC_OP_H, RC_OP_N, w, w, m, x, ldx, x, ldx, g.p, lds, rc_one<T>(), rc_zero<T>());
+        if (sharded) for (int64_t i = 0; i < w; ++i) comm_allreduce_sum(c, g.p + i * lds, (size_t)w, dtype);
+        if (!chol_inv<T>(c, g.p, lds, w, rr, ri, lds, status.p)) return false;
+        RC_CUDA(cudaMemcpyAsync(h, status.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        RC_CUDA(cudaStreamSynchronize(c->stream));
+        return h[0] == 0.0 && h[1] > 0.0;
+    };
+    if (!gram_chol(y, ldy, r1.p, rinv1.p) || h[2] / h[1] > max_ratio) { c->cholqr_fallbacks++; return false; }
+    q1.alloc(c, (size_t)m * lds);
+    gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, y, ldy, rinv1.p, lds, q1.p, lds, rc_one<T>(), rc_zero<T>());
+    rinv2.alloc(c, (size_t)w * lds);
+    if (!gram_chol(q1.p, lds, r2.p, rinv2.p) || h[3] > 0.25) { c->cholqr_fallbacks++; return false; }
+    rfac.alloc(c, (size_t)w * lds);
+    gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, r2.p, lds, r1.p, lds, rfac.p, lds, rc_one<T>(), rc_zero<T>());
+    c->cholqr_used++;
+    return true;
+}
+
 // Tall-skinny route: Y = Q0 R0 by (distributed) Householder TSQR, pivoting on R0, Q = Q0 Q1.
 // Panels wider than the shared-memory limit are orthogonalised block by block against the
 // previous panels (two projection passes) before their own TSQR.
@@ -149,7 +189,18 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
     MatPtr q(mat_new(c, dtype, m, ncq));
     DevBuf<T> q1(c, (size_t)w * ncq);
 
-    if (w <= wmax) {
+    DevBuf<T> cq1, crinv2, crfac;
+    int64_t lds = 0;
+    if (cholqr2<T>(c, y, ldy, m, w, sharded, dtype, cq1, crinv2, crfac, lds)) {
+        // pivot on R = R2 R1, then Q = q1 (R2^{-1} Q1piv)
+        k_transpose<T>(c, wc.p, w, crfac.p, lds, w, w, false);
+        pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
+        pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1.p, ncq);
+        DevBuf<T> tq(c, (size_t)w * rc_pad_ld(dtype, ncq));
+        const int64_t ldtq = rc_pad_ld(dtype, ncq);
+        gemm<T>(c, RC_OP_N, RC_OP_N, w, ncq, w, crinv2.p, lds, q1.p, ncq, tq.p, ldtq, rc_one<T>(), rc_zero<T>());
+        gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, cq1.p, lds, tq.p, ldtq, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
+    } else if (w <= wmax) {
         DistTsqr<T> ts;
         ts.factor(c, y, ldy, m, w, sharded);
         // column-major copy of R0 = transpose of the row-major factor
@@ -258,7 +309,15 @@ void svd_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int dtype, boo
     DevBuf<double> ds(c, (size_t)w);
     MatPtr um(mat_new(c, dtype, m, w)), wm(mat_new(c, dtype, w, w));
     const int64_t wmax = tsqr_max_width(c, dtype);
-    if (w <= wmax && m >= w) {
+    DevBuf<T> cq1, crinv2, crfac;
+    int64_t lds = 0;
+    if (m >= w && cholqr2<T>(c, y, ldy, m, w, sharded, dtype, cq1, crinv2, crfac, lds)) {
+        const int64_t ldu = rc_pad_ld(dtype, w);
+        DevBuf<T> ur(c, (size_t)w * ldu), tq(c, (size_t)w * ldu);
+        jacobi_svd<T>(c, crfac.p, lds, w, w, ur.p, ldu, ds.p, P<T>(wm.get()), wm->ld);
+        gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, crinv2.p, lds, ur.p, ldu, tq.p, ldu, rc_one<T>(), rc_zero<T>());
+        gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, cq1.p, lds, tq.p, ldu, P<T>(um.get()), um->ld, rc_one<T>(), rc_zero<T>());
+    } else if (w <= wmax && m >= w) {
         DistTsqr<T> ts;
         ts.factor(c, y, ldy, m, w, sharded);
         DevBuf<T> ur(c, (size_t)w * w);
@@ -689,6 +748,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
     return guard(c, [&] {
         if (!strcmp(key, "gemm_impl")) c->gemm_impl = (int)v;
         else if (!strcmp(key, "true_power_iteration")) c->true_power_iteration = (int)v;
+        else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;
         else RC_THROW(RC_INVALID_ARGUMENT, "unknown option '%s'", key);
     });
 }
@@ -699,12 +759,15 @@ rc_status rc_ctx_get_counter(rc_ctx* c, const char* key, int64_t* out) {
         else if (!strcmp(key, "gemm_flops")) *out = c->gemm_flops;
         else if (!strcmp(key, "h2d_bytes")) *out = c->h2d_bytes;
         else if (!strcmp(key, "d2h_bytes")) *out = c->d2h_bytes;
+        else if (!strcmp(key, "cholqr_used")) *out = c->cholqr_used;
+        else if (!strcmp(key, "cholqr_fallbacks")) *out = c->cholqr_fallbacks;
         else RC_THROW(RC_INVALID_ARGUMENT, "unknown counter '%s'", key);
     });
 }
 rc_status rc_ctx_reset_counters(rc_ctx* c) {
     if (!c) return RC_INVALID_ARGUMENT;
     c->launches = c->gemm_flops = c->h2d_bytes = c->d2h_bytes = 0;
+    c->cholqr_used = c->cholqr_fallbacks = 0;
     return RC_OK;
 }
 

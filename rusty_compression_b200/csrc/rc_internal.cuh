@@ -47,6 +47,8 @@ struct rc_ctx {
     // options
     int gemm_impl = 0;            // 0 auto, 1 generic only
     int true_power_iteration = 0;
+    int qr_mode = 0;              // 0 auto (Cholesky-QR2 fast path with Householder-TSQR fallback), 1 TSQR only
+    int64_t cholqr_used = 0, cholqr_fallbacks = 0;
     // counters
     int64_t launches = 0, gemm_flops = 0, h2d_bytes = 0, d2h_bytes = 0;
     int* tile_counter = nullptr;   // device scratch for the dynamic GEMM tile scheduler
@@ -206,6 +208,13 @@ void jacobi_svd(rc_ctx*, const T* g, int64_t ldg, int64_t rows, int64_t n, T* u,
 template <class T>
 void trsm_upper(rc_ctx*, const T* u, int64_t ldu, bool u_transposed, int64_t k, const T* b, int64_t ldb,
                 int64_t nrhs, T* x, int64_t ldx);
+
+// ------------------------------------------------------------------ chol.cu
+// Cholesky factor G = R^H R and R^{-1} of a small Hermitian positive-definite matrix (one CTA).
+// status_dev: 4 doubles {breakdown flag, min diag R, max diag R, max |G - I|}.
+template <class T>
+bool chol_inv(rc_ctx*, const T* g, int64_t ldg, int64_t w, T* r, T* rinv, int64_t ldo, double* status_dev);
+int64_t chol_max_width(rc_ctx*, int dtype);
 
 // ------------------------------------------------------------------ comm.cu
 void comm_get_unique_id(void* out128);

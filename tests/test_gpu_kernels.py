@@ -123,6 +123,22 @@ def test_tcgen05_tf32x3_gemm_matches_f64_reference(api, shape):
     assert relerr(z_tc, want_t) < 5e-6, relerr(z_tc, want_t)
 
 
+def test_cholqr2_falls_back_on_ill_conditioned_panels(api):
+    """A sketch with condition number ~1e12 must take the Householder TSQR route and stay orthonormal."""
+    ctx = api.default_context()
+    a = ref.random_approximate_low_rank_matrix((3000, 60), 1.0, 1e-12, np.float64, seed=9)
+    ctx.reset_counters()
+    q, r, ind = api.pivoted_qr(a)
+    assert ctx.counter("cholqr_fallbacks") >= 1 and ctx.counter("cholqr_used") == 0
+    assert np.max(np.abs(q.T.dot(q) - np.eye(60))) < 1e-13
+    assert relerr(q.dot(r), a[:, ind]) < 1e-13
+    well = ref.random_approximate_low_rank_matrix((3000, 60), 1.0, 1e-3, np.float64, seed=9)
+    ctx.reset_counters()
+    q, r, ind = api.pivoted_qr(well)
+    assert ctx.counter("cholqr_used") == 1
+    assert np.max(np.abs(q.T.dot(q) - np.eye(60))) < 1e-13
+
+
 def test_strided_views_upload(api):
     a = rnd((40, 30), np.float64, 7)
     assert np.array_equal(api.DeviceMatrix.from_numpy(a.T).to_numpy(), a.T)
@@ -138,12 +154,18 @@ def test_norms_and_rel_diff(api, dtype):
     assert abs(api.rel_diff_l2(a[:, 0], b[:, 0]) - ref.rel_diff_l2(a[:, 0], b[:, 0])) < 1e-6
 
 
+@pytest.mark.parametrize("qr_mode", [0, 1], ids=["cholqr2-auto", "householder-tsqr"])
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2000, 40), (300, 74), (5000, 7), (64, 64), (150, 100)])
-def test_tall_pivoted_qr_matches_lapack(api, dtype, shape):
-    """TSQR + pivot-on-R against ?geqp3/?orgqr: same pivots, |R| equal, Q equal up to phases."""
+def test_tall_pivoted_qr_matches_lapack(api, dtype, shape, qr_mode):
+    """Tall route (Cholesky-QR2 fast path with fallback / Householder TSQR) + pivot-on-R against
+    ?geqp3/?orgqr: same pivots, |R| equal, Q orthonormal, Q R = A P."""
     a = ref.random_approximate_low_rank_matrix(shape, 1.0, 1e-4, dtype, seed=5)
-    q, r, ind = api.pivoted_qr(a)
+    api.default_context().set_option("qr_mode", qr_mode)
+    try:
+        q, r, ind = api.pivoted_qr(a)
+    finally:
+        api.default_context().set_option("qr_mode", 0)
     q0, r0, ind0 = ref.pivoted_qr(a)
     tol = 2e-4 if dtype in (np.float32, np.complex64) else 1e-9
     k = min(shape)

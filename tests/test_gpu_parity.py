@@ -29,9 +29,16 @@ def check_indices(a_for_gaps, got, want, min_gap):
     pytest.skip(f"pivot tie at step {j} (gap {gaps[j]:.2e} <= {min_gap}): later quantities not comparable")
 
 
+@pytest.fixture(params=[0, 1], ids=["cholqr2-auto", "householder-tsqr"])
+def qr_mode(request, api):
+    api.default_context().set_option("qr_mode", request.param)
+    yield request.param
+    api.default_context().set_option("qr_mode", 0)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32, np.complex64])
 @pytest.mark.parametrize("it_count", [0, 2])
-def test_rsvd_parity(api, dtype, it_count):
+def test_rsvd_parity(api, dtype, it_count, qr_mode):
     """Config-2 pipeline at oracle-sized scale: sample_range_power_iteration ->
     SVD::compute_from_range_estimate (src/random_sampling.rs:131-160, src/svd.rs:171-183)."""
     m, n, k, p = 4096, 1024, 64, 10
