@@ -15,8 +15,6 @@ chol_inv_kernel(const T* __restrict__ g, int64_t ldg, int w, T* __restrict__ r, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* S = reinterpret_cast<T*>(smem_raw);          // w x w row-major working copy (upper part used)
     T* X = S + (size_t)w * w;                        // inverse
-    __shared__ double s_piv;
-    __shared__ int s_bad;
     __shared__ double s_red[CT / 32];
     const int tid = threadIdx.x;
     double defect = 0.0;
@@ -27,50 +25,64 @@ chol_inv_kernel(const T* __restrict__ g, int64_t ldg, int w, T* __restrict__ r, 
         T d = (i == j) ? v - rc_one<T>() : v;
         defect = fmax(defect, rc_abs(d));
     }
-    if (tid == 0) s_bad = 0;
     // block max of the defect
     for (int m = 16; m > 0; m >>= 1) defect = fmax(defect, __shfl_xor_sync(0xffffffffu, defect, m));
     if ((tid & 31) == 0) s_red[tid >> 5] = defect;
     __syncthreads();
     if (tid == 0) { double d = 0.0; for (int i = 0; i < CT / 32; ++i) d = fmax(d, s_red[i]); status[3] = d; }
-    double dmin = 1e300, dmax = 0.0;
-    for (int j = 0; j < w; ++j) {
-        if (tid == 0) {
-            double d = (double)rc_real(S[j * w + j]);
-            if (!(d > 0.0)) { s_bad = 1; d = 1.0; }
-            s_piv = sqrt(d);
-        }
-        __syncthreads();
-        const double piv = s_piv;
-        dmin = fmin(dmin, piv); dmax = fmax(dmax, piv);
-        const RealOf<T> ip = (RealOf<T>)(1.0 / piv);
-        for (int c = j + tid; c < w; c += CT) S[j * w + c] = (c == j) ? rc_make<T>(piv, 0.0) : S[j * w + c] * ip;
-        __syncthreads();
-        // trailing update of the upper triangle: S[i][c] -= conj(R[j][i]) * R[j][c],  j < i <= c
-        const int nt = w - j - 1;
-        for (int e = tid; e < nt * nt; e += CT) {
-            int ii = e / nt, cc = e - ii * nt;
-            if (cc >= ii) {
-                int i = j + 1 + ii, c = j + 1 + cc;
-                S[i * w + c] = S[i * w + c] - rc_conj(S[j * w + i]) * S[j * w + c];
+    // Row-by-row (left-looking) Cholesky by the first 128 threads, one thread per column:
+    //   R[j][c] = (G[j][c] - sum_{l<j} conj(R[l][j]) R[l][c]) / R[j][j]
+    // The l-loop reads R[l][j] as a broadcast and R[l][c] conflict-free; the two barriers per row are
+    // 128-thread named barriers (the other 28 warps wait at the block barrier below).
+    __shared__ double s_d;
+    if (tid < 128) {
+        double dmin = 1e300, dmax = 0.0;
+        int bad = 0;
+        for (int j = 0; j < w; ++j) {
+            for (int c = j + tid; c < w; c += 128) {
+                T a0 = S[j * w + c], a1 = rc_zero<T>();
+                int l = 0;
+                for (; l + 1 < j; l += 2) {
+                    a0 = a0 - rc_conj(S[l * w + j]) * S[l * w + c];
+                    a1 = a1 - rc_conj(S[(l + 1) * w + j]) * S[(l + 1) * w + c];
+                }
+                if (l < j) a0 = a0 - rc_conj(S[l * w + j]) * S[l * w + c];
+                a0 = a0 + a1;
+                S[j * w + c] = a0;
+                if (c == j) s_d = (double)rc_real(a0);
             }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            double d = s_d;
+            if (!(d > 0.0)) { bad = 1; d = 1.0; }
+            const double piv = sqrt(d);
+            dmin = fmin(dmin, piv); dmax = fmax(dmax, piv);
+            const RealOf<T> ip = (RealOf<T>)(1.0 / piv);
+            for (int c = j + tid; c < w; c += 128) S[j * w + c] = (c == j) ? rc_make<T>(piv, 0.0) : S[j * w + c] * ip;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        __syncthreads();
+        if (tid == 0) { status[0] = (double)bad; status[1] = dmin; status[2] = dmax; }
     }
-    if (tid == 0) { status[0] = (double)s_bad; status[1] = dmin; status[2] = dmax; }
+    __syncthreads();
     // R out (upper triangular, zeros below)
     for (int e = tid; e < w * w; e += CT) {
         int i = e / w, j = e - i * w;
         r[(int64_t)i * ldo + j] = (j >= i) ? S[e] : rc_zero<T>();
     }
-    // X = R^{-1}: one thread per column, back substitution
-    for (int c = tid; c < w; c += CT) {
-        for (int i = w - 1; i > c; --i) X[i * w + c] = rc_zero<T>();
-        X[c * w + c] = rc_one<T>() / S[c * w + c];
-        for (int i = c - 1; i >= 0; --i) {
-            T acc = rc_zero<T>();
-            for (int l = i + 1; l <= c; ++l) acc = rc_fma(S[i * w + l], X[l * w + c], acc);
-            X[i * w + c] = -(acc / S[i * w + i]);
+    // X = R^{-1}: columns are independent; one warp per column walks its rows upwards, the lanes
+    // split each inner product (a thread-per-column loop was a 2.7K-long dependent chain)
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int c = warp; c < w; c += CT / 32) {
+            for (int i = w - 1 - lane; i > c; i -= 32) X[i * w + c] = rc_zero<T>();
+            if (lane == 0) X[c * w + c] = rc_one<T>() / S[c * w + c];
+            __syncwarp();
+            for (int i = c - 1; i >= 0; --i) {
+                T acc = rc_zero<T>();
+                for (int l = i + 1 + lane; l <= c; l += 32) acc = rc_fma(S[i * w + l], X[l * w + c], acc);
+                acc = rc_warp_sum(acc);
+                if (lane == 0) X[i * w + c] = -(acc / S[i * w + i]);
+                __syncwarp();
+            }
         }
     }
     __syncthreads();

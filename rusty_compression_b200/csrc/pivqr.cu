@@ -215,6 +215,94 @@ pivqr_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, double* __r
     }
 }
 
+
+// Small factors (the l x l R of a sketch): one CTA, everything in shared memory, and the serial part
+// of a step (argmax -> pivot column -> ?larfg scalars) done by ONE warp, so a step costs two block
+// barriers instead of seven.  Same pivot rule and numerics as pivqr_kernel.
+template <class T, int NT>
+__global__ void __launch_bounds__(NT)
+pivqr_small_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, int* __restrict__ ind,
+                   T* __restrict__ vbuf, T* __restrict__ tau_out, T* __restrict__ diag) {
+    constexpr int NW = NT / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xs = reinterpret_cast<T*>(smem_raw);                 // reflector, p entries
+    T* W = xs + p;                                          // p x n column-major
+    double* vn = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(W + (size_t)p * n) + 7) & ~(uintptr_t)7);
+    int* lpos = reinterpret_cast<int*>(vn + n);
+    __shared__ T s_tau;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < p * n; e += NT) { int c = e / p, r = e - c * p; W[e] = Wg[(int64_t)c * ldwg + r]; }
+    __syncthreads();
+    for (int c = warp; c < n; c += NW) {
+        const T* col = W + (size_t)c * p;
+        double a = 0.0;
+        for (int r = lane; r < p; r += 32) a += rc_abs2(col[r]);
+        a = rc_warp_sum(a);
+        if (lane == 0) { vn[c] = sqrt(a); lpos[c] = c; }
+    }
+    __syncthreads();
+    for (int i = 0; i < kk; ++i) {
+        if (warp == 0) {
+            Cand best; best.val = -1.0; best.lpos = 0x7fffffff; best.phys = -1;
+            int disp = -1;
+            for (int c = lane; c < n; c += 32) {
+                int lp = lpos[c];
+                if (lp >= i) {
+                    Cand cnd; cnd.val = vn[c]; cnd.lpos = lp; cnd.phys = c;
+                    if (better(cnd, best)) best = cnd;
+                    if (lp == i) disp = c;
+                }
+            }
+            best = warp_best(best);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, m));
+            const int pv = best.phys;
+            if (lane == 0) {
+                if (disp >= 0 && disp != pv) lpos[disp] = best.lpos;
+                lpos[pv] = i;
+                ind[i] = pv;
+            }
+            const T* pcol = W + (size_t)pv * p;
+            double a = 0.0;
+            for (int r = i + lane; r < p; r += 32) { T v = pcol[r]; xs[r] = v; if (r > i) a += rc_abs2(v); }
+            a = rc_warp_sum(a);
+            __syncwarp();
+            T tau, scale, beta;
+            larfg_dev<T>(xs[i], a, tau, scale, beta);      // every lane: identical inputs, identical result
+            __syncwarp();
+            for (int r = i + 1 + lane; r < p; r += 32) xs[r] = xs[r] * scale;
+            __syncwarp();
+            T* vcol = vbuf + (int64_t)i * p;
+            for (int r = lane; r < p; r += 32) vcol[r] = (r < i) ? rc_zero<T>() : (r == i ? rc_one<T>() : xs[r]);
+            if (lane == 0) { tau_out[i] = tau; diag[i] = beta; s_tau = tau; }
+        }
+        __syncthreads();
+        const T ctau = rc_conj(s_tau);
+        for (int c = warp; c < n; c += NW) {
+            if (lpos[c] <= i) continue;
+            T* col = W + (size_t)c * p;
+            using A = typename AccOf<T>::type;
+            A part = rc_zero<A>();
+            for (int r = i + 1 + lane; r < p; r += 32) part = rc_cfma(rc_widen(xs[r]), rc_widen(col[r]), part);
+            part = rc_warp_sum(part);
+            T ci = col[i];
+            T f = ctau * rc_narrow<T>(rc_widen(ci) + part);
+            double nrm = 0.0;
+            for (int r = i + 1 + lane; r < p; r += 32) {
+                T v = col[r] - f * xs[r];
+                col[r] = v;
+                nrm += rc_abs2(v);
+            }
+            nrm = rc_warp_sum(nrm);
+            if (lane == 0) { col[i] = ci - f; vn[c] = sqrt(nrm); }
+        }
+        __syncthreads();
+    }
+    for (int c = tid; c < n; c += NT) { int lp = lpos[c]; if (lp >= kk) ind[lp] = c; }
+    __syncthreads();
+    for (int e = tid; e < p * n; e += NT) { int c = e / p, r = e - c * p; Wg[(int64_t)c * ldwg + r] = W[e]; }
+}
+
 // r (kk x n row-major) from the factored column-major W, logical order `ind`.
 template <class T>
 __global__ void gather_r_kernel(const T* __restrict__ W, int64_t ldw, int kk, int n, const int* __restrict__ ind,
@@ -268,19 +356,11 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
     int pi = (int)p, ni = (int)n;
     size_t smem_all = ((size_t)p + (size_t)p * n + 1) * sizeof(T) + (size_t)n * (sizeof(double) + sizeof(int)) + 16;
     if (smem_all + 8192 <= lim && n <= 2048) {
-        // small factor: one CTA, matrix resident in shared memory; fewer warps when there are few
-        // columns (block barriers are the critical path of the 74-step chain)
-        DevBuf<Cand> slots(c, 2);
-        DevBuf<int> slots_disp(c, 2);
-        void* args[] = {&wc, &ldw, &pi, &ni, &kk, &vn.p, &lpos.p, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p};
-        if (n <= 0) {   // (256 threads measured slower than 1024 even for 74 columns)
-            RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
-            RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T, 256, true>, dim3(1), dim3(256), args, smem_all, c->stream));
-        } else {
-            RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
-            RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T, 1024, true>, dim3(1), dim3(1024), args, smem_all, c->stream));
-        }
-        RC_COUNT_LAUNCH(c);
+        // small factor: one CTA, matrix resident in shared memory
+        constexpr int NTS = 1024;
+        RC_CUDA(cudaFuncSetAttribute(pivqr_small_kernel<T, NTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
+        pivqr_small_kernel<T, NTS><<<1, NTS, smem_all, c->stream>>>(wc, ldw, pi, ni, kk, ind, vbuf, tau, diag.p);
+        RC_CHECK_LAUNCH(c);
     } else {
         constexpr int NT = 256;
         constexpr int NW = NT / 32;
