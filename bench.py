@@ -135,7 +135,7 @@ def cpu_sample(m_sample, route, reps=1):
     return flops / best / 1e9, best
 
 
-def reference_arm(args):
+def reference_arm(args, result_out):
     """`--impl reference`: the reference's own CPU implementation of the path (oracle port, the
     Rust crate cannot be built here), all host threads, bounded row sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -162,7 +162,8 @@ def reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample,
                              "reference_faithful_gemv_route_gflops": faithful},
             "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    result_out.write(json.dumps(line) + "\n")
+    result_out.flush()
     return 0
 
 
@@ -176,7 +177,17 @@ def workload_config(n_gpus):
 
 
 # ----------------------------------------------------------------------------------- CUDA arm
+def _claim_stdout():
+    """Exactly ONE line may reach stdout (the JSON result): libraries such as NCCL print banners to
+    fd 1, so fd 1 is pointed at stderr for the whole run and the result goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    result_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -193,7 +204,7 @@ def main():
     if args.n:
         CFG["n"] = args.n
     if args.impl == "reference":
-        return reference_arm(args)
+        return reference_arm(args, result_out)
 
     import torch
     import torch.distributed as dist
@@ -339,7 +350,8 @@ def main():
                 "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "hbm_gbs_algorithmic": hbm_gbs, "algorithmic_flops_per_step_per_gpu": flops_rank}
-        print(json.dumps(line))
+        result_out.write(json.dumps(line) + "\n")
+        result_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -158,8 +158,9 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
     const bool single = (dtype == RC_F32 || dtype == RC_C32);
     const double max_ratio = single ? 2.0e2 : 1.0e6;
     auto gram_chol = [&](const T* x, int64_t ldx, T* rr, T* ri) -> bool {
+        if (sharded && lds != w) RC_CUDA(cudaMemsetAsync(g.p, 0, sizeof(T) * w * lds, c->stream));   // padding is summed too
         gemm<T>(c, RC_OP_H, RC_OP_N, w, w, m, x, ldx, x, ldx, g.p, lds, rc_one<T>(), rc_zero<T>());
-        if (sharded) for (int64_t i = 0; i < w; ++i) comm_allreduce_sum(c, g.p + i * lds, (size_t)w, dtype);
+        if (sharded) comm_allreduce_sum(c, g.p, (size_t)w * lds, dtype);      // one all-reduce of the Gram matrix
         if (!chol_inv<T>(c, g.p, lds, w, rr, ri, lds, status.p)) return false;
         RC_CUDA(cudaMemcpyAsync(h, status.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         RC_CUDA(cudaStreamSynchronize(c->stream));
