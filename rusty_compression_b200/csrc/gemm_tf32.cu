@@ -502,3 +502,52 @@ bool gemm_tf32x3_f32_tn(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float*
     c->gemm_flops += 2 * M * N * K;
     return true;
 }
+
+// ---- c32 through the same tcgen05 kernels via the exact real expansion (see gemm_dmma_c64):
+//   NN:  (A viewed as real m x 2n) * X' = (A X viewed as real m x 2l),  X' rows 2k / 2k+1 = X_k / i X_k
+//   TN:  W = (A viewed as real)^T * (X viewed as real) is 2n x 2l;  A^H X is recombined from W.
+namespace {
+__global__ void expand_rhs_c32_kernel(float* dst, int64_t ldd, const c32* x, int64_t ldx, int64_t rows, int64_t cols) {
+    int64_t n = rows * cols;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t k = e / cols, j = e - k * cols;
+        c32 v = x[k * ldx + j];
+        float* r0 = dst + (2 * k) * ldd + 2 * j;
+        float* r1 = dst + (2 * k + 1) * ldd + 2 * j;
+        r0[0] = v.re; r0[1] = v.im;
+        r1[0] = -v.im; r1[1] = v.re;
+    }
+}
+__global__ void combine_conj_c32_kernel(int64_t n, int64_t l, const float* __restrict__ w, int64_t ldw, c32* __restrict__ z, int64_t ldz) {
+    int64_t tot = n * l;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t j = e / l, c = e - j * l;
+        const float* r0 = w + (2 * j) * ldw + 2 * c;
+        const float* r1 = w + (2 * j + 1) * ldw + 2 * c;
+        z[j * ldz + c] = c32(r0[0] + r1[1], r0[1] - r1[0]);
+    }
+}
+}  // namespace
+
+bool gemm_tf32x3_c32(rc_ctx* c, bool a_conj_transposed, int64_t M, int64_t N, int64_t K, const c32* A, int64_t lda,
+                     const c32* B, int64_t ldb, c32* C, int64_t ldc) {
+    if (M <= 0 || N <= 0 || K <= 0) return false;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 1)) return false;
+    if (!a_conj_transposed) {
+        int64_t ldx = 2 * N;
+        DevBuf<float> xp(c, (size_t)(2 * K) * ldx);
+        int nb = (int)std::min<int64_t>((K * N + 255) / 256, 148 * 8);
+        expand_rhs_c32_kernel<<<nb, 256, 0, c->stream>>>(xp.p, ldx, B, ldb, K, N);
+        RC_CHECK_LAUNCH(c);
+        return gemm_tf32x3_f32(c, M, 2 * N, 2 * K, reinterpret_cast<const float*>(A), 2 * lda, xp.p, ldx,
+                               reinterpret_cast<float*>(C), 2 * ldc);
+    }
+    int64_t ldw = 2 * N;
+    DevBuf<float> w(c, (size_t)(2 * M) * ldw);
+    if (!gemm_tf32x3_f32_tn(c, 2 * M, 2 * N, K, reinterpret_cast<const float*>(A), 2 * lda,
+                            reinterpret_cast<const float*>(B), 2 * ldb, w.p, ldw)) return false;
+    int nb = (int)std::min<int64_t>((M * N + 255) / 256, 148 * 8);
+    combine_conj_c32_kernel<<<nb, 256, 0, c->stream>>>(M, N, w.p, ldw, C, ldc);
+    RC_CHECK_LAUNCH(c);
+    return true;
+}

@@ -88,6 +88,12 @@ void gemm(rc_ctx* c, RcOp opa, RcOp opb, int64_t M, int64_t N, int64_t K, const 
             } else if (opa != RC_OP_N && M >= 128 && K >= 256) {
                 if (gemm_tf32x3_f32_tn(c, M, N, K, A, lda, B, ldb, C, ldc)) return;
             }
+        } else if constexpr (std::is_same<T, c32>::value) {
+            if (opa == RC_OP_N && M >= 128) {
+                if (gemm_tf32x3_c32(c, false, M, N, K, A, lda, B, ldb, C, ldc)) return;
+            } else if (opa == RC_OP_H && M >= 64 && K >= 256) {
+                if (gemm_tf32x3_c32(c, true, M, N, K, A, lda, B, ldb, C, ldc)) return;
+            }
         }
     }
     gemm_generic<T>(c, opa, opb, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);

@@ -155,6 +155,8 @@ bool gemm_tf32x3_f32(rc_ctx*, int64_t M, int64_t N, int64_t K, const float* A, i
                      const float* X, int64_t ldx, float* Y, int64_t ldy);
 bool gemm_tf32x3_f32_tn(rc_ctx*, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
                         const float* Y, int64_t ldy, float* Z, int64_t ldz);
+bool gemm_tf32x3_c32(rc_ctx*, bool a_conj_transposed, int64_t M, int64_t N, int64_t K, const c32* A, int64_t lda,
+                     const c32* B, int64_t ldb, c32* C, int64_t ldc);
 bool gemm_dmma_c64(rc_ctx*, bool a_conj_transposed, int64_t M, int64_t N, int64_t K, const c64* A, int64_t lda,
                    const c64* B, int64_t ldb, c64* C, int64_t ldc);
 

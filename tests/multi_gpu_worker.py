@@ -74,6 +74,24 @@ def main():
             assert abs(ra - ra_ref) <= max(tol, 1e-8) * ra_ref + (5e-7 if tol > 1e-6 else 0.0), (dtype, ra, ra_ref)
             print(f"[multi-gpu x{world}] {np.dtype(dtype).name}: sv err {err_s:.2e}, rec {rec:.3e} (ref {rec_ref:.3e}), "
                   f"id err {e:.3e} (ref {e_ref:.3e}), adaptive rank {hist[-1][0]}", flush=True)
+    # --- config-4 shape at reduced m: row-sharded tall-skinny range finder, f32, rank 256 (+10): the sketch
+    #     (l = 266) is wider than one TSQR panel, so it goes through the panel path with all-reduced projections
+    from oracle.inputs import tall_shard_matrix
+    m, n, k, p = 16384, 1024, 256, 10
+    rows = m // world
+    a_loc = tall_shard_matrix(rank * rows, rows, n, np.float32, seed=9, m_total=m, r0=512, decade_every=64.0)
+    op = api.DeviceMatrix.from_numpy(a_loc, ctx=ctx).set_shard(m, rank * rows)
+    q = api.sample_range_by_rank(op, k, p, seed=42, ctx=ctx, device=True)      # Omega regenerated from the shared Philox seed
+    q_full = gather_rows(q.to_numpy())
+    a_full = gather_rows(a_loc)
+    if rank == 0:
+        omega = random_gaussian((n, k + p), np.float32, seed=42)
+        q_ref = ref.sample_range_by_rank(a_full, k, p, ref.OmegaStream(np.float32, blocks=[omega]))
+        orth = np.max(np.abs(q_full.T.astype(np.float64).dot(q_full.astype(np.float64)) - np.eye(k)))
+        r, r_ref = ref.range_residual(a_full, q_full), ref.range_residual(a_full, q_ref)
+        print(f"[multi-gpu x{world}] config-4 shape f32 {m}x{n}, rank {k}: |Q^T Q - I| {orth:.2e}, residual {r:.4e} (oracle {r_ref:.4e})", flush=True)
+        assert orth < 5e-5
+        assert abs(r - r_ref) <= 2e-2 * r_ref + 1e-6, (r, r_ref)
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_OK", flush=True)

@@ -123,6 +123,18 @@ def test_tcgen05_tf32x3_gemm_matches_f64_reference(api, shape):
     assert relerr(z_tc, want_t) < 5e-6, relerr(z_tc, want_t)
 
 
+@pytest.mark.parametrize("shape", [(2048, 512, 74), (1000, 258, 20)])
+def test_c32_runs_on_tcgen05_through_real_expansion(api, shape):
+    """c32 contractions reuse the tcgen05 TF32x3 kernels through the exact real expansion."""
+    m, n, l = shape
+    a, x, y = rnd((m, n), np.complex64, 21), rnd((n, l), np.complex64, 22), rnd((m, l), np.complex64, 23)
+    op = api.DeviceMatrix.from_numpy(a)
+    want = a.astype(np.complex128).dot(x.astype(np.complex128))
+    want_h = np.conj(a.astype(np.complex128).T).dot(y.astype(np.complex128))
+    assert relerr(op.matmat(x).to_numpy(), want) < 5e-6
+    assert relerr(op.conj_matmat(y).to_numpy(), want_h) < 5e-6
+
+
 def test_cholqr2_falls_back_on_ill_conditioned_panels(api):
     """A sketch with condition number ~1e12 must take the Householder TSQR route and stay orthonormal."""
     ctx = api.default_context()
