@@ -107,6 +107,7 @@ struct DmmaParams {
     int m_tiles, n_chunks, splits;
     int k_chunk;          // multiple of BK
     int* tile_counter;    // dynamic tile scheduler (zeroed before the launch)
+    uint32_t zero;        // always 0 at run time (opaque to ptxas): ties the stage release to the loaded data
 };
 
 template <int BN, bool TRANS_A>
@@ -203,6 +204,7 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int k0 = kbeg; k0 < kend; k0 += BK) {
                 if (k0 != kbeg) mbar_wait(full0 + 8 * stage, phase);
                 const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                uint32_t dep = 0;
 #pragma unroll
                 for (int kg = 0; kg < BK / 8; ++kg) {
                     double a[RG][2], b[CG][2];
@@ -241,9 +243,14 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int i = 0; i < RG; ++i)
 #pragma unroll
                             for (int j = 0; j < CG; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i][h], b[j][h]);
+                    dep |= (uint32_t)__double2loint(a[RG - 1][1]) | (uint32_t)__double2loint(b[CG - 1][1]);
                 }
+                // Release the stage only once the fragments are in registers: the barrier address carries a
+                // data dependence on the last loads (dep & 0 at run time).  Without it the arrive issues right
+                // behind the LDS *issue* and a TMA refill could, in principle, overtake loads that are still
+                // queued in a backed-up load/store pipe.
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+                if (lane == 0) mbar_arrive(empty0 + 8 * stage + (dep & prm.zero));
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
             // ---- epilogue: accumulators -> global (direct or split partial)
@@ -360,6 +367,7 @@ bool gemm_dmma_f64(rc_ctx* c, bool a_transposed, int64_t M, int64_t N, int64_t K
 
     if (!c->tile_counter) RC_CUDA(cudaMalloc((void**)&c->tile_counter, 256));
     prm.tile_counter = c->tile_counter;
+    prm.zero = 0;
     DevBuf<double> part;
     if (splits == 1) {
         prm.d = C; prm.ldd = ldc; prm.part_stride = 0;

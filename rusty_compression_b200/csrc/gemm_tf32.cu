@@ -9,12 +9,15 @@
 // Structure (one CTA per SM, persistent over 128-row tiles of A):
 //   warp 0      TMA producer: raw f32 A tile [128 x 32] + pre-split X^T tiles (hi, lo) [N x 32],
 //               SWIZZLE_128B, 2-4-deep mbarrier ring
-//   warps 2-5   splitter: A tile -> A_hi (in place) and A_lo (second buffer), element positions
-//               preserved so the TMA-written canonical K-major layout stays valid for UMMA;
-//               fence.proxy.async, then signal the MMA warp.  Splitting A on the fly avoids a
+//   warps 2-5   splitter: raw A tile (shared memory) -> A_hi, A_lo written straight into TENSOR MEMORY
+//               (tcgen05.st, one thread per tile row); the MMAs take A from TMEM, so the split tiles never
+//               go back through shared memory (the SS form of this kernel was shared-memory-bandwidth
+//               bound: 152 KB of smem traffic per 16 KB of A).  Splitting A on the fly avoids a
 //               pre-split copy that would double the HBM traffic of the pass.
-//   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma (3 products x 4 K-steps of 8)
-//               per stage, tcgen05.commit frees the stage; accumulator double-buffered in TMEM
+//   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma (3 products x 4 K-steps of 8, A from
+//               TMEM, B from shared memory) per stage, tcgen05.commit frees the rings' slots; accumulator
+//               double-buffered in TMEM
+//   warp 10     TMA producer of the X^T tiles (own ring)
 //   warps 6-9   epilogue: tcgen05.ld (32 lanes x 16 columns) -> registers -> global Y
 // X is tiny (n x l): it is transposed and split once by a prologue kernel so that both B operands
 // are K-major TMA tiles.
@@ -31,8 +34,9 @@ namespace {
 
 constexpr int BM = 128;           // UMMA M (cta_group::1)
 constexpr int BK = 32;            // floats per stage = one 128-byte swizzle row
-constexpr int NTHREADS = 320;     // 10 warps
-constexpr int MAX_STAGES = 4;
+constexpr int NTHREADS = 352;     // 11 warps
+constexpr int MAX_RS = 8, MAX_MS = 4, MAX_BS = 4;   // ring depths: raw A tiles (smem), split A (TMEM), B tiles (smem)
+constexpr int A_TMEM_COLS = 64;   // one split stage in TMEM: A_hi (32 columns = 32 k) + A_lo (32 columns)
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -118,6 +122,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (128 lanes = tile rows, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 consecutive TMEM columns of this thread's lane <- 32 registers
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -132,6 +155,12 @@ struct Tf32Params {
     // TRANS (Z = A^T Y): split-K over the rows of A; partial results at y + split * part_stride
     int splits, kb_per_split;
     int64_t part_stride;
+    // N > 128: the columns are processed as `nchunks` chunks of npad columns each (the promoted FP32
+    // accumulator of a row has to fit the registers of one epilogue thread).  The chunk index is the
+    // FASTEST-varying part of the work-item order, so the CTAs that work on the same rows of A run
+    // side by side and A is fetched from HBM once and served to the other chunks out of L2.
+    int nchunks;
+    int vec_store;        // y and ldy are 16-byte aligned: the epilogue may use float4 stores
 };
 
 // KC k-blocks (KC * 32 values of K) are accumulated inside the tensor core before the partial sum is
@@ -140,34 +169,39 @@ struct Tf32Params {
 // (measured 2.9e-5 at K = 4096 without promotion).
 constexpr int KC = 8;
 
-template <int STAGES, int NPADC, bool TRANS>
+// Three rings decouple the HBM latency from the tensor pipe:
+//   raw  (RS deep, 16 KB each)  TMA landing zone for the raw f32 A tiles -- deep, because at l <= 100 the
+//                               pass is HBM-bound and ~64 KB per SM must be in flight to cover the latency
+//   ahl  (MS deep, 64 TMEM cols) A_hi / A_lo in tensor memory (lane = tile row, column = k), written by the splitter
+//   bt   (BS deep)              X_hi^T / X_lo^T tiles (L2-resident), own TMA producer warp
+template <int RS, int MS, int BS, int NPADC, bool TRANS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, Tf32Params prm) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    __shared__ __align__(8) unsigned long long bars[3 * MAX_STAGES + 4];
+    __shared__ __align__(8) unsigned long long bars[2 * MAX_RS + 2 * MAX_MS + 2 * MAX_BS + 4];
     __shared__ uint32_t tmem_base_smem;
-    const uint32_t full0 = smem_u32(&bars[0]);                   // TMA landed (raw A + B hi/lo)
-    const uint32_t split0 = smem_u32(&bars[MAX_STAGES]);         // A split into hi/lo
-    const uint32_t empty0 = smem_u32(&bars[2 * MAX_STAGES]);     // MMAs that read the stage are done
-    const uint32_t accf0 = smem_u32(&bars[3 * MAX_STAGES]);      // accumulator buffer full (2)
-    const uint32_t acce0 = smem_u32(&bars[3 * MAX_STAGES + 2]);  // accumulator buffer drained (2)
+    const uint32_t rawfull0 = smem_u32(&bars[0]);                          // raw A tile landed
+    const uint32_t rawempty0 = smem_u32(&bars[MAX_RS]);                    // raw A tile consumed by the splitter
+    const uint32_t split0 = smem_u32(&bars[2 * MAX_RS]);                   // A_hi / A_lo written
+    const uint32_t aempty0 = smem_u32(&bars[2 * MAX_RS + MAX_MS]);         // MMAs that read A_hi / A_lo are done
+    const uint32_t bfull0 = smem_u32(&bars[2 * MAX_RS + 2 * MAX_MS]);      // B tiles landed
+    const uint32_t bempty0 = smem_u32(&bars[2 * MAX_RS + 2 * MAX_MS + MAX_BS]);
+    const uint32_t accf0 = smem_u32(&bars[2 * MAX_RS + 2 * MAX_MS + 2 * MAX_BS]);      // accumulator buffer full (2)
+    const uint32_t acce0 = accf0 + 16;                                                 // accumulator buffer drained (2)
 
     constexpr int npad = NPADC;
-    const uint32_t A_BYTES = BM * BK * 4;                        // 16 KB
-    const uint32_t B_BYTES = (uint32_t)npad * BK * 4;
-    // stage layout: [raw A (TRANS only)] [A_hi] [A_lo] [B_hi] [B_lo]; in NN mode the raw tile is split in place
-    const uint32_t RAW_BYTES = TRANS ? A_BYTES : 0u;
-    const uint32_t STAGE_BYTES = RAW_BYTES + 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t A_BYTES = BM * BK * 4;                    // 16 KB
+    constexpr uint32_t B_BYTES = (uint32_t)NPADC * BK * 4;
+    const uint32_t raw_base = smem_base;
+    const uint32_t bt_base = raw_base + RS * A_BYTES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(split0 + 8 * s, 4);        // one arrival per splitter warp
-            mbar_init(empty0 + 8 * s, 1);
-        }
+        for (int s = 0; s < RS; ++s) { mbar_init(rawfull0 + 8 * s, 1); mbar_init(rawempty0 + 8 * s, 4); }
+        for (int s = 0; s < MS; ++s) { mbar_init(split0 + 8 * s, 4); mbar_init(aempty0 + 8 * s, 1); }
+        for (int s = 0; s < BS; ++s) { mbar_init(bfull0 + 8 * s, 1); mbar_init(bempty0 + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -182,36 +216,52 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t tmem_base = tmem_base_smem;
 
     const int kblocks_all = (prm.K + BK - 1) / BK;
-    const int total_items = prm.m_tiles * prm.splits;      // NN: splits == 1
-    // work item -> (tile along M, k-block range)
+    const int total_items = prm.m_tiles * prm.splits * prm.nchunks;      // NN: splits == 1
+    // work item -> (column chunk, tile along M, k-block range)
 #define RC_ITEM(t)                                                                         \
-    const int mt_ = (t) % prm.m_tiles, sp_ = (t) / prm.m_tiles;                            \
+    const int ch_ = (t) % prm.nchunks, rest_ = (t) / prm.nchunks;                          \
+    const int mt_ = rest_ % prm.m_tiles, sp_ = rest_ / prm.m_tiles;                        \
     const int kb0_ = sp_ * prm.kb_per_split;                                               \
     const int kb1_ = min(kblocks_all, kb0_ + prm.kb_per_split);                            \
     const int kblocks = kb1_ - kb0_;                                                       \
-    (void)mt_; (void)sp_; (void)kblocks;
+    (void)mt_; (void)sp_; (void)kblocks; (void)ch_;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer: raw A tiles =====================
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
+            int rs = 0; uint32_t rph = 0;
             for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
                 RC_ITEM(t)
                 const int m0 = mt_ * BM;
                 for (int kb = kb0_; kb < kb1_; ++kb) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1u);
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    const uint32_t fb = full0 + 8 * stage;
-                    mbar_expect_tx(fb, A_BYTES + 2 * B_BYTES);
+                    mbar_wait(rawempty0 + 8 * rs, rph ^ 1u);
+                    const uint32_t sa = raw_base + rs * A_BYTES;
+                    const uint32_t fb = rawfull0 + 8 * rs;
+                    mbar_expect_tx(fb, A_BYTES);
                     if (!TRANS) {
                         tma_load_2d(sa, &tmA, kb * BK, m0, fb);                                   // [128 rows][32 k]
                     } else {
 #pragma unroll
                         for (int b = 0; b < BM / 32; ++b) tma_load_2d(sa + b * 4096, &tmA, m0 + 32 * b, kb * BK, fb);   // raw [32 k][32 i] x 4
                     }
-                    tma_load_2d(sa + RAW_BYTES + 2 * A_BYTES, &tmBhi, kb * BK, 0, fb);            // [npad rows][32 k]
-                    tma_load_2d(sa + RAW_BYTES + 2 * A_BYTES + B_BYTES, &tmBlo, kb * BK, 0, fb);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++rs == RS) { rs = 0; rph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===================== TMA producer: X_hi^T / X_lo^T tiles =====================
+        if (lane == 0) {
+            int bs = 0; uint32_t bph = 0;
+            for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+                RC_ITEM(t)
+                for (int kb = kb0_; kb < kb1_; ++kb) {
+                    mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
+                    const uint32_t sb = bt_base + bs * 2 * B_BYTES;
+                    const uint32_t fb = bfull0 + 8 * bs;
+                    mbar_expect_tx(fb, 2 * B_BYTES);
+                    tma_load_2d(sb, &tmBhi, kb * BK, ch_ * npad, fb);                             // [npad rows][32 k]
+                    tma_load_2d(sb + B_BYTES, &tmBlo, kb * BK, ch_ * npad, fb);
+                    if (++bs == BS) { bs = 0; bph ^= 1u; }
                 }
             }
         }
@@ -219,7 +269,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ===================== MMA issuer (one elected thread) =====================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32((uint32_t)npad);
-            int stage = 0; uint32_t phase = 0;
+            int ms = 0; uint32_t mph = 0;
+            int bs = 0; uint32_t bph = 0;
             int it = 0;                                              // counts K-chunks (TMEM buffer hand-offs)
             for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
                 RC_ITEM(t)
@@ -231,82 +282,86 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * npad);
                     const int kc1 = min(kblocks, kc0 + KC);
                     for (int kb = kc0; kb < kc1; ++kb) {
-                        mbar_wait(split0 + 8 * stage, phase);
+                        mbar_wait(bfull0 + 8 * bs, bph);
+                        mbar_wait(split0 + 8 * ms, mph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                        const uint32_t a_hi = sa + RAW_BYTES, a_lo = a_hi + A_BYTES, b_hi = a_lo + A_BYTES, b_lo = b_hi + B_BYTES;
+                        const uint32_t a_hi = tmem_base + (uint32_t)(2 * npad + ms * A_TMEM_COLS), a_lo = a_hi + 32u;
+                        const uint32_t b_hi = bt_base + bs * 2 * B_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {
-                            // K-major: 8 floats along K inside the swizzle row; MN-major: next group of 8 k-rows
+                            // B K-major: 8 floats along K inside the swizzle row; A: 8 TMEM columns per K-step
                             const uint32_t koff = (uint32_t)k * 32u;
-                            const uint64_t dah = umma_desc_sw128(a_hi + koff), dal = umma_desc_sw128(a_lo + koff);
                             const uint64_t dbh = umma_desc_sw128(b_hi + koff), dbl = umma_desc_sw128(b_lo + koff);
                             // small terms first, then the dominant one
-                            umma_tf32(d_tmem, dal, dbh, idesc, (kb != kc0 || k != 0) ? 1u : 0u);
-                            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                            umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                            umma_tf32_ts(d_tmem, a_lo + 8u * k, dbh, idesc, (kb != kc0 || k != 0) ? 1u : 0u);
+                            umma_tf32_ts(d_tmem, a_hi + 8u * k, dbl, idesc, 1u);
+                            umma_tf32_ts(d_tmem, a_hi + 8u * k, dbh, idesc, 1u);
                         }
-                        umma_commit(empty0 + 8 * stage);             // frees the stage when the MMAs retire
+                        umma_commit(aempty0 + 8 * ms);               // frees the rings' slots when the MMAs retire
+                        umma_commit(bempty0 + 8 * bs);
                         if (kb == kc1 - 1) umma_commit(accf0 + 8 * buf);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        if (++ms == MS) { ms = 0; mph ^= 1u; }
+                        if (++bs == BS) { bs = 0; bph ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp < 6) {
-        // ===================== splitter: A -> (A_hi in place, A_lo) =====================
-        const int st = tid - 64;                                     // 0..127
-        int stage = 0; uint32_t phase = 0;
+        // ===================== splitter: raw A tile (smem) -> A_hi, A_lo (TMEM) =====================
+        // thread <-> tile row: a warp may only touch the TMEM lane quadrant (warp % 4)
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        int rs = 0; uint32_t rph = 0;
+        int ms = 0; uint32_t mph = 0;
+        const unsigned char* const smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
         for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
             RC_ITEM(t)
             for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(full0 + 8 * stage, phase);
-                unsigned char* base = smem_dyn + (smem_base - smem_u32(smem_dyn)) + (size_t)stage * STAGE_BYTES;
+                mbar_wait(rawfull0 + 8 * rs, rph);
+                const unsigned char* rawp = smem_al + (size_t)rs * A_BYTES;
+                float vals[32];
                 if (!TRANS) {
-                    float4* raw = reinterpret_cast<float4*>(base);
-                    float4* lo = reinterpret_cast<float4*>(base + A_BYTES);
+                    // row `row` of the [128 rows][32 k] tile: 16-byte chunk j sits at chunk position j ^ (row & 7)
+                    // (SWIZZLE_128B), so the eight LDS.128 of a quarter-warp hit all 32 banks
+                    const unsigned char* rp = rawp + row * 128;
 #pragma unroll
-                    for (int i = 0; i < (int)(A_BYTES / 16 / 128); ++i) {
-                        const int idx = st + 128 * i;
-                        float4 v = raw[idx], h, l;
-                        uint32_t u;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
-                        raw[idx] = h;
-                        lo[idx] = l;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 v = *reinterpret_cast<const float4*>(rp + ((j ^ (row & 7)) << 4));
+                        vals[4 * j + 0] = v.x; vals[4 * j + 1] = v.y; vals[4 * j + 2] = v.z; vals[4 * j + 3] = v.w;
                     }
                 } else {
-                    // Transposing split: the raw tile is 4 boxes of [32 k][32 i] (the contraction index is the
-                    // row index of A).  Thread `st` owns output row i = st of the K-major [128 i][32 k] tiles:
-                    // 32 conflict-free LDS.32 (a warp reads one 128-byte row per k), split, then 2 x 8 STS.128
-                    // into the SWIZZLE_128B positions UMMA expects for a K-major operand.
-                    const int bx = st >> 5, ci = st & 31;
-                    const unsigned char* rawb = base + bx * 4096;
-                    float4* hi = reinterpret_cast<float4*>(base + A_BYTES);
-                    float4* lo = reinterpret_cast<float4*>(base + 2 * A_BYTES);
-                    float vals[32];
+                    // the raw tile is 4 boxes of [32 k][32 i] (the contraction index is the row index of A);
+                    // this thread owns tile row i = row: 32 conflict-free LDS.32 (a warp reads one 128-byte row per k)
+                    const unsigned char* rawb = rawp + quad * 4096;
 #pragma unroll
                     for (int k = 0; k < 32; ++k)
-                        vals[k] = *reinterpret_cast<const float*>(rawb + k * 128 + ((((ci >> 2) ^ (k & 7)) << 4) | ((ci & 3) << 2)));
-#pragma unroll
-                    for (int cch = 0; cch < 8; ++cch) {
-                        float4 h, l;
-                        uint32_t u;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[4 * cch + 0])); h.x = __uint_as_float(u); l.x = vals[4 * cch + 0] - h.x;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[4 * cch + 1])); h.y = __uint_as_float(u); l.y = vals[4 * cch + 1] - h.y;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[4 * cch + 2])); h.z = __uint_as_float(u); l.z = vals[4 * cch + 2] - h.z;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[4 * cch + 3])); h.w = __uint_as_float(u); l.w = vals[4 * cch + 3] - h.w;
-                        const int dst = st * 8 + (cch ^ (st & 7));       // float4 index: row st, swizzled 16-byte chunk
-                        hi[dst] = h;
-                        lo[dst] = l;
-                    }
+                        vals[k] = *reinterpret_cast<const float*>(rawb + k * 128 + ((((lane >> 2) ^ (k & 7)) << 4) | ((lane & 3) << 2)));
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    uint32_t u;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[k]));
+                    hi[k] = u;
+                    lo[k] = __float_as_uint(vals[k] - __uint_as_float(u));
+                }
+                mbar_wait(aempty0 + 8 * ms, mph ^ 1u);                   // MMAs that read this TMEM stage are done
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * npad + ms * A_TMEM_COLS);
+                tmem_st32(ta, hi);
+                tmem_st32(ta + 32u, lo);
+                // The raw slot is released only BEHIND the tcgen05.st: they cannot issue before the LDS results
+                // are in registers.  (An arrive placed right after the loads issues behind the LDS *issue*, and
+                // when the load/store pipe is backed up by the epilogue's store burst the TMA refill of the slot
+                // overtook the loads: whole lane-quadrants of wrong rows on CTAs with more than one work item.)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(split0 + 8 * stage);
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                if (lane == 0) mbar_arrive(rawempty0 + 8 * rs);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(split0 + 8 * ms);
+                if (++rs == RS) { rs = 0; rph ^= 1u; }
+                if (++ms == MS) { ms = 0; mph ^= 1u; }
             }
         }
     } else {
@@ -342,10 +397,22 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             const int row = mt_ * BM + lg * 32 + lane;
             if (row < prm.M) {
-                float* yrow = prm.y + (int64_t)sp_ * prm.part_stride + (int64_t)row * prm.ldy;
+                float* yrow = prm.y + (int64_t)sp_ * prm.part_stride + (int64_t)row * prm.ldy + ch_ * npad;
+                const int nvalid = prm.N - ch_ * npad;
+                if (prm.vec_store) {          // 16-byte stores: a quarter of the LSU transactions of scalar stores
 #pragma unroll
-                for (int j = 0; j < NPADC; ++j)
-                    if (j < prm.N) yrow[j] = acc[j];
+                    for (int j = 0; j < NPADC; j += 4) {
+                        if (j + 3 < nvalid) *reinterpret_cast<float4*>(yrow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                        else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) if (j + q < nvalid) yrow[j + q] = acc[j + q];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NPADC; ++j)
+                        if (j < nvalid) yrow[j] = acc[j];
+                }
             }
         }
     }
@@ -373,25 +440,30 @@ __global__ void split_transpose_kernel(const float* __restrict__ x, int64_t ldx,
     }
 }
 
-template <int STAGES, int NPADC, bool TRANS>
+template <int RS, int MS, int BS, int NPADC, bool TRANS>
 void launch_tf32(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
-                 const Tf32Params& prm) {
-    constexpr size_t stage_bytes = (TRANS ? 3 : 2) * (size_t)BM * BK * 4 + 2 * (size_t)NPADC * BK * 4;
-    constexpr size_t smem = STAGES * stage_bytes + 1024;
-    static_assert(smem <= 227 * 1024, "stage configuration exceeds shared memory");
-    RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<STAGES, NPADC, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = std::min(prm.m_tiles * prm.splits, c->sm_count);
-    tf32x3_gemm_kernel<STAGES, NPADC, TRANS><<<grid, NTHREADS, smem, c->stream>>>(tmA, tmBhi, tmBlo, prm);
+                 Tf32Params prm) {
+    static_assert(RS <= MAX_RS && MS <= MAX_MS && BS <= MAX_BS, "ring depth");
+    static_assert(2 * NPADC + MS * A_TMEM_COLS <= 512, "tensor memory columns");
+    constexpr size_t smem = (size_t)RS * BM * BK * 4 + (size_t)BS * 2 * NPADC * BK * 4 + 1024;
+    static_assert(smem <= 226 * 1024, "ring configuration exceeds shared memory");
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * NPADC + MS * A_TMEM_COLS)) cols <<= 1;
+    prm.tmem_cols = cols;
+    prm.vec_store = ((reinterpret_cast<uintptr_t>(prm.y) & 15) == 0 && (prm.ldy & 3) == 0 && (prm.part_stride & 3) == 0) ? 1 : 0;
+    RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<RS, MS, BS, NPADC, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = std::min(prm.m_tiles * prm.splits * prm.nchunks, c->sm_count);
+    tf32x3_gemm_kernel<RS, MS, BS, NPADC, TRANS><<<grid, NTHREADS, smem, c->stream>>>(tmA, tmBhi, tmBlo, prm);
     RC_CHECK_LAUNCH(c);
 }
 template <bool TRANS>
 void dispatch_tf32(rc_ctx* c, int npad, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
                    const Tf32Params& prm) {
-    switch (npad) {
-        case 32: launch_tf32<(TRANS ? 3 : 4), 32, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;
-        case 64: launch_tf32<(TRANS ? 3 : 4), 64, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;
-        case 96: launch_tf32<(TRANS ? 3 : 4), 96, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;
-        default: launch_tf32<(TRANS ? 2 : 3), 128, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;
+    switch (npad) {      //      raw (smem)  A hi/lo (TMEM)  X^T (smem)
+        case 32: launch_tf32<8, 3, 4, 32, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 32 KB
+        case 64: launch_tf32<8, 3, 4, 64, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 64 KB
+        case 96: launch_tf32<7, 3, 4, 96, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 112 + 96 KB
+        default: launch_tf32<6, 3, 4, 128, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;    // 96 + 128 KB
     }
 }
 
@@ -416,32 +488,30 @@ bool gemm_tf32x3_f32(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float* A,
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3)) return false;      // TMA: 16-byte base and pitch
     if (M > (1LL << 30) || K > (1LL << 30)) return false;
     // columns are processed in chunks of at most 128 (the promoted FP32 accumulator of a row lives in
-    // the registers of one epilogue thread)
-    int64_t nchunks = (N + 127) / 128;
-    int64_t per = ((N + nchunks - 1) / nchunks + 31) / 32 * 32;
-    int64_t ldt = (K + 3) / 4 * 4;
-    for (int64_t n0 = 0; n0 < N; n0 += per) {
-        const int ncols = (int)std::min<int64_t>(per, N - n0);
-        const int npad = (ncols + 31) / 32 * 32;          // 32, 64, 96 or 128
-        DevBuf<float> hiT(c, (size_t)npad * ldt), loT(c, (size_t)npad * ldt);
-        {
-            int64_t total = (int64_t)npad * K;
-            int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-            split_transpose_kernel<<<nb, 256, 0, c->stream>>>(X + n0, ldx, (int)K, ncols, npad, hiT.p, loT.p, ldt);
-            RC_CHECK_LAUNCH(c);
-        }
-        CUtensorMap tmA = make_map_f32(A, M, K, lda, BM);
-        CUtensorMap tmBhi = make_map_f32(hiT.p, npad, K, ldt, npad);
-        CUtensorMap tmBlo = make_map_f32(loT.p, npad, K, ldt, npad);
-        Tf32Params prm;
-        prm.y = Y + n0; prm.ldy = ldy; prm.M = (int)M; prm.N = ncols; prm.K = (int)K; prm.npad = npad;
-        prm.m_tiles = (int)((M + BM - 1) / BM);
-        uint32_t cols = 32;
-        while (cols < (uint32_t)(2 * npad)) cols <<= 1;
-        prm.tmem_cols = cols;
-        prm.splits = 1; prm.kb_per_split = (int)((K + BK - 1) / BK); prm.part_stride = 0;
-        dispatch_tf32<false>(c, npad, tmA, tmBhi, tmBlo, prm);
+    // the registers of one epilogue thread); all chunks run in ONE launch, chunk-fastest (Tf32Params)
+    const int nchunks = (int)((N + 127) / 128);
+    const int npad = (int)(((N + nchunks - 1) / nchunks + 31) / 32 * 32);          // 32, 64, 96 or 128
+    const int64_t ldt = (K + 3) / 4 * 4;
+    const int nrows = nchunks * npad;                   // stacked X^T: column j of X is row j
+    DevBuf<float> hiT(c, (size_t)nrows * ldt), loT(c, (size_t)nrows * ldt);
+    {
+        int64_t total = (int64_t)nrows * K;
+        int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+        split_transpose_kernel<<<nb, 256, 0, c->stream>>>(X, ldx, (int)K, (int)N, nrows, hiT.p, loT.p, ldt);
+        RC_CHECK_LAUNCH(c);
     }
+    CUtensorMap tmA = make_map_f32(A, M, K, lda, BM);
+    CUtensorMap tmBhi = make_map_f32(hiT.p, nrows, K, ldt, npad);
+    CUtensorMap tmBlo = make_map_f32(loT.p, nrows, K, ldt, npad);
+    Tf32Params prm;
+    prm.y = Y; prm.ldy = ldy; prm.M = (int)M; prm.N = (int)N; prm.K = (int)K; prm.npad = npad;
+    prm.m_tiles = (int)((M + BM - 1) / BM);
+    prm.nchunks = nchunks;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * npad)) cols <<= 1;
+    prm.tmem_cols = cols;
+    prm.splits = 1; prm.kb_per_split = (int)((K + BK - 1) / BK); prm.part_stride = 0;
+    dispatch_tf32<false>(c, npad, tmA, tmBhi, tmBlo, prm);
     c->gemm_flops += 2 * M * N * K;
     return true;
 }
@@ -454,50 +524,49 @@ bool gemm_tf32x3_f32_tn(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float*
     if (M <= 0 || N <= 0 || K <= 0) return false;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3)) return false;
     if (M > (1LL << 30) || K > (1LL << 30)) return false;
-    int64_t nchunks = (N + 127) / 128;
-    int64_t per = ((N + nchunks - 1) / nchunks + 31) / 32 * 32;
+    const int nchunks = (int)((N + 127) / 128);
+    const int npad = (int)(((N + nchunks - 1) / nchunks + 31) / 32 * 32);
+    const int nrows = nchunks * npad;
     const int64_t kblocks = (K + BK - 1) / BK;
-    for (int64_t n0 = 0; n0 < N; n0 += per) {
-        const int ncols = (int)std::min<int64_t>(per, N - n0);
-        const int npad = (ncols + 31) / 32 * 32;
-        // B operand K-major: Y^T split into hi / lo once (Y is the small m x l matrix)
-        const int64_t ldt = (K + 3) / 4 * 4;
-        DevBuf<float> hi(c, (size_t)npad * ldt), lo(c, (size_t)npad * ldt);
-        {
-            int64_t total = (int64_t)npad * K;
-            int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-            split_transpose_kernel<<<nb, 256, 0, c->stream>>>(Y + n0, ldy, (int)K, ncols, npad, hi.p, lo.p, ldt);
-            RC_CHECK_LAUNCH(c);
-        }
-        CUtensorMap tmA = make_map_f32(A, K, M, lda, 32);           // boxes [32 k rows][32 cols]
-        CUtensorMap tmBhi = make_map_f32(hi.p, npad, K, ldt, npad);
-        CUtensorMap tmBlo = make_map_f32(lo.p, npad, K, ldt, npad);
-        Tf32Params prm;
-        prm.M = (int)M; prm.N = ncols; prm.K = (int)K; prm.npad = npad;
-        prm.m_tiles = (int)((M + BM - 1) / BM);
-        uint32_t cols = 32;
-        while (cols < (uint32_t)(2 * npad)) cols <<= 1;
-        prm.tmem_cols = cols;
-        // split-K: about 2 work items per SM, each at least KC k-blocks
-        int64_t want = std::max<int64_t>(1, (2LL * c->sm_count + prm.m_tiles - 1) / prm.m_tiles);
-        int64_t maxs = std::max<int64_t>(1, kblocks / KC);
-        int splits = (int)std::min(want, maxs);
-        int64_t kbps = ((kblocks + splits - 1) / splits + KC - 1) / KC * KC;
-        splits = (int)((kblocks + kbps - 1) / kbps);
-        prm.splits = splits; prm.kb_per_split = (int)kbps;
-        DevBuf<float> part;
-        if (splits == 1) { prm.y = Z + n0; prm.ldy = ldz; prm.part_stride = 0; }
-        else {
-            part.alloc(c, (size_t)splits * M * npad);
-            prm.y = part.p; prm.ldy = npad; prm.part_stride = M * (int64_t)npad;
-        }
-        dispatch_tf32<true>(c, npad, tmA, tmBhi, tmBlo, prm);
-        if (splits > 1) {
-            int64_t n = M * (int64_t)ncols;
-            int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-            tf32_reduce_kernel<<<nb, 256, 0, c->stream>>>(M, ncols, splits, part.p, npad, prm.part_stride, Z + n0, ldz);
-            RC_CHECK_LAUNCH(c);
-        }
+    // B operand K-major: Y^T split into hi / lo once (Y is the small m x l matrix), chunks stacked
+    const int64_t ldt = (K + 3) / 4 * 4;
+    DevBuf<float> hi(c, (size_t)nrows * ldt), lo(c, (size_t)nrows * ldt);
+    {
+        int64_t total = (int64_t)nrows * K;
+        int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+        split_transpose_kernel<<<nb, 256, 0, c->stream>>>(Y, ldy, (int)K, (int)N, nrows, hi.p, lo.p, ldt);
+        RC_CHECK_LAUNCH(c);
+    }
+    CUtensorMap tmA = make_map_f32(A, K, M, lda, 32);           // boxes [32 k rows][32 cols]
+    CUtensorMap tmBhi = make_map_f32(hi.p, nrows, K, ldt, npad);
+    CUtensorMap tmBlo = make_map_f32(lo.p, nrows, K, ldt, npad);
+    Tf32Params prm;
+    prm.M = (int)M; prm.N = (int)N; prm.K = (int)K; prm.npad = npad;
+    prm.m_tiles = (int)((M + BM - 1) / BM);
+    prm.nchunks = nchunks;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * npad)) cols <<= 1;
+    prm.tmem_cols = cols;
+    // split-K: about 2 work items per SM, each at least KC k-blocks
+    const int64_t base_items = (int64_t)prm.m_tiles * nchunks;
+    int64_t want = std::max<int64_t>(1, (2LL * c->sm_count + base_items - 1) / base_items);
+    int64_t maxs = std::max<int64_t>(1, kblocks / KC);
+    int splits = (int)std::min(want, maxs);
+    int64_t kbps = ((kblocks + splits - 1) / splits + KC - 1) / KC * KC;
+    splits = (int)((kblocks + kbps - 1) / kbps);
+    prm.splits = splits; prm.kb_per_split = (int)kbps;
+    DevBuf<float> part;
+    if (splits == 1) { prm.y = Z; prm.ldy = ldz; prm.part_stride = 0; }
+    else {
+        part.alloc(c, (size_t)splits * M * nrows);
+        prm.y = part.p; prm.ldy = nrows; prm.part_stride = M * (int64_t)nrows;
+    }
+    dispatch_tf32<true>(c, npad, tmA, tmBhi, tmBlo, prm);
+    if (splits > 1) {
+        int64_t n = M * N;
+        int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+        tf32_reduce_kernel<<<nb, 256, 0, c->stream>>>(M, (int)N, splits, part.p, nrows, prm.part_stride, Z, ldz);
+        RC_CHECK_LAUNCH(c);
     }
     c->gemm_flops += 2 * M * N * K;
     return true;

@@ -83,7 +83,8 @@ void gemm(rc_ctx* c, RcOp opa, RcOp opb, int64_t M, int64_t N, int64_t K, const 
             if (opa == RC_OP_N || opa == RC_OP_H)
                 if (gemm_dmma_c64(c, opa == RC_OP_H, M, N, K, A, lda, B, ldb, C, ldc)) return;
         } else if constexpr (std::is_same<T, float>::value) {
-            if (opa == RC_OP_N && M >= 128) {
+            // (fewer than ~1/4 of the SMs' worth of 128-row tiles and a long K: the split-K SIMT tiles win)
+            if (opa == RC_OP_N && M >= 128 && (M >= 128 * 37 || K < 4096)) {
                 if (gemm_tf32x3_f32(c, M, N, K, A, lda, B, ldb, C, ldc)) return;
             } else if (opa != RC_OP_N && M >= 128 && K >= 256) {
                 if (gemm_tf32x3_f32_tn(c, M, N, K, A, lda, B, ldb, C, ldc)) return;
@@ -490,10 +491,21 @@ rc_matrix* sample_adaptive_impl(rc_ctx* c, const rc_matrix* a, double rel_tol_in
     MatPtr y(matmat_impl<T>(c, a, omega));                                       // :239
     const R operator_norm = (R)max_col_norm_impl<T>(c, y.get()) * tol_factor;    // :241
     R max_norm = operator_norm;
-    MatPtr qbuf(mat_new(c, a->dtype, m, cap)), bbuf(mat_new(c, a->dtype, cap, n));
+    // Q (m x cur) and B (cur x n) grow geometrically (the rank is not known in advance and the crate's
+    // only bound is min(m, n): pre-allocating that would be two A-sized buffers)
+    int64_t cur = std::min<int64_t>(cap, std::max<int64_t>(8 * s, 512));
+    MatPtr qbuf(mat_new(c, a->dtype, m, cur)), bbuf(mat_new(c, a->dtype, cur, n));
     int64_t r = 0;
     while (max_norm / operator_norm >= rel_tol) {                                // :248
         if (r + s > max_rank) RC_THROW(RC_COMPRESSION_ERROR, "adaptive sampler exceeded max_rank %lld", (long long)max_rank);
+        if (r + s > cur) {
+            const int64_t grown = std::min<int64_t>(cap, std::max<int64_t>(2 * cur, r + s));
+            MatPtr q2(mat_new(c, a->dtype, m, grown)), b2(mat_new(c, a->dtype, grown, n));
+            k_copy<T>(c, P<T>(q2.get()), q2->ld, P<T>(qbuf.get()), qbuf->ld, m, r);
+            k_copy<T>(c, P<T>(b2.get()), b2->ld, P<T>(bbuf.get()), bbuf->ld, r, n);
+            qbuf.reset(q2.release()); bbuf.reset(b2.release());
+            cur = grown;
+        }
         if (r > 0) {                                                             // :250-252
             DevBuf<T> t(c, (size_t)r * s);
             gemm<T>(c, RC_OP_H, RC_OP_N, r, s, m, P<T>(qbuf.get()), qbuf->ld, P<T>(y.get()), y->ld, t.p, s, rc_one<T>(), rc_zero<T>());
@@ -520,14 +532,31 @@ rc_matrix* sample_adaptive_impl(rc_ctx* c, const rc_matrix* a, double rel_tol_in
     }
     MatPtr q(mat_slice<T>(c, qbuf.get(), 0, m, 0, r));
     inherit_shard(q.get(), a);
+    if (a->owns) {      // B = Q^H A is a by-product: keep it with Q for compute_from_range_estimate
+        q->companion = mat_slice<T>(c, bbuf.get(), 0, r, 0, n);
+        q->companion_op_id = a->id;
+    }
     return q.release();
+}
+
+// A^H Q (n x k) for a range estimate Q: the conj_matmat of src/qr.rs:315 / src/svd.rs:175, or -- when Q
+// came out of the adaptive sampler on this very operator -- the transpose of the B = Q^H A it built.
+template <class T>
+rc_matrix* ah_range(rc_ctx* c, const rc_matrix* op, const rc_matrix* range) {
+    const rc_matrix* b = range->companion;
+    if (c->reuse_range_b && b && op->owns && range->companion_op_id == op->id && b->rows == range->cols &&
+        b->cols == op->cols && b->dtype == op->dtype) {
+        c->range_b_reused++;
+        return mat_conj_transpose<T>(c, b);
+    }
+    return conj_matmat_impl<T>(c, op, range);
 }
 
 // QRTraits::compute_from_range_estimate (src/qr.rs:311-323)
 template <class T>
 void qr_from_range_impl(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, QrParts& out) {
     RC_REQUIRE(range->rows == op->rows, "range estimate and operator row counts differ");
-    MatPtr z(conj_matmat_impl<T>(c, op, range));                 // A^H Q  (n x k)
+    MatPtr z(ah_range<T>(c, op, range));                         // A^H Q  (n x k)
     QrParts qb;
     pivoted_qr_impl<T>(c, z.get(), true, -1, false, qb);         // pivoted QR of b = (A^H Q)^H, :315-316
     out.q.reset(mat_mul<T>(c, RC_OP_N, range, RC_OP_N, qb.q.get()));   // :319
@@ -540,7 +569,7 @@ void qr_from_range_impl(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, 
 template <class T>
 void svd_from_range_impl(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, SvdParts& out) {
     RC_REQUIRE(range->rows == op->rows, "range estimate and operator row counts differ");
-    MatPtr z(conj_matmat_impl<T>(c, op, range));                 // A^H Q = b^H  (n x k)
+    MatPtr z(ah_range<T>(c, op, range));                         // A^H Q = b^H  (n x k)
     SvdParts sb;
     svd_impl<T>(c, z.get(), true, sb);                           // SVD of b, :175-176
     out.u.reset(mat_mul<T>(c, RC_OP_N, range, RC_OP_N, sb.u.get()));   // :179
@@ -756,6 +785,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
         if (!strcmp(key, "gemm_impl")) c->gemm_impl = (int)v;
         else if (!strcmp(key, "true_power_iteration")) c->true_power_iteration = (int)v;
         else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;
+        else if (!strcmp(key, "reuse_range_b")) c->reuse_range_b = (int)v;
         else RC_THROW(RC_INVALID_ARGUMENT, "unknown option '%s'", key);
     });
 }
@@ -768,13 +798,14 @@ rc_status rc_ctx_get_counter(rc_ctx* c, const char* key, int64_t* out) {
         else if (!strcmp(key, "d2h_bytes")) *out = c->d2h_bytes;
         else if (!strcmp(key, "cholqr_used")) *out = c->cholqr_used;
         else if (!strcmp(key, "cholqr_fallbacks")) *out = c->cholqr_fallbacks;
+        else if (!strcmp(key, "range_b_reused")) *out = c->range_b_reused;
         else RC_THROW(RC_INVALID_ARGUMENT, "unknown counter '%s'", key);
     });
 }
 rc_status rc_ctx_reset_counters(rc_ctx* c) {
     if (!c) return RC_INVALID_ARGUMENT;
     c->launches = c->gemm_flops = c->h2d_bytes = c->d2h_bytes = 0;
-    c->cholqr_used = c->cholqr_fallbacks = 0;
+    c->cholqr_used = c->cholqr_fallbacks = c->range_b_reused = 0;
     return RC_OK;
 }
 
@@ -834,6 +865,7 @@ rc_status rc_matrix_wrap_device(rc_ctx* c, rc_dtype dt, void* dptr, int64_t rows
         RC_REQUIRE(dt >= 0 && dt <= 3 && dptr && rows >= 0 && cols >= 0 && ld >= cols, "bad arguments");
         rc_matrix* m = new rc_matrix();
         m->ctx = c; m->dtype = dt; m->rows = rows; m->cols = cols; m->ld = ld; m->data = dptr; m->owns = false;
+        m->id = rc_next_matrix_id();
         *out = m;
     });
 }

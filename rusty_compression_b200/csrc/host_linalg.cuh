@@ -2,6 +2,7 @@
 // by host_api.cu).  Every routine cites the reference lines whose behaviour it reproduces.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -14,11 +15,16 @@ inline int64_t rc_pad_ld(int dtype, int64_t cols) {
     return std::max<int64_t>((cols + e - 1) / e * e, e);
 }
 
+inline uint64_t rc_next_matrix_id() {
+    static std::atomic<uint64_t> next{1};
+    return next.fetch_add(1);
+}
 inline rc_matrix* mat_new(rc_ctx* c, int dtype, int64_t rows, int64_t cols) {
     RC_REQUIRE(rows >= 0 && cols >= 0, "negative matrix dimension");
     std::unique_ptr<rc_matrix> m(new rc_matrix());
     m->ctx = c; m->dtype = dtype; m->rows = rows; m->cols = cols; m->ld = rc_pad_ld(dtype, cols);
     m->owns = true;
+    m->id = rc_next_matrix_id();
     size_t bytes = (size_t)std::max<int64_t>(rows, 1) * m->ld * rc_dtype_size(dtype);
     RC_CUDA(cudaMallocAsync(&m->data, bytes, c->stream));
     return m.release();
@@ -26,6 +32,7 @@ inline rc_matrix* mat_new(rc_ctx* c, int dtype, int64_t rows, int64_t cols) {
 inline void mat_free(rc_matrix* m) {
     if (!m) return;
     if (m->owns && m->data) cudaFreeAsync(m->data, m->ctx->stream);
+    if (m->companion) mat_free(m->companion);
     delete m;
 }
 struct MatPtr {   // RAII owner used while a routine can still throw

@@ -58,27 +58,27 @@ __device__ __forceinline__ void larfg_dev(T alpha, double xnorm2, T& tau, T& sca
     beta = rc_make<T>(b, 0.0);
 }
 
-// W: p x n column-major (ld = ldw).  Work arrays: vn (n doubles), lpos (n ints),
-// slots: 2 * gridDim.x Cand + 2 * gridDim.x ints (displaced column).
-template <class T, int NT, bool SMEM>
+// L1-bypassing load: the pivot column was last written by another SM (before the grid-wide sync)
+// and a 128-byte line may straddle two columns owned by different SMs, so never serve it from L1.
+__device__ __forceinline__ float  ld_cg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ c32 ld_cg(const c32* p) { float2 v = __ldcg(reinterpret_cast<const float2*>(p)); return c32(v.x, v.y); }
+__device__ __forceinline__ c64 ld_cg(const c64* p) { double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return c64(v.x, v.y); }
+
+// W: p x n column-major (ld = ldw), resident in L2 for the k x n factors of the path (42 MB at
+// config 3).  Work arrays: vn (n doubles), lpos (n ints), slots: 2 * gridDim.x Cand + 2 * gridDim.x
+// ints (displaced column).  One CTA of NT threads per SM; every warp owns the columns
+// c = gw (mod GW) and updates CU of them at a time, so CU independent load -> dot -> shuffle-reduce
+// -> update chains are in flight per warp (the step is latency-bound, not bandwidth-bound).
+template <class T, int NT, int CU>
 __global__ void __launch_bounds__(NT)
-pivqr_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, double* __restrict__ vn_g,
-             int* __restrict__ lpos_g, int* __restrict__ ind, T* __restrict__ vbuf, T* __restrict__ tau_out,
+pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __restrict__ vn,
+             int* __restrict__ lpos, int* __restrict__ ind, T* __restrict__ vbuf, T* __restrict__ tau_out,
              T* __restrict__ diag, Cand* __restrict__ slots, int* __restrict__ slots_disp) {
     constexpr int NW = NT / 32;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* xs = reinterpret_cast<T*>(smem_raw);     // pivot column / reflector, p entries
-    // SMEM: the whole (column-major) matrix lives in shared memory; single CTA, no grid sync
-    T* W = SMEM ? xs + p : Wg;
-    const int64_t ldw = SMEM ? p : ldwg;
-    // SMEM: the norm / logical-position tables live in shared memory too (no global round trips)
-    double* vn = SMEM ? reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(W + (size_t)p * n) + 7) & ~(uintptr_t)7) : vn_g;
-    int* lpos = SMEM ? reinterpret_cast<int*>(vn + n) : lpos_g;
-    if (SMEM) {
-        for (int e = threadIdx.x; e < p * n; e += NT) { int c = e / p, r = e - c * p; W[e] = Wg[(int64_t)c * ldwg + r]; }
-        __syncthreads();
-    }
     __shared__ Cand s_cand[NW];
     __shared__ int s_disp[NW];
     __shared__ double s_red[NW];
@@ -112,35 +112,32 @@ pivqr_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, double* __r
             }
         }
         best = warp_best(best);
-        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 16));
-        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 8));
-        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 4));
-        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 2));
-        disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, 1));
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, m));
         if (lane == 0) { s_cand[warp] = best; s_disp[warp] = disp; }
         __syncthreads();
-        if (!SMEM) {
-            if (tid == 0) {
-                Cand b = s_cand[0]; int d = s_disp[0];
-                for (int w2 = 1; w2 < NW; ++w2) { if (better(s_cand[w2], b)) b = s_cand[w2]; d = max(d, s_disp[w2]); }
+        if (warp == 0) {
+            Cand b; b.val = -1.0; b.lpos = 0x7fffffff; b.phys = -1;
+            int d = -1;
+            if (lane < NW) { b = s_cand[lane]; d = s_disp[lane]; }
+            b = warp_best(b);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, m));
+            if (lane == 0) {
                 slots[(i & 1) * gridDim.x + blockIdx.x] = b;
                 slots_disp[(i & 1) * gridDim.x + blockIdx.x] = d;
             }
-            // (b) one grid-wide sync per step
-            grid.sync();
         }
+        // (b) one grid-wide sync per step
+        grid.sync();
         // (c) global winner (every CTA reduces the same slots -> same answer)
         if (warp == 0) {
             Cand b; b.val = -1.0; b.lpos = 0x7fffffff; b.phys = -1;
             int d = -1;
-            if (SMEM) {
-                if (lane < NW) { b = s_cand[lane]; d = s_disp[lane]; }
-            } else {
-                for (int s = lane; s < (int)gridDim.x; s += 32) {
-                    Cand o = slots[(i & 1) * gridDim.x + s];
-                    if (better(o, b)) b = o;
-                    d = max(d, slots_disp[(i & 1) * gridDim.x + s]);
-                }
+            for (int s = lane; s < (int)gridDim.x; s += 32) {
+                Cand o = slots[(i & 1) * gridDim.x + s];
+                if (better(o, b)) b = o;
+                d = max(d, slots_disp[(i & 1) * gridDim.x + s]);
             }
             b = warp_best(b);
 #pragma unroll
@@ -161,17 +158,19 @@ pivqr_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, double* __r
         const T* pcol = W + (int64_t)pv * ldw;
         double a = 0.0;
         for (int r = i + tid; r < p; r += NT) {
-            T v = pcol[r];
+            T v = ld_cg(pcol + r);
             xs[r] = v;
             if (r > i) a += rc_abs2(v);
         }
         a = rc_warp_sum(a);
         if (lane == 0) s_red[warp] = a;
         __syncthreads();
-        if (tid == 0) {      // one thread derives the reflector scalars (FP64 sqrt/div are long sequences)
-            double xnorm2 = 0.0;
-            for (int w2 = 0; w2 < NW; ++w2) xnorm2 += s_red[w2];
-            larfg_dev<T>(xs[i], xnorm2, s_hs[0], s_hs[1], s_hs[2]);
+        if (warp == 0) {     // every lane of warp 0 derives the same reflector scalars
+            double xnorm2 = (lane < NW) ? s_red[lane] : 0.0;
+            xnorm2 = rc_warp_sum(xnorm2);
+            T t0, t1, t2;
+            larfg_dev<T>(xs[i], xnorm2, t0, t1, t2);
+            if (lane == 0) { s_hs[0] = t0; s_hs[1] = t1; s_hs[2] = t2; }
         }
         __syncthreads();
         const T tau = s_hs[0], scale = s_hs[1], beta = s_hs[2];
@@ -182,25 +181,57 @@ pivqr_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, double* __r
             for (int r = tid; r < p; r += NT) vcol[r] = (r < i) ? rc_zero<T>() : (r == i ? rc_one<T>() : xs[r]);
             if (tid == 0) { tau_out[i] = tau; diag[i] = beta; }
         }
-        // (f) trailing update of owned columns + exact partial norms
+        // (f) trailing update of owned columns + exact partial norms, CU columns per pass
         const T ctau = rc_conj(tau);
-        for (int c = gw; c < n; c += GW) {
-            if (lpos[c] <= i) continue;      // warp-uniform
-            T* col = W + (int64_t)c * ldw;
-            using A = typename AccOf<T>::type;
-            A part = rc_zero<A>();
-            for (int r = i + 1 + lane; r < p; r += 32) part = rc_cfma(rc_widen(xs[r]), rc_widen(col[r]), part);
-            part = rc_warp_sum(part);
-            T ci = col[i];
-            T f = ctau * rc_narrow<T>(rc_widen(ci) + part);
-            double nrm = 0.0;
-            for (int r = i + 1 + lane; r < p; r += 32) {
-                T v = col[r] - f * xs[r];
-                col[r] = v;
-                nrm += rc_abs2(v);
+        using A = typename AccOf<T>::type;
+        for (int c0 = gw; c0 < n; c0 += GW * CU) {
+            T* col[CU];
+            bool act[CU];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < CU; ++j) {
+                const int c = c0 + j * GW;
+                act[j] = (c < n) && (lpos[min(c, n - 1)] > i);      // warp-uniform
+                col[j] = W + (int64_t)min(c, n - 1) * ldw;
+                any |= act[j];
             }
-            nrm = rc_warp_sum(nrm);
-            if (lane == 0) { col[i] = ci - f; vn[c] = sqrt(nrm); }
+            if (!any) continue;
+            A part[CU];
+#pragma unroll
+            for (int j = 0; j < CU; ++j) part[j] = rc_zero<A>();
+            for (int r = i + 1 + lane; r < p; r += 32) {
+                const A xv = rc_widen(xs[r]);
+#pragma unroll
+                for (int j = 0; j < CU; ++j)
+                    if (act[j]) part[j] = rc_cfma(xv, rc_widen(col[j][r]), part[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < CU; ++j) part[j] = rc_warp_sum(part[j]);
+            T ci[CU], f[CU];
+            double nrm[CU];
+#pragma unroll
+            for (int j = 0; j < CU; ++j) {
+                ci[j] = act[j] ? col[j][i] : rc_zero<T>();
+                f[j] = ctau * rc_narrow<T>(rc_widen(ci[j]) + part[j]);
+                nrm[j] = 0.0;
+            }
+            for (int r = i + 1 + lane; r < p; r += 32) {
+                const T xv = xs[r];
+#pragma unroll
+                for (int j = 0; j < CU; ++j)
+                    if (act[j]) {
+                        T v = col[j][r] - f[j] * xv;
+                        col[j][r] = v;
+                        nrm[j] += rc_abs2(v);
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < CU; ++j) nrm[j] = rc_warp_sum(nrm[j]);
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < CU; ++j)
+                    if (act[j]) { col[j][i] = ci[j] - f[j]; vn[c0 + j * GW] = sqrt(nrm[j]); }
+            }
         }
         __syncthreads();   // xs is rewritten next step; lpos/vn written by lane 0 are read by the warp
     }
@@ -208,10 +239,6 @@ pivqr_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, double* __r
     for (int c = gw + lane * GW; c < n; c += 32 * GW) {
         int lp = lpos[c];
         if (lp >= kk) ind[lp] = c;
-    }
-    if (SMEM) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < p * n; e += NT) { int c = e / p, r = e - c * p; Wg[(int64_t)c * ldwg + r] = W[e]; }
     }
 }
 
@@ -362,21 +389,20 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
         pivqr_small_kernel<T, NTS><<<1, NTS, smem_all, c->stream>>>(wc, ldw, pi, ni, kk, ind, vbuf, tau, diag.p);
         RC_CHECK_LAUNCH(c);
     } else {
-        constexpr int NT = 256;
+        constexpr int NT = 1024, CU = std::is_same<T, c64>::value ? 2 : 4;   // c64 x 4 columns spills at 64 registers
         constexpr int NW = NT / 32;
         size_t smem = (size_t)p * sizeof(T);
         RC_REQUIRE(smem + 4096 <= lim, "pivoted_qr: %lld rows exceed the shared-memory column buffer", (long long)p);
-        RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T, NT, CU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pivqr_kernel<T, NT, false>, NT, smem));
+        RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pivqr_kernel<T, NT, CU>, NT, smem));
         RC_REQUIRE(per_sm >= 1, "pivoted_qr: kernel does not fit on an SM");
-        int64_t max_grid = (int64_t)per_sm * c->sm_count;
-        int64_t want = (n + NW * 4 - 1) / (NW * 4);
-        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(max_grid, c->sm_count)));
+        int64_t want = (n + NW * 2 - 1) / (NW * 2);       // at least ~2 columns per warp
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, c->sm_count));
         DevBuf<Cand> slots(c, (size_t)2 * grid);
         DevBuf<int> slots_disp(c, (size_t)2 * grid);
         void* args[] = {&wc, &ldw, &pi, &ni, &kk, &vn.p, &lpos.p, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p};
-        RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T, NT, false>, dim3(grid), dim3(NT), args, smem, c->stream));
+        RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T, NT, CU>, dim3(grid), dim3(NT), args, smem, c->stream));
         RC_COUNT_LAUNCH(c);
     }
     int64_t total = (int64_t)kk * n;

@@ -47,8 +47,9 @@ struct rc_ctx {
     // options
     int gemm_impl = 0;            // 0 auto, 1 generic only
     int true_power_iteration = 0;
+    int reuse_range_b = 1;        // reuse B = Q^H A of the adaptive sampler in compute_from_range_estimate
     int qr_mode = 0;              // 0 auto (Cholesky-QR2 fast path with Householder-TSQR fallback), 1 TSQR only
-    int64_t cholqr_used = 0, cholqr_fallbacks = 0;
+    int64_t cholqr_used = 0, cholqr_fallbacks = 0, range_b_reused = 0;
     // counters
     int64_t launches = 0, gemm_flops = 0, h2d_bytes = 0, d2h_bytes = 0;
     int* tile_counter = nullptr;   // device scratch for the dynamic GEMM tile scheduler
@@ -66,6 +67,12 @@ struct rc_matrix {
     // row sharding: this handle holds rows [row_offset, row_offset + rows) of a
     // global_rows x cols matrix (global_rows == 0: not sharded)
     int64_t global_rows = 0, row_offset = 0;
+    // identity of this buffer (unique per allocation) and, for a range estimate Q produced by the
+    // adaptive sampler, the factor B = Q^H A it already computed for the operator `companion_op_id`
+    // (QR/SVD::compute_from_range_estimate reuse it instead of another pass over A)
+    uint64_t id = 0;
+    rc_matrix* companion = nullptr;
+    uint64_t companion_op_id = 0;
 };
 
 inline size_t rc_dtype_size(int dt) {
