@@ -146,6 +146,13 @@ rc_status rc_random_approximate_low_rank_matrix(rc_ctx* ctx, rc_dtype dtype, int
 rc_status rc_decaying_spectrum_matrix(rc_ctx* ctx, rc_dtype dtype, int64_t rows, int64_t cols,
                                       int64_t r0, double decade_every, uint64_t seed,
                                       int64_t row_offset, rc_matrix** out);
+/* Bench input of BASELINE config 4: rows [row_offset, row_offset + rows) of
+ * A = m_total^(-1/2) G diag(10^(-j/decade_every)) V^H with G_ij ~ N(0,1) keyed by (global row, j) and V a
+ * shared orthonormal factor, generated on device so that every rank of a row-sharded run builds exactly
+ * its own 2^23/P rows (the 256 GiB matrix never exists in one place). */
+rc_status rc_tall_shard_matrix(rc_ctx* ctx, rc_dtype dtype, int64_t rows, int64_t cols, int64_t r0,
+                               double decade_every, uint64_t seed, int64_t row_offset,
+                               int64_t m_total, rc_matrix** out);
 
 /* RelDiff::{rel_diff_fro, rel_diff_l2} (src/types.rs:162-204): ||first - second|| / ||second||. */
 rc_status rc_rel_diff_fro(rc_ctx* ctx, const rc_matrix* first, const rc_matrix* second, double* out);

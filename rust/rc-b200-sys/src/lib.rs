@@ -53,6 +53,7 @@ extern "C" {
     pub fn rc_random_orthogonal_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, seed: u64, stream: u32, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_random_approximate_low_rank_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, sigma_max: f64, sigma_min: f64, seed: u64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_decaying_spectrum_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, r0: i64, decade_every: f64, seed: u64, row_offset: i64, out: *mut *mut rc_matrix) -> c_int;
+    pub fn rc_tall_shard_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, r0: i64, decade_every: f64, seed: u64, row_offset: i64, m_total: i64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_rel_diff_fro(ctx: *mut rc_ctx, first: *const rc_matrix, second: *const rc_matrix, out: *mut f64) -> c_int;
     pub fn rc_rel_diff_l2(ctx: *mut rc_ctx, first: *const rc_matrix, second: *const rc_matrix, out: *mut f64) -> c_int;
     pub fn rc_max_col_norm(ctx: *mut rc_ctx, m: *const rc_matrix, out: *mut f64) -> c_int;

@@ -663,6 +663,15 @@ def decaying_spectrum_matrix(shape, dtype, seed, r0=512, decade_every=16.0, row_
     return DeviceMatrix(ctx, h)
 
 
+def tall_shard_matrix(row_offset, rows, cols, dtype, seed, m_total, r0=512, decade_every=64.0, ctx=None):
+    """Device-generated rows [row_offset, row_offset + rows) of the config-4 input."""
+    ctx = ctx or default_context()
+    h = c_void_p()
+    ctx.check(ctx.lib.rc_tall_shard_matrix(ctx.h, DTYPE_CODE[np.dtype(dtype)], rows, cols, r0, decade_every, seed,
+                                           row_offset, m_total, ctypes.byref(h)))
+    return DeviceMatrix(ctx, h)
+
+
 def _omega_handle(omega, ctx):
     if omega is None:
         return None, c_void_p(None)

@@ -53,6 +53,11 @@ EncodeFn get_encode() {
     }
     return fn;
 }
+CUtensorMapL2promotion l2_promotion() {
+    static int v = getenv("RC_TF32_L2PROMO") ? atoi(getenv("RC_TF32_L2PROMO")) : 256;          // tuning aid
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
 // Row-major [rows][cols] f32 matrix, box = 32 cols (128 B) x box_rows, SWIZZLE_128B.
 CUtensorMap make_map_f32(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     RC_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map box rows out of range");
@@ -63,7 +68,7 @@ CUtensorMap make_map_f32(const float* base, int64_t rows, int64_t cols, int64_t 
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RC_THROW(RC_CUDA_ERROR, "cuTensorMapEncodeTiled (f32) failed (%d)", (int)r);
     return m;
 }
@@ -141,6 +146,19 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
+// One lane of a converged warp (the CUTLASS elect_one_sync idiom): lets the compiler issue the
+// uniform-datapath tcgen05 instructions without a per-active-thread serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -161,6 +179,7 @@ struct Tf32Params {
     // side by side and A is fetched from HBM once and served to the other chunks out of L2.
     int nchunks;
     int vec_store;        // y and ldy are 16-byte aligned: the epilogue may use float4 stores
+    int agroup;           // raw A tiles requested per group (<= RS / 2)
 };
 
 // KC k-blocks (KC * 32 values of K) are accumulated inside the tensor core before the partial sum is
@@ -228,23 +247,37 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer: raw A tiles =====================
+        // Tiles are requested in groups of `agroup` consecutive k-blocks (agroup x 128 B contiguous per row of
+        // A, issued back to back): with a row pitch of tens of KB every 128-byte piece of a tile row sits in
+        // its own DRAM page, and single pieces spaced a stage apart leave HBM at about half of its peak.
         if (lane == 0) {
             int rs = 0; uint32_t rph = 0;
+            const int G = prm.agroup;
             for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
                 RC_ITEM(t)
                 const int m0 = mt_ * BM;
-                for (int kb = kb0_; kb < kb1_; ++kb) {
-                    mbar_wait(rawempty0 + 8 * rs, rph ^ 1u);
-                    const uint32_t sa = raw_base + rs * A_BYTES;
-                    const uint32_t fb = rawfull0 + 8 * rs;
-                    mbar_expect_tx(fb, A_BYTES);
-                    if (!TRANS) {
-                        tma_load_2d(sa, &tmA, kb * BK, m0, fb);                                   // [128 rows][32 k]
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < BM / 32; ++b) tma_load_2d(sa + b * 4096, &tmA, m0 + 32 * b, kb * BK, fb);   // raw [32 k][32 i] x 4
+                for (int kbg = kb0_; kbg < kb1_; kbg += G) {
+                    const int ng = min(G, kb1_ - kbg);
+                    {   // all slots of the group must be free before the first request goes out
+                        int s2 = rs; uint32_t p2 = rph;
+                        for (int g = 0; g < ng; ++g) {
+                            mbar_wait(rawempty0 + 8 * s2, p2 ^ 1u);
+                            if (++s2 == RS) { s2 = 0; p2 ^= 1u; }
+                        }
                     }
-                    if (++rs == RS) { rs = 0; rph ^= 1u; }
+                    for (int g = 0; g < ng; ++g) {
+                        const int kb = kbg + g;
+                        const uint32_t sa = raw_base + rs * A_BYTES;
+                        const uint32_t fb = rawfull0 + 8 * rs;
+                        mbar_expect_tx(fb, A_BYTES);
+                        if (!TRANS) {
+                            tma_load_2d(sa, &tmA, kb * BK, m0, fb);                                   // [128 rows][32 k]
+                        } else {
+#pragma unroll
+                            for (int b = 0; b < BM / 32; ++b) tma_load_2d(sa + b * 4096, &tmA, m0 + 32 * b, kb * BK, fb);   // raw [32 k][32 i] x 4
+                        }
+                        if (++rs == RS) { rs = 0; rph ^= 1u; }
+                    }
                 }
             }
         }
@@ -255,7 +288,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
                 RC_ITEM(t)
                 for (int kb = kb0_; kb < kb1_; ++kb) {
-                    mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
+                    mbar_wait(aempty0 + 8 * bs, bph ^ 1u);           // MS == BS: one commit frees the A (TMEM) and B slot
                     const uint32_t sb = bt_base + bs * 2 * B_BYTES;
                     const uint32_t fb = bfull0 + 8 * bs;
                     mbar_expect_tx(fb, 2 * B_BYTES);
@@ -266,9 +299,15 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one elected thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer =====================
+        // The whole warp runs the control flow (converged, so the tcgen05 instructions of the elected lane
+        // compile to plain uniform-datapath issues); the single-thread form of this loop spent ~100 cycles
+        // per MMA on elect/branch scaffolding and capped the kernel at 12 MMAs per 1380 cycles.
+        {
             const uint32_t idesc = umma_idesc_tf32((uint32_t)npad);
+            // UMMA shared-memory descriptor of the X^T tiles: constant high word, low word = address >> 4
+            const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+            const uint32_t bt_lo = (bt_base & 0x3FFFFu) >> 4;
             int ms = 0; uint32_t mph = 0;
             int bs = 0; uint32_t bph = 0;
             int it = 0;                                              // counts K-chunks (TMEM buffer hand-offs)
@@ -278,28 +317,28 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const int buf = it & 1;
                     const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
                     mbar_wait(acce0 + 8 * buf, acc_phase ^ 1u);      // epilogue drained this buffer
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * npad);
                     const int kc1 = min(kblocks, kc0 + KC);
                     for (int kb = kc0; kb < kc1; ++kb) {
                         mbar_wait(bfull0 + 8 * bs, bph);
                         mbar_wait(split0 + 8 * ms, mph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_hi = tmem_base + (uint32_t)(2 * npad + ms * A_TMEM_COLS), a_lo = a_hi + 32u;
-                        const uint32_t b_hi = bt_base + bs * 2 * B_BYTES, b_lo = b_hi + B_BYTES;
+                        if (elect_one()) {
+                            const uint32_t a_hi = tmem_base + (uint32_t)(2 * npad + ms * A_TMEM_COLS), a_lo = a_hi + 32u;
+                            const uint32_t bh = bt_lo + (uint32_t)bs * (2 * B_BYTES >> 4), bl = bh + (B_BYTES >> 4);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k) {
-                            // B K-major: 8 floats along K inside the swizzle row; A: 8 TMEM columns per K-step
-                            const uint32_t koff = (uint32_t)k * 32u;
-                            const uint64_t dbh = umma_desc_sw128(b_hi + koff), dbl = umma_desc_sw128(b_lo + koff);
-                            // small terms first, then the dominant one
-                            umma_tf32_ts(d_tmem, a_lo + 8u * k, dbh, idesc, (kb != kc0 || k != 0) ? 1u : 0u);
-                            umma_tf32_ts(d_tmem, a_hi + 8u * k, dbl, idesc, 1u);
-                            umma_tf32_ts(d_tmem, a_hi + 8u * k, dbh, idesc, 1u);
+                            for (int k = 0; k < BK / 8; ++k) {
+                                // B K-major: 8 floats (32 B) along K inside the swizzle row; A: 8 TMEM columns per K-step
+                                const uint64_t dbh = desc_hi | (uint64_t)(bh + 2u * k), dbl = desc_hi | (uint64_t)(bl + 2u * k);
+                                // small terms first, then the dominant one
+                                umma_tf32_ts(d_tmem, a_lo + 8u * k, dbh, idesc, (kb != kc0 || k != 0) ? 1u : 0u);
+                                umma_tf32_ts(d_tmem, a_hi + 8u * k, dbl, idesc, 1u);
+                                umma_tf32_ts(d_tmem, a_hi + 8u * k, dbh, idesc, 1u);
+                            }
+                            umma_commit(aempty0 + 8 * ms);               // frees the TMEM stage and the B slot when the MMAs retire
+                            if (kb == kc1 - 1) umma_commit(accf0 + 8 * buf);
                         }
-                        umma_commit(aempty0 + 8 * ms);               // frees the rings' slots when the MMAs retire
-                        umma_commit(bempty0 + 8 * bs);
-                        if (kb == kc1 - 1) umma_commit(accf0 + 8 * buf);
+                        __syncwarp();
                         if (++ms == MS) { ms = 0; mph ^= 1u; }
                         if (++bs == BS) { bs = 0; bph ^= 1u; }
                     }
@@ -443,13 +482,17 @@ __global__ void split_transpose_kernel(const float* __restrict__ x, int64_t ldx,
 template <int RS, int MS, int BS, int NPADC, bool TRANS>
 void launch_tf32(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
                  Tf32Params prm) {
-    static_assert(RS <= MAX_RS && MS <= MAX_MS && BS <= MAX_BS, "ring depth");
+    static_assert(RS <= MAX_RS && MS <= MAX_MS && BS <= MAX_BS && MS == BS, "ring depth (A-TMEM and B rings share their release barrier)");
     static_assert(2 * NPADC + MS * A_TMEM_COLS <= 512, "tensor memory columns");
     constexpr size_t smem = (size_t)RS * BM * BK * 4 + (size_t)BS * 2 * NPADC * BK * 4 + 1024;
     static_assert(smem <= 226 * 1024, "ring configuration exceeds shared memory");
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * NPADC + MS * A_TMEM_COLS)) cols <<= 1;
     prm.tmem_cols = cols;
+    {
+        static int g_env = getenv("RC_TF32_AGROUP") ? atoi(getenv("RC_TF32_AGROUP")) : 0;     // tuning aid
+        prm.agroup = std::max(1, std::min(g_env > 0 ? g_env : (TRANS ? 1 : RS / 2), RS));
+    }
     prm.vec_store = ((reinterpret_cast<uintptr_t>(prm.y) & 15) == 0 && (prm.ldy & 3) == 0 && (prm.part_stride & 3) == 0) ? 1 : 0;
     RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<RS, MS, BS, NPADC, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(prm.m_tiles * prm.splits * prm.nchunks, c->sm_count);
@@ -460,10 +503,10 @@ template <bool TRANS>
 void dispatch_tf32(rc_ctx* c, int npad, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
                    const Tf32Params& prm) {
     switch (npad) {      //      raw (smem)  A hi/lo (TMEM)  X^T (smem)
-        case 32: launch_tf32<8, 3, 4, 32, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 32 KB
-        case 64: launch_tf32<8, 3, 4, 64, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 64 KB
-        case 96: launch_tf32<7, 3, 4, 96, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 112 + 96 KB
-        default: launch_tf32<6, 3, 4, 128, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;    // 96 + 128 KB
+        case 32: launch_tf32<8, 4, 4, 32, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 32 KB
+        case 64: launch_tf32<8, 4, 4, 64, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 64 KB
+        case 96: launch_tf32<7, 4, 4, 96, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 112 + 96 KB
+        default: launch_tf32<6, 4, 4, 128, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;    // 96 + 128 KB
     }
 }
 

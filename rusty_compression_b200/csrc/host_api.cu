@@ -217,34 +217,55 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
         pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1.p, ncq);
         ts.apply(q1.p, ncq, ncq, P<T>(q.get()), q->ld);
     } else {
-        int64_t npan = (w + wmax - 1) / wmax;
+        // Panels of at most min(wmax, Cholesky width) columns.  Each panel is orthogonalised against the
+        // previous ones (block classical Gram-Schmidt, twice) and then factored on its own: Cholesky-QR2 when
+        // it is well conditioned (all GEMM-shaped, tensor pipe), Householder TSQR otherwise.
+        const int64_t wpan = std::min(wmax, c->qr_mode == 1 ? wmax : chol_max_width(c, dtype));
+        int64_t npan = (w + wpan - 1) / wpan;
         int64_t wp = (w + npan - 1) / npan;
-        DevBuf<T> qfull(c, (size_t)m * w);
+        {   // panel starts on 16-byte boundaries (TMA operand alignment), as long as the panel still fits
+            const int64_t e = std::max<int64_t>(1, (int64_t)(16 / rc_dtype_size(dtype)));
+            const int64_t up = (wp + e - 1) / e * e;
+            if (up <= wpan) wp = up;
+        }
+        const int64_t ldq = rc_pad_ld(dtype, w);          // 16-byte row pitch: the tensor-pipe GEMMs can take it
+        DevBuf<T> qfull(c, (size_t)m * ldq);
         k_fill<T>(c, r0.p, w, w, w, rc_zero<T>());
         for (int64_t c0 = 0; c0 < w; c0 += wp) {
             int64_t cw = std::min(wp, w - c0);
             T* yp = y + c0;
             if (c0 > 0) {
-                // block classical Gram-Schmidt against the previous panels, twice ("twice is enough")
-                DevBuf<T> t(c, (size_t)c0 * cw);
+                const int64_t ldt = rc_pad_ld(dtype, cw);
+                DevBuf<T> t(c, (size_t)c0 * ldt), proj(c, (size_t)m * ldt);
                 for (int pass = 0; pass < 2; ++pass) {
-                    gemm<T>(c, RC_OP_H, RC_OP_N, c0, cw, m, qfull.p, w, yp, ldy, t.p, cw, rc_one<T>(), rc_zero<T>());
-                    if (sharded) comm_allreduce_sum(c, t.p, (size_t)c0 * cw, dtype);
-                    gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, c0, qfull.p, w, t.p, cw, yp, ldy, rc_make<T>(-1.0, 0.0), rc_one<T>());
-                    k_add<T>(c, r0.p + c0, w, r0.p + c0, w, t.p, cw, c0, cw);     // R0[0:c0, c0:c0+cw] += t
+                    if (sharded && ldt != cw) RC_CUDA(cudaMemsetAsync(t.p, 0, sizeof(T) * c0 * ldt, c->stream));
+                    gemm<T>(c, RC_OP_H, RC_OP_N, c0, cw, m, qfull.p, ldq, yp, ldy, t.p, ldt, rc_one<T>(), rc_zero<T>());
+                    if (sharded) comm_allreduce_sum(c, t.p, (size_t)c0 * ldt, dtype);
+                    gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, c0, qfull.p, ldq, t.p, ldt, proj.p, ldt, rc_one<T>(), rc_zero<T>());
+                    k_sub<T>(c, yp, ldy, yp, ldy, proj.p, ldt, m, cw);                    // Y_p -= Q (Q^H Y_p)
+                    k_add<T>(c, r0.p + c0, w, r0.p + c0, w, t.p, ldt, c0, cw);             // R0[0:c0, c0:c0+cw] += t
                 }
             }
-            DistTsqr<T> ts;
-            ts.factor(c, yp, ldy, m, cw, sharded);
-            k_copy<T>(c, r0.p + c0 * w + c0, w, ts.r(), cw, cw, cw);
-            DevBuf<T> eye(c, (size_t)cw * cw);
-            k_eye<T>(c, eye.p, cw, cw, cw);
-            ts.apply(eye.p, cw, cw, qfull.p + c0, w);
+            DevBuf<T> pq1, prinv2, prfac;
+            int64_t lds = 0;
+            if (cholqr2<T>(c, yp, ldy, m, cw, sharded, dtype, pq1, prinv2, prfac, lds)) {
+                gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, cw, pq1.p, lds, prinv2.p, lds, qfull.p + c0, ldq, rc_one<T>(), rc_zero<T>());
+                k_copy<T>(c, r0.p + c0 * w + c0, w, prfac.p, lds, cw, cw);
+            } else {
+                DistTsqr<T> ts;
+                ts.factor(c, yp, ldy, m, cw, sharded);
+                k_copy<T>(c, r0.p + c0 * w + c0, w, ts.r(), cw, cw, cw);
+                DevBuf<T> eye(c, (size_t)cw * cw);
+                k_eye<T>(c, eye.p, cw, cw, cw);
+                ts.apply(eye.p, cw, cw, qfull.p + c0, ldq);
+            }
         }
         k_transpose<T>(c, wc.p, w, r0.p, w, w, w, false);
         pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
-        pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1.p, ncq);
-        gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, qfull.p, w, q1.p, ncq, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
+        const int64_t ldq1 = rc_pad_ld(dtype, ncq);
+        DevBuf<T> q1p(c, (size_t)w * ldq1);
+        pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1p.p, ldq1);
+        gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, qfull.p, ldq, q1p.p, ldq1, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
     }
     download_ind(c, dind.p, w, out.ind);
     out.q.reset(q.release());
@@ -961,6 +982,29 @@ rc_status rc_decaying_spectrum_matrix(rc_ctx* c, rc_dtype dt, int64_t rows, int6
             MatPtr u(ortho(rows, 201, row_offset)), v(ortho(cols, 202, 0));
             MatPtr vt(mat_conj_transpose<T>(c, v.get()));
             *out = low_rank_from_factors<T>(c, u.get(), sig, vt.get());
+        });
+    });
+}
+
+// BASELINE config 4 input: rows [row_offset, row_offset + rows) of
+// A = m_total^(-1/2) G diag(10^(-j/decade_every)) V^H, G_ij ~ N(0,1) from Philox keyed by (global row, j)
+// (stream 7, like oracle/inputs.py::tall_shard_matrix), V (cols x r0) a shared orthonormal factor.  The left
+// factor is NOT orthonormalised, so any rank of any world size regenerates exactly its own rows.
+rc_status rc_tall_shard_matrix(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t cols, int64_t r0, double decade_every,
+                               uint64_t seed, int64_t row_offset, int64_t m_total, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(rows > 0 && cols > 0 && r0 > 0 && decade_every > 0 && m_total >= row_offset + rows, "bad arguments");
+        r0 = std::min(r0, cols);
+        std::vector<double> sig((size_t)r0);
+        for (int64_t j = 0; j < r0; ++j) sig[j] = std::pow(10.0, -(double)j / decade_every) / std::sqrt((double)m_total);
+        RC_DISPATCH(dt, {
+            MatPtr g(gaussian_new<T>(c, dt, rows, r0, seed, 7, row_offset));
+            MatPtr gv(gaussian_new<T>(c, dt, cols, r0, seed, 202, 0));
+            QrParts qr;
+            pivoted_qr_impl<T>(c, gv.get(), false, -1, true, qr);
+            MatPtr vt(mat_conj_transpose<T>(c, qr.q.get()));
+            *out = low_rank_from_factors<T>(c, g.get(), sig, vt.get());
         });
     });
 }
