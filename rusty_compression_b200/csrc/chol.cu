@@ -16,7 +16,9 @@ chol_inv_kernel(const T* __restrict__ g, int64_t ldg, int w, T* __restrict__ r, 
     T* S = reinterpret_cast<T*>(smem_raw);          // w x w row-major working copy (upper part used)
     T* X = S + (size_t)w * w;                        // inverse
     __shared__ double s_red[CT / 32];
-    const int tid = threadIdx.x;
+    __shared__ double s_piv[256];                    // pivots d_j = R_jj^2 (w <= 256 is guaranteed by the smem limit)
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double defect = 0.0;
     for (int e = tid; e < w * w; e += CT) {
         int i = e / w, j = e - i * w;
@@ -25,62 +27,72 @@ chol_inv_kernel(const T* __restrict__ g, int64_t ldg, int w, T* __restrict__ r, 
         T d = (i == j) ? v - rc_one<T>() : v;
         defect = fmax(defect, rc_abs(d));
     }
+    if (tid == 0) s_bad = 0;
     // block max of the defect
     for (int m = 16; m > 0; m >>= 1) defect = fmax(defect, __shfl_xor_sync(0xffffffffu, defect, m));
-    if ((tid & 31) == 0) s_red[tid >> 5] = defect;
+    if (lane == 0) s_red[warp] = defect;
     __syncthreads();
     if (tid == 0) { double d = 0.0; for (int i = 0; i < CT / 32; ++i) d = fmax(d, s_red[i]); status[3] = d; }
-    // Row-by-row (left-looking) Cholesky by the first 128 threads, one thread per column:
-    //   R[j][c] = (G[j][c] - sum_{l<j} conj(R[l][j]) R[l][c]) / R[j][j]
-    // The l-loop reads R[l][j] as a broadcast and R[l][c] conflict-free; the two barriers per row are
-    // 128-thread named barriers (the other 28 warps wait at the block barrier below).
-    __shared__ double s_d;
-    if (tid < 128) {
-        double dmin = 1e300, dmax = 0.0;
-        int bad = 0;
+    // Right-looking (outer-product) Cholesky with ONE block barrier per step: step j updates the trailing
+    // upper triangle with the UNSCALED row j, S[r][c] -= conj(S[j][r]) S[j][c] / d_j, so no thread has to wait
+    // for the scaled pivot row; the rows are scaled by 1 / sqrt(d_j) once at the end.  32 x 32 thread tile.
+    {
+        const int tx = lane, ty = warp;
         for (int j = 0; j < w; ++j) {
-            for (int c = j + tid; c < w; c += 128) {
-                T a0 = S[j * w + c], a1 = rc_zero<T>();
-                int l = 0;
-                for (; l + 1 < j; l += 2) {
-                    a0 = a0 - rc_conj(S[l * w + j]) * S[l * w + c];
-                    a1 = a1 - rc_conj(S[(l + 1) * w + j]) * S[(l + 1) * w + c];
-                }
-                if (l < j) a0 = a0 - rc_conj(S[l * w + j]) * S[l * w + c];
-                a0 = a0 + a1;
-                S[j * w + c] = a0;
-                if (c == j) s_d = (double)rc_real(a0);
+            const double d = (double)rc_real(S[j * w + j]);
+            if (tid == 0) { s_piv[j] = d; if (!(d > 0.0)) s_bad = 1; }
+            const RealOf<T> id = (RealOf<T>)(1.0 / ((d > 0.0) ? d : 1.0));
+            for (int rr = j + 1 + ty; rr < w; rr += 32) {
+                const T f = rc_conj(S[j * w + rr]) * id;
+                for (int cc = j + 1 + tx; cc < w; cc += 32)
+                    if (cc >= rr) S[rr * w + cc] = S[rr * w + cc] - f * S[j * w + cc];
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            double d = s_d;
-            if (!(d > 0.0)) { bad = 1; d = 1.0; }
-            const double piv = sqrt(d);
-            dmin = fmin(dmin, piv); dmax = fmax(dmax, piv);
-            const RealOf<T> ip = (RealOf<T>)(1.0 / piv);
-            for (int c = j + tid; c < w; c += 128) S[j * w + c] = (c == j) ? rc_make<T>(piv, 0.0) : S[j * w + c] * ip;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            __syncthreads();
         }
-        if (tid == 0) { status[0] = (double)bad; status[1] = dmin; status[2] = dmax; }
+    }
+    // scale the rows: R[j][c] = S[j][c] / sqrt(d_j); diagonal real positive
+    for (int e = tid; e < w * w; e += CT) {
+        int i = e / w, j = e - i * w;
+        if (j >= i) {
+            const double d = s_piv[i];
+            const double piv = sqrt((d > 0.0) ? d : 1.0);
+            S[e] = (i == j) ? rc_make<T>(piv, 0.0) : S[e] * (RealOf<T>)(1.0 / piv);
+        }
     }
     __syncthreads();
+    if (warp == 0) {
+        double dmin = 1e300, dmax = 0.0;
+        for (int j = lane; j < w; j += 32) { double pv = (double)rc_real(S[j * w + j]); dmin = fmin(dmin, pv); dmax = fmax(dmax, pv); }
+        for (int m = 16; m > 0; m >>= 1) { dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, m)); dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, m)); }
+        if (lane == 0) { status[0] = (double)s_bad; status[1] = dmin; status[2] = dmax; }
+    }
     // R out (upper triangular, zeros below)
     for (int e = tid; e < w * w; e += CT) {
         int i = e / w, j = e - i * w;
         r[(int64_t)i * ldo + j] = (j >= i) ? S[e] : rc_zero<T>();
     }
-    // X = R^{-1}: columns are independent; one warp per column walks its rows upwards, the lanes
-    // split each inner product (a thread-per-column loop was a 2.7K-long dependent chain)
+    // X = R^{-1}: columns are independent (no block barriers); four lanes share a column and split each
+    // inner product, so the dependent chain of a column is c steps of (c - i) / 4 FMAs + two shuffles.  The
+    // eight columns of a warp run a common trip count (the shuffles need the whole warp).
     {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int c = warp; c < w; c += CT / 32) {
-            for (int i = w - 1 - lane; i > c; i -= 32) X[i * w + c] = rc_zero<T>();
-            if (lane == 0) X[c * w + c] = rc_one<T>() / S[c * w + c];
+        const int sub = lane & 3;
+        for (int cbase = warp * 8; cbase < w; cbase += (CT / 32) * 8) {
+            const int c = cbase + (lane >> 2);
+            const bool active = c < w;
+            const int cmax = min(cbase + 7, w - 1);
+            if (active) {
+                for (int i = w - 1 - sub; i > c; i -= 4) X[i * w + c] = rc_zero<T>();
+                if (sub == 0) X[c * w + c] = rc_one<T>() / S[c * w + c];
+            }
             __syncwarp();
-            for (int i = c - 1; i >= 0; --i) {
+            for (int i = cmax - 1; i >= 0; --i) {
+                const bool work = active && i < c;
                 T acc = rc_zero<T>();
-                for (int l = i + 1 + lane; l <= c; l += 32) acc = rc_fma(S[i * w + l], X[l * w + c], acc);
-                acc = rc_warp_sum(acc);
-                if (lane == 0) X[i * w + c] = -(acc / S[i * w + i]);
+                if (work)
+                    for (int l = i + 1 + sub; l <= c; l += 4) acc = rc_fma(S[i * w + l], X[l * w + c], acc);
+                acc = acc + rc_shfl_xor(acc, 1);
+                acc = acc + rc_shfl_xor(acc, 2);
+                if (work && sub == 0) X[i * w + c] = -(acc / S[i * w + i]);
                 __syncwarp();
             }
         }
@@ -96,7 +108,7 @@ template <class T>
 bool chol_inv(rc_ctx* c, const T* g, int64_t ldg, int64_t w, T* r, T* rinv, int64_t ldo, double* status_dev) {
     size_t smem = 2 * (size_t)w * w * sizeof(T);
     size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
-    if (smem + 8192 > lim) return false;
+    if (smem + 8192 > lim || w > 256) return false;
     RC_CUDA(cudaFuncSetAttribute(chol_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     chol_inv_kernel<T><<<1, CT, smem, c->stream>>>(g, ldg, (int)w, r, rinv, ldo, status_dev);
     RC_CHECK_LAUNCH(c);

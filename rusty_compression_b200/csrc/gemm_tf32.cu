@@ -34,8 +34,9 @@ namespace {
 
 constexpr int BM = 128;           // UMMA M (cta_group::1)
 constexpr int BK = 32;            // floats per stage = one 128-byte swizzle row
-constexpr int NTHREADS = 352;     // 11 warps
+constexpr int NTHREADS = 480;     // 15 warps: A-TMA, MMA, 4 splitters, 4 epilogue, B-TMA, 4 more splitters
 constexpr int MAX_RS = 8, MAX_MS = 4, MAX_BS = 4;   // ring depths: raw A tiles (smem), split A (TMEM), B tiles (smem)
+constexpr int MAX_CHUNK = 96;     // columns per work item: the promoted FP32 accumulator row lives in one epilogue thread's registers
 constexpr int A_TMEM_COLS = 64;   // one split stage in TMEM: A_hi (32 columns = 32 k) + A_lo (32 columns)
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -53,11 +54,6 @@ EncodeFn get_encode() {
     }
     return fn;
 }
-CUtensorMapL2promotion l2_promotion() {
-    static int v = getenv("RC_TF32_L2PROMO") ? atoi(getenv("RC_TF32_L2PROMO")) : 256;          // tuning aid
-    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-         : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-}
 // Row-major [rows][cols] f32 matrix, box = 32 cols (128 B) x box_rows, SWIZZLE_128B.
 CUtensorMap make_map_f32(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     RC_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map box rows out of range");
@@ -68,7 +64,7 @@ CUtensorMap make_map_f32(const float* base, int64_t rows, int64_t cols, int64_t 
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RC_THROW(RC_CUDA_ERROR, "cuTensorMapEncodeTiled (f32) failed (%d)", (int)r);
     return m;
 }
@@ -247,9 +243,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer: raw A tiles =====================
-        // Tiles are requested in groups of `agroup` consecutive k-blocks (agroup x 128 B contiguous per row of
-        // A, issued back to back): with a row pitch of tens of KB every 128-byte piece of a tile row sits in
-        // its own DRAM page, and single pieces spaced a stage apart leave HBM at about half of its peak.
+        // Tiles can be requested in groups of `agroup` consecutive k-blocks (agroup x 128 B contiguous per row
+        // of A, issued back to back) -- an experiment on DRAM page locality that did not pay off on B200.
         if (lane == 0) {
             int rs = 0; uint32_t rph = 0;
             const int G = prm.agroup;
@@ -345,17 +340,22 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 6 || warp >= 11) {
         // ===================== splitter: raw A tile (smem) -> A_hi, A_lo (TMEM) =====================
-        // thread <-> tile row: a warp may only touch the TMEM lane quadrant (warp % 4)
+        // Two groups of four warps (warps 2-5 and 11-14) take alternate k-blocks: one block is a serial chain
+        // (wait, LDS, convert, wait, tcgen05.st, wait::st, arrive) of ~500 cycles, which a single group
+        // cannot hide.  thread <-> tile row: a warp may only touch the TMEM lane quadrant (warp % 4).
+        const int grp = (warp >= 11) ? 1 : 0;
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        int rs = 0; uint32_t rph = 0;
-        int ms = 0; uint32_t mph = 0;
+        int rs = grp; uint32_t rph = 0;            // ring positions of this group's first block (RS, MS >= 2)
+        int ms = grp; uint32_t mph = 0;
+        int seq = 0;                               // k-block sequence number over all work items of this CTA
         const unsigned char* const smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
         for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
             RC_ITEM(t)
-            for (int kb = 0; kb < kblocks; ++kb) {
+            for (int kb = 0; kb < kblocks; ++kb, ++seq) {
+                if ((seq & 1) != grp) continue;
                 mbar_wait(rawfull0 + 8 * rs, rph);
                 const unsigned char* rawp = smem_al + (size_t)rs * A_BYTES;
                 float vals[32];
@@ -399,8 +399,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(split0 + 8 * ms);
-                if (++rs == RS) { rs = 0; rph ^= 1u; }
-                if (++ms == MS) { ms = 0; mph ^= 1u; }
+                rs += 2; if (rs >= RS) { rs -= RS; rph ^= 1u; }
+                ms += 2; if (ms >= MS) { ms -= MS; mph ^= 1u; }
             }
         }
     } else {
@@ -464,19 +464,43 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
-// X (K x N row-major) -> XhiT, XloT (npad x K row-major, K contiguous), rows >= N zero.
-__global__ void split_transpose_kernel(const float* __restrict__ x, int64_t ldx, int K, int N, int npad,
-                                       float* __restrict__ hiT, float* __restrict__ loT, int64_t ldt) {
-    int64_t total = (int64_t)npad * K;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        int j = (int)(e / K), k = (int)(e - (int64_t)j * K);
-        float v = (j < N) ? x[(int64_t)k * ldx + j] : 0.f;
-        uint32_t u;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-        float h = __uint_as_float(u);
-        hiT[(int64_t)j * ldt + k] = h;
-        loT[(int64_t)j * ldt + k] = v - h;
+// X (K x N row-major) -> XhiT, XloT (nrows x K row-major, K contiguous), rows >= N zero.  32 x 32 tiles
+// through shared memory: reads run along the rows of X, writes along K (both coalesced); for the Gram
+// matrices of the Cholesky-QR path X is the m x l sketch itself, so this is a bandwidth kernel.
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ x, int64_t ldx, int K, int N, int nrows,
+                       float* __restrict__ hiT, float* __restrict__ loT, int64_t ldt) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int j0 = blockIdx.y * 32;
+    for (int64_t kt = blockIdx.x; kt * 32 < K; kt += gridDim.x) {
+        const int64_t k0 = kt * 32;
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int64_t k = k0 + r; const int j = j0 + tx;
+            tile[r][tx] = (k < K && j < N) ? x[k * ldx + j] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int j = j0 + r; const int64_t k = k0 + tx;
+            if (k < K && j < nrows) {
+                const float v = tile[tx][r];
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                const float h = __uint_as_float(u);
+                hiT[(int64_t)j * ldt + k] = h;
+                loT[(int64_t)j * ldt + k] = v - h;
+            }
+        }
+        __syncthreads();
     }
+}
+void launch_split_transpose(rc_ctx* c, const float* x, int64_t ldx, int64_t K, int N, int nrows, float* hiT, float* loT, int64_t ldt) {
+    dim3 block(32, 8);
+    dim3 grid((unsigned)std::min<int64_t>((K + 31) / 32, 148 * 64), (unsigned)((nrows + 31) / 32));
+    split_transpose_kernel<<<grid, block, 0, c->stream>>>(x, ldx, (int)K, N, nrows, hiT, loT, ldt);
+    RC_CHECK_LAUNCH(c);
 }
 
 template <int RS, int MS, int BS, int NPADC, bool TRANS>
@@ -489,10 +513,7 @@ void launch_tf32(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmBhi, co
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * NPADC + MS * A_TMEM_COLS)) cols <<= 1;
     prm.tmem_cols = cols;
-    {
-        static int g_env = getenv("RC_TF32_AGROUP") ? atoi(getenv("RC_TF32_AGROUP")) : 0;     // tuning aid
-        prm.agroup = std::max(1, std::min(g_env > 0 ? g_env : (TRANS ? 1 : RS / 2), RS));
-    }
+    prm.agroup = 1;     // measured: 1 is best on B200 (2, 4, 8 are 0-4 % slower at 32768^2 x 64)
     prm.vec_store = ((reinterpret_cast<uintptr_t>(prm.y) & 15) == 0 && (prm.ldy & 3) == 0 && (prm.part_stride & 3) == 0) ? 1 : 0;
     RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<RS, MS, BS, NPADC, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(prm.m_tiles * prm.splits * prm.nchunks, c->sm_count);
@@ -505,8 +526,7 @@ void dispatch_tf32(rc_ctx* c, int npad, const CUtensorMap& tmA, const CUtensorMa
     switch (npad) {      //      raw (smem)  A hi/lo (TMEM)  X^T (smem)
         case 32: launch_tf32<8, 4, 4, 32, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 32 KB
         case 64: launch_tf32<8, 4, 4, 64, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 64 KB
-        case 96: launch_tf32<7, 4, 4, 96, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 112 + 96 KB
-        default: launch_tf32<6, 4, 4, 128, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;    // 96 + 128 KB
+        default: launch_tf32<7, 4, 4, 96, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 112 + 96 KB
     }
 }
 
@@ -530,19 +550,14 @@ bool gemm_tf32x3_f32(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float* A,
     if (M <= 0 || N <= 0 || K <= 0) return false;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3)) return false;      // TMA: 16-byte base and pitch
     if (M > (1LL << 30) || K > (1LL << 30)) return false;
-    // columns are processed in chunks of at most 128 (the promoted FP32 accumulator of a row lives in
+    // columns are processed in chunks of at most MAX_CHUNK (the promoted FP32 accumulator of a row lives in
     // the registers of one epilogue thread); all chunks run in ONE launch, chunk-fastest (Tf32Params)
-    const int nchunks = (int)((N + 127) / 128);
-    const int npad = (int)(((N + nchunks - 1) / nchunks + 31) / 32 * 32);          // 32, 64, 96 or 128
+    const int nchunks = (int)((N + MAX_CHUNK - 1) / MAX_CHUNK);
+    const int npad = (int)(((N + nchunks - 1) / nchunks + 31) / 32 * 32);          // 32, 64 or 96
     const int64_t ldt = (K + 3) / 4 * 4;
     const int nrows = nchunks * npad;                   // stacked X^T: column j of X is row j
     DevBuf<float> hiT(c, (size_t)nrows * ldt), loT(c, (size_t)nrows * ldt);
-    {
-        int64_t total = (int64_t)nrows * K;
-        int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-        split_transpose_kernel<<<nb, 256, 0, c->stream>>>(X, ldx, (int)K, (int)N, nrows, hiT.p, loT.p, ldt);
-        RC_CHECK_LAUNCH(c);
-    }
+    launch_split_transpose(c, X, ldx, K, (int)N, nrows, hiT.p, loT.p, ldt);
     CUtensorMap tmA = make_map_f32(A, M, K, lda, BM);
     CUtensorMap tmBhi = make_map_f32(hiT.p, nrows, K, ldt, npad);
     CUtensorMap tmBlo = make_map_f32(loT.p, nrows, K, ldt, npad);
@@ -567,19 +582,14 @@ bool gemm_tf32x3_f32_tn(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float*
     if (M <= 0 || N <= 0 || K <= 0) return false;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3)) return false;
     if (M > (1LL << 30) || K > (1LL << 30)) return false;
-    const int nchunks = (int)((N + 127) / 128);
+    const int nchunks = (int)((N + MAX_CHUNK - 1) / MAX_CHUNK);
     const int npad = (int)(((N + nchunks - 1) / nchunks + 31) / 32 * 32);
     const int nrows = nchunks * npad;
     const int64_t kblocks = (K + BK - 1) / BK;
     // B operand K-major: Y^T split into hi / lo once (Y is the small m x l matrix), chunks stacked
     const int64_t ldt = (K + 3) / 4 * 4;
     DevBuf<float> hi(c, (size_t)nrows * ldt), lo(c, (size_t)nrows * ldt);
-    {
-        int64_t total = (int64_t)nrows * K;
-        int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-        split_transpose_kernel<<<nb, 256, 0, c->stream>>>(Y, ldy, (int)K, (int)N, nrows, hi.p, lo.p, ldt);
-        RC_CHECK_LAUNCH(c);
-    }
+    launch_split_transpose(c, Y, ldy, K, (int)N, nrows, hi.p, lo.p, ldt);
     CUtensorMap tmA = make_map_f32(A, K, M, lda, 32);           // boxes [32 k rows][32 cols]
     CUtensorMap tmBhi = make_map_f32(hi.p, nrows, K, ldt, npad);
     CUtensorMap tmBlo = make_map_f32(lo.p, nrows, K, ldt, npad);
