@@ -61,6 +61,16 @@ double dev_scalar(rc_ctx* c, const double* d) {
 
 }  // namespace
 
+// Stage timer for tuning (option "trace" = 1): synchronises the stream at every mark, so it perturbs the run.
+#include <chrono>
+static void rc_trace(rc_ctx* c, const char* label) {
+    if (!c->trace) return;
+    cudaStreamSynchronize(c->stream);
+    double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (label) fprintf(stderr, "[rc trace] %-34s %9.3f ms\n", label, now - c->trace_t0);
+    c->trace_t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // ============================================================================ GEMM dispatch
 // Replaces ndarray `.dot` (reference N5).  f64/c64 contractions with a plain or (conj-)transposed
 // left operand go to the TMA-fed DMMA kernels; everything else to the generic SIMT tiles.
@@ -86,7 +96,7 @@ void gemm(rc_ctx* c, RcOp opa, RcOp opb, int64_t M, int64_t N, int64_t K, const 
             // (fewer than ~1/4 of the SMs' worth of 128-row tiles and a long K: the split-K SIMT tiles win)
             if (opa == RC_OP_N && M >= 128 && (M >= 128 * 37 || K < 4096)) {
                 if (gemm_tf32x3_f32(c, M, N, K, A, lda, B, ldb, C, ldc)) return;
-            } else if (opa != RC_OP_N && M >= 128 && K >= 256) {
+            } else if (opa != RC_OP_N && M >= 32 && K >= 256) {
                 if (gemm_tf32x3_f32_tn(c, M, N, K, A, lda, B, ldb, C, ldc)) return;
             }
         } else if constexpr (std::is_same<T, c32>::value) {
@@ -174,10 +184,13 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
         return h[0] == 0.0 && h[1] > 0.0;
     };
     if (!gram_chol(y, ldy, r1.p, rinv1.p) || h[2] / h[1] > max_ratio) { c->cholqr_fallbacks++; return false; }
+    rc_trace(c, "  cholqr2: gram + chol #1");
     q1.alloc(c, (size_t)m * lds);
     gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, y, ldy, rinv1.p, lds, q1.p, lds, rc_one<T>(), rc_zero<T>());
+    rc_trace(c, "  cholqr2: q1 = Y rinv1");
     rinv2.alloc(c, (size_t)w * lds);
     if (!gram_chol(q1.p, lds, r2.p, rinv2.p) || h[3] > 0.25) { c->cholqr_fallbacks++; return false; }
+    rc_trace(c, "  cholqr2: gram + chol #2");
     rfac.alloc(c, (size_t)w * lds);
     gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, r2.p, lds, r1.p, lds, rfac.p, lds, rc_one<T>(), rc_zero<T>());
     c->cholqr_used++;
@@ -197,9 +210,11 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
     MatPtr q(mat_new(c, dtype, m, ncq));
     DevBuf<T> q1(c, (size_t)w * ncq);
 
+    rc_trace(c, nullptr);
     DevBuf<T> cq1, crinv2, crfac;
     int64_t lds = 0;
     if (cholqr2<T>(c, y, ldy, m, w, sharded, dtype, cq1, crinv2, crfac, lds)) {
+        rc_trace(c, "pqr_tall: cholqr2");
         // pivot on R = R2 R1, then Q = q1 (R2^{-1} Q1piv)
         k_transpose<T>(c, wc.p, w, crfac.p, lds, w, w, false);
         pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
@@ -220,7 +235,9 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
         // Panels of at most min(wmax, Cholesky width) columns.  Each panel is orthogonalised against the
         // previous ones (block classical Gram-Schmidt, twice) and then factored on its own: Cholesky-QR2 when
         // it is well conditioned (all GEMM-shaped, tensor pipe), Householder TSQR otherwise.
-        const int64_t wpan = std::min(wmax, c->qr_mode == 1 ? wmax : chol_max_width(c, dtype));
+        int64_t wpan = std::min(wmax, c->qr_mode == 1 ? wmax : chol_max_width(c, dtype));
+        const bool single = (dtype == RC_F32 || dtype == RC_C32);
+        (void)single;
         int64_t npan = (w + wpan - 1) / wpan;
         int64_t wp = (w + npan - 1) / npan;
         {   // panel starts on 16-byte boundaries (TMA operand alignment), as long as the panel still fits
@@ -245,12 +262,15 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
                     k_sub<T>(c, yp, ldy, yp, ldy, proj.p, ldt, m, cw);                    // Y_p -= Q (Q^H Y_p)
                     k_add<T>(c, r0.p + c0, w, r0.p + c0, w, t.p, ldt, c0, cw);             // R0[0:c0, c0:c0+cw] += t
                 }
+                rc_trace(c, "pqr_tall: panel projection x2");
             }
             DevBuf<T> pq1, prinv2, prfac;
             int64_t lds = 0;
             if (cholqr2<T>(c, yp, ldy, m, cw, sharded, dtype, pq1, prinv2, prfac, lds)) {
+                rc_trace(c, "pqr_tall: panel cholqr2");
                 gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, cw, pq1.p, lds, prinv2.p, lds, qfull.p + c0, ldq, rc_one<T>(), rc_zero<T>());
                 k_copy<T>(c, r0.p + c0 * w + c0, w, prfac.p, lds, cw, cw);
+                rc_trace(c, "pqr_tall: panel Q = q1 rinv2");
             } else {
                 DistTsqr<T> ts;
                 ts.factor(c, yp, ldy, m, cw, sharded);
@@ -262,10 +282,12 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
         }
         k_transpose<T>(c, wc.p, w, r0.p, w, w, w, false);
         pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
+        rc_trace(c, "pqr_tall: pivoted QR of R");
         const int64_t ldq1 = rc_pad_ld(dtype, ncq);
         DevBuf<T> q1p(c, (size_t)w * ldq1);
         pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1p.p, ldq1);
         gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, qfull.p, ldq, q1p.p, ldq1, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
+        rc_trace(c, "pqr_tall: form Q1, Q = Qfull Q1");
     }
     download_ind(c, dind.p, w, out.ind);
     out.q.reset(q.release());
@@ -442,7 +464,9 @@ rc_matrix* sample_by_rank_impl(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t
     MatPtr gen;
     if (!omega) { gen.reset(gaussian_new<T>(c, a->dtype, n, l, seed, 0, 0)); omega = gen.get(); }
     RC_REQUIRE(omega->rows == n && omega->cols == l, "omega must be %lld x %lld", (long long)n, (long long)l);
+    rc_trace(c, nullptr);
     MatPtr y(matmat_impl<T>(c, a, omega));                       // :111-112
+    rc_trace(c, "by_rank: Y = A Omega");
     QrParts qr;
     int64_t kk = std::min<int64_t>(mat_sharded(a) ? a->global_rows : a->rows, l);
     pivoted_qr_impl<T>(c, y.get(), false, std::min(k, kk), true, qr);   // :114-115 compress(RANK(k))
@@ -807,6 +831,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
         else if (!strcmp(key, "true_power_iteration")) c->true_power_iteration = (int)v;
         else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;
         else if (!strcmp(key, "reuse_range_b")) c->reuse_range_b = (int)v;
+        else if (!strcmp(key, "trace")) c->trace = (int)v;
         else RC_THROW(RC_INVALID_ARGUMENT, "unknown option '%s'", key);
     });
 }

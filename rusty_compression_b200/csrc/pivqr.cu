@@ -246,7 +246,7 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
 // Small factors (the l x l R of a sketch): one CTA, everything in shared memory, and the serial part
 // of a step (argmax -> pivot column -> ?larfg scalars) done by ONE warp, so a step costs two block
 // barriers instead of seven.  Same pivot rule and numerics as pivqr_kernel.
-template <class T, int NT>
+template <class T, int NT, int LPC>
 __global__ void __launch_bounds__(NT)
 pivqr_small_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, int* __restrict__ ind,
                    T* __restrict__ vbuf, T* __restrict__ tau_out, T* __restrict__ diag) {
@@ -305,23 +305,36 @@ pivqr_small_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, int* 
         }
         __syncthreads();
         const T ctau = rc_conj(s_tau);
-        for (int c = warp; c < n; c += NW) {
-            if (lpos[c] <= i) continue;
-            T* col = W + (size_t)c * p;
+        // trailing update: LPC lanes per column, 32 / LPC columns per warp at a time (for the l x l factors of
+        // the path, p <= 128, all columns are updated in ONE pass of the 32 warps with 3-step reductions)
+        {
+            constexpr int CPW = 32 / LPC;
+            const int sl = lane % LPC, sc = lane / LPC;
             using A = typename AccOf<T>::type;
-            A part = rc_zero<A>();
-            for (int r = i + 1 + lane; r < p; r += 32) part = rc_cfma(rc_widen(xs[r]), rc_widen(col[r]), part);
-            part = rc_warp_sum(part);
-            T ci = col[i];
-            T f = ctau * rc_narrow<T>(rc_widen(ci) + part);
-            double nrm = 0.0;
-            for (int r = i + 1 + lane; r < p; r += 32) {
-                T v = col[r] - f * xs[r];
-                col[r] = v;
-                nrm += rc_abs2(v);
+            for (int cb = warp * CPW; cb < n; cb += NW * CPW) {
+                const int c = cb + sc;
+                const bool act = (c < n) && (lpos[min(c, n - 1)] > i);
+                T* col = W + (size_t)min(c, n - 1) * p;
+                A part = rc_zero<A>();
+                if (act)
+                    for (int r = i + 1 + sl; r < p; r += LPC) part = rc_cfma(rc_widen(xs[r]), rc_widen(col[r]), part);
+#pragma unroll
+                for (int m = LPC / 2; m > 0; m >>= 1) part = part + rc_shfl_xor(part, m);
+                T ci = rc_zero<T>(), f = rc_zero<T>();
+                double nrm = 0.0;
+                if (act) {
+                    ci = col[i];
+                    f = ctau * rc_narrow<T>(rc_widen(ci) + part);
+                    for (int r = i + 1 + sl; r < p; r += LPC) {
+                        T v = col[r] - f * xs[r];
+                        col[r] = v;
+                        nrm += rc_abs2(v);
+                    }
+                }
+#pragma unroll
+                for (int m = LPC / 2; m > 0; m >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, m);
+                if (act && sl == 0) { col[i] = ci - f; vn[c] = sqrt(nrm); }
             }
-            nrm = rc_warp_sum(nrm);
-            if (lane == 0) { col[i] = ci - f; vn[c] = sqrt(nrm); }
         }
         __syncthreads();
     }
@@ -385,8 +398,13 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
     if (smem_all + 8192 <= lim && n <= 2048) {
         // small factor: one CTA, matrix resident in shared memory
         constexpr int NTS = 1024;
-        RC_CUDA(cudaFuncSetAttribute(pivqr_small_kernel<T, NTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
-        pivqr_small_kernel<T, NTS><<<1, NTS, smem_all, c->stream>>>(wc, ldw, pi, ni, kk, ind, vbuf, tau, diag.p);
+        if (p <= 128) {
+            RC_CUDA(cudaFuncSetAttribute(pivqr_small_kernel<T, NTS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
+            pivqr_small_kernel<T, NTS, 8><<<1, NTS, smem_all, c->stream>>>(wc, ldw, pi, ni, kk, ind, vbuf, tau, diag.p);
+        } else {
+            RC_CUDA(cudaFuncSetAttribute(pivqr_small_kernel<T, NTS, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
+            pivqr_small_kernel<T, NTS, 32><<<1, NTS, smem_all, c->stream>>>(wc, ldw, pi, ni, kk, ind, vbuf, tau, diag.p);
+        }
         RC_CHECK_LAUNCH(c);
     } else {
         constexpr int NT = 1024, CU = std::is_same<T, c64>::value ? 2 : 4;   // c64 x 4 columns spills at 64 registers

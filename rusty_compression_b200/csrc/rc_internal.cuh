@@ -47,6 +47,8 @@ struct rc_ctx {
     // options
     int gemm_impl = 0;            // 0 auto, 1 generic only
     int true_power_iteration = 0;
+    int trace = 0;                // option "trace": print wall time between rc_trace() marks (stream-synchronising)
+    double trace_t0 = 0.0;
     int reuse_range_b = 1;        // reuse B = Q^H A of the adaptive sampler in compute_from_range_estimate
     int qr_mode = 0;              // 0 auto (Cholesky-QR2 fast path with Householder-TSQR fallback), 1 TSQR only
     int64_t cholqr_used = 0, cholqr_fallbacks = 0, range_b_reused = 0;

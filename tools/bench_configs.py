@@ -1,5 +1,6 @@
-"""One pass of BASELINE configs 3 and 5 at full size (parity-test cases, not bench lines): timing of each
-stage plus the size-independent properties the domain offers.  Usage: tools/bench_configs.py [3] [5]"""
+"""BASELINE configs 3 and 5 at full size (parity-test cases, not bench lines): wall time of each stage
+(second, warm pass reported as well as the first, cold one) plus the size-independent properties the
+domain offers.  Usage: tools/bench_configs.py [3] [5]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -23,11 +24,15 @@ if 3 in which:
     n = 32768
     print(f"config 3: f32 {n}x{n}, sigma_j = 10^(-j/64), adaptive tol 1e-4, sample_size 64")
     a = timed("generate A on device", lambda: api.decaying_spectrum_matrix((n, n), np.float32, 1235, r0=1024, decade_every=64.0))
-    q, hist = timed("sample_range_adaptive(1e-4, 64)", lambda: api.sample_range_adaptive(a, 1e-4, 64, seed=42, device=True))
+    for rep in ("cold", "warm"):
+        print(f"  -- {rep} pass")
+        t0 = time.perf_counter()
+        q, hist = timed("sample_range_adaptive(1e-4, 64)", lambda: api.sample_range_adaptive(a, 1e-4, 64, seed=42, device=True))
+        qr = timed("QR::compute_from_range_estimate", lambda: api.QR.compute_from_range_estimate(q, a))
+        qrc = timed("compress(ADAPTIVE(1e-4))", lambda: qr.compress(api.ADAPTIVE(1e-4)))
+        cid = timed("column_id()", lambda: qrc.column_id())
+        ctx.synchronize(); print(f"   {'pipeline total':<46s} {(time.perf_counter() - t0) * 1e3:9.2f} ms")
     print("   ranks/residuals:", [(r, float(f"{e:.2e}")) for r, e in hist])
-    qr = timed("QR::compute_from_range_estimate", lambda: api.QR.compute_from_range_estimate(q, a))
-    qrc = timed("compress(ADAPTIVE(1e-4))", lambda: qr.compress(api.ADAPTIVE(1e-4)))
-    cid = timed("column_id()", lambda: qrc.column_id())
     k = qrc.rank()
     # property: ||A - C Z|| / ||A|| ~ tol, checked on a random probe (A - CZ) x without forming CZ
     x = api.DeviceMatrix.random_gaussian((n, 8), np.float32, 3)
@@ -45,11 +50,15 @@ if 5 in which:
     from oracle.inputs import helmholtz_kernel_matrix
     t0 = time.perf_counter(); ah = helmholtz_kernel_matrix(n, n, np.complex128); print(f"   host generation {time.perf_counter()-t0:.1f} s")
     a = timed("upload A (4 GiB)", lambda: api.DeviceMatrix.from_numpy(ah))
-    q = timed("sample_range_by_rank(128, 10)", lambda: api.sample_range_by_rank(a, k, p, seed=42, device=True))
-    qr = timed("QR::compute_from_range_estimate", lambda: api.QR.compute_from_range_estimate(q, a))
-    qrc = timed("compress(RANK(128))", lambda: qr.compress(api.RANK(k)))
-    cid = timed("column_id()", lambda: qrc.column_id())
-    ts = timed("two_sided_id()", lambda: cid.two_sided_id())
+    for rep in ("cold", "warm"):
+        print(f"  -- {rep} pass")
+        t0 = time.perf_counter()
+        q = timed("sample_range_by_rank(128, 10)", lambda: api.sample_range_by_rank(a, k, p, seed=42, device=True))
+        qr = timed("QR::compute_from_range_estimate", lambda: api.QR.compute_from_range_estimate(q, a))
+        qrc = timed("compress(RANK(128))", lambda: qr.compress(api.RANK(k)))
+        cid = timed("column_id()", lambda: qrc.column_id())
+        ts = timed("two_sided_id()", lambda: cid.two_sided_id())
+        ctx.synchronize(); print(f"   {'pipeline total':<46s} {(time.perf_counter() - t0) * 1e3:9.2f} ms")
     x = api.DeviceMatrix.random_gaussian((n, 4), np.complex128, 3)
     ax = a.matmat(x).to_numpy()
     err_c = np.linalg.norm(ax - cid.dot(x.to_numpy())) / np.linalg.norm(ax)
