@@ -60,25 +60,31 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, 0.0
 
     def start(self):
+        """Started BEFORE the warm-up steps: the first nvidia-smi on a fresh box takes seconds to come up and
+        would otherwise disturb the timed region; only samples taken after mark() are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def mark(self):
+        self.t_mark = time.monotonic()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_end = time.monotonic()
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -86,7 +92,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t_mark <= t <= t_end + 0.05] or [r for _, r in self.rows[-2:]]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, flag in zip(names, r[5:9]):
@@ -202,7 +209,7 @@ def main():
     result_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--m", type=int, default=None, help="rows per GPU (default: config)")
@@ -259,10 +266,12 @@ def main():
         svd = api.SVD.compute_from_range_estimate(q, a_dev)
         return q, svd
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, on_start=None):
         for _ in range(warmup):
             fn()
         barrier()
+        if on_start:
+            on_start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
@@ -282,7 +291,7 @@ def main():
         sampler.start()
     ctx.reset_counters()
     launches_before = ctx.counter("kernel_launches")
-    ms_step = timed(step_device, args.steps, args.warmup)
+    ms_step = timed(step_device, args.steps, args.warmup, on_start=sampler.mark)
     launches = (ctx.counter("kernel_launches") - launches_before) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop() if rank == 0 else None
 

@@ -107,6 +107,20 @@ rc_status rc_matrix_from_host(rc_ctx* ctx, rc_dtype dtype, const void* host, int
 /* Borrow device memory (row-major, leading dimension `ld` elements); never freed by the library. */
 rc_status rc_matrix_wrap_device(rc_ctx* ctx, rc_dtype dtype, void* device_ptr, int64_t rows,
                                 int64_t cols, int64_t ld, rc_matrix** out);
+/* dst <- src, device to device, same shape and scalar type; leading dimensions may differ (wrapped buffers). */
+rc_status rc_matrix_copy(rc_ctx* ctx, const rc_matrix* src, rc_matrix* dst);
+/* Matrix-free operators -- the crate's plugin API (`MatVec`, `ConjMatVec`, `MatMat`, `ConjMatMat` implemented
+ * by the caller, src/types.rs:40-101; the samplers and compute_from_range_estimate are generic over them,
+ * src/random_sampling.rs:102,130,222, src/qr.rs:221-224, src/svd.rs:110-113).  The callbacks compute
+ * Y = A X (matmat; X cols x ncols, Y rows x ncols) and Z = A^H X (conj_matmat; X rows x ncols, Z cols x ncols)
+ * on DEVICE buffers, row-major with the given leading dimensions (in elements), enqueued on `cuda_stream`
+ * (the cudaStream_t the context works on); they return 0 on success.  The handle is accepted wherever an
+ * operator is: rc_matmat, rc_conj_matmat, the three samplers, rc_qr/rc_svd_compute_from_range_estimate.
+ * Entry points that need a dense matrix return RC_INVALID_ARGUMENT for it.  Free with rc_matrix_free. */
+typedef int (*rc_matmat_fn)(void* user, const void* x, int64_t ldx, int64_t ncols, void* y, int64_t ldy,
+                            void* cuda_stream);
+rc_status rc_operator_create(rc_ctx* ctx, rc_dtype dtype, int64_t rows, int64_t cols, rc_matmat_fn matmat,
+                             rc_matmat_fn conj_matmat, void* user, rc_matrix** out);
 /* Download to a dense row-major host buffer of rows*cols elements. */
 rc_status rc_matrix_to_host(rc_ctx* ctx, const rc_matrix* m, void* host);
 /* Device-to-device copy into a dense row-major device buffer (ld = cols). */

@@ -22,6 +22,9 @@ pub const RC_LAYOUT_ERROR: c_int = 3;
 pub const RC_PIVOTED_QR_ERROR: c_int = 4;
 pub const RC_INVALID_ARGUMENT: c_int = 5;
 
+/// `rc_matmat_fn` of include/rc_api.h: device-side product callback of a matrix-free operator.
+pub type rc_matmat_fn = Option<unsafe extern "C" fn(user: *mut c_void, x: *const c_void, ldx: i64, ncols: i64, y: *mut c_void, ldy: i64, cuda_stream: *mut c_void) -> c_int>;
+
 extern "C" {
     pub fn rc_version() -> c_int;
     pub fn rc_ctx_create(device: c_int, out: *mut *mut rc_ctx) -> c_int;
@@ -53,6 +56,8 @@ extern "C" {
     pub fn rc_random_orthogonal_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, seed: u64, stream: u32, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_random_approximate_low_rank_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, sigma_max: f64, sigma_min: f64, seed: u64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_decaying_spectrum_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, r0: i64, decade_every: f64, seed: u64, row_offset: i64, out: *mut *mut rc_matrix) -> c_int;
+    pub fn rc_matrix_copy(ctx: *mut rc_ctx, src: *const rc_matrix, dst: *mut rc_matrix) -> c_int;
+    pub fn rc_operator_create(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, matmat: rc_matmat_fn, conj_matmat: rc_matmat_fn, user: *mut c_void, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_tall_shard_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, r0: i64, decade_every: f64, seed: u64, row_offset: i64, m_total: i64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_rel_diff_fro(ctx: *mut rc_ctx, first: *const rc_matrix, second: *const rc_matrix, out: *mut f64) -> c_int;
     pub fn rc_rel_diff_l2(ctx: *mut rc_ctx, first: *const rc_matrix, second: *const rc_matrix, out: *mut f64) -> c_int;

@@ -18,6 +18,9 @@ PH = POINTER(c_void_p)
 PU64 = POINTER(c_uint64)
 PD = POINTER(c_double)
 
+# rc_matmat_fn: int (*)(void* user, const void* x, int64 ldx, int64 ncols, void* y, int64 ldy, void* cuda_stream)
+MATMAT_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p)
+
 # name -> (restype, argtypes); must list every symbol rc_api.h declares (tests/test_abi_symbols.py)
 SIGNATURES = {
     "rc_version": (c_int, []),
@@ -35,6 +38,8 @@ SIGNATURES = {
     "rc_matrix_create": (c_int, [H, c_int, c_int64, c_int64, PH]),
     "rc_matrix_from_host": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, PH]),
     "rc_matrix_wrap_device": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, PH]),
+    "rc_matrix_copy": (c_int, [H, H, H]),
+    "rc_operator_create": (c_int, [H, c_int, c_int64, c_int64, MATMAT_FN, MATMAT_FN, c_void_p, PH]),
     "rc_matrix_to_host": (c_int, [H, H, c_void_p]),
     "rc_matrix_to_device": (c_int, [H, H, c_void_p]),
     "rc_matrix_free": (c_int, [H]),

@@ -213,6 +213,11 @@ class DeviceMatrix:
         return out
 
     # -- plugin API
+    def copy_from(self, src):
+        """self <- src on the device (same shape and dtype)."""
+        self.ctx.check(self.ctx.lib.rc_matrix_copy(self.ctx.h, src.h, self.h))
+        return self
+
     def matmat(self, x):
         x = _as_dev(x, self.ctx)
         h = c_void_p()
@@ -241,6 +246,39 @@ class DeviceMatrix:
             self.free()
         except Exception:
             pass
+
+
+class Operator(DeviceMatrix):
+    """A matrix-free operator: the crate's plugin API (MatVec / ConjMatVec / MatMat / ConjMatMat implemented by
+    the caller, src/types.rs:40-101).  `matmat(x, ncols, y, stream)` and `conj_matmat(x, ncols, z, stream)`
+    receive DeviceMatrix views of the device buffers (x: cols x ncols -> y: rows x ncols; x: rows x ncols ->
+    z: cols x ncols) and the cudaStream_t (as an int) to enqueue their work on.  Accepted by the samplers and by
+    QR/SVD.compute_from_range_estimate in place of a dense DeviceMatrix."""
+
+    def __init__(self, shape, dtype, matmat, conj_matmat=None, ctx=None):
+        ctx = ctx or default_context()
+        rows, cols = int(shape[0]), int(shape[1])
+        dt = np.dtype(dtype)
+
+        def wrap(fn, in_rows, out_rows):
+            def cb(_user, x, ldx, ncols, y, ldy, stream):
+                try:
+                    xv = DeviceMatrix.wrap_device(x, in_rows, ncols, ldx, dt, ctx=ctx)
+                    yv = DeviceMatrix.wrap_device(y, out_rows, ncols, ldy, dt, ctx=ctx)
+                    fn(xv, int(ncols), yv, int(stream or 0))
+                    return 0
+                except Exception as e:          # never let an exception cross the C boundary
+                    self.last_exception = e
+                    return 1
+            return _lib.MATMAT_FN(cb)
+
+        self.last_exception = None
+        self._cb_matmat = wrap(matmat, cols, rows)                      # keep the thunks alive with the handle
+        self._cb_conj = wrap(conj_matmat, rows, cols) if conj_matmat else _lib.MATMAT_FN(0)
+        h = c_void_p()
+        ctx.check(ctx.lib.rc_operator_create(ctx.h, DTYPE_CODE[dt], rows, cols, self._cb_matmat, self._cb_conj, None,
+                                             ctypes.byref(h)))
+        super().__init__(ctx, h)
 
 
 def _as_dev(x, ctx=None):

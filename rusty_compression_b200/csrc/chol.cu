@@ -33,23 +33,26 @@ chol_inv_kernel(const T* __restrict__ g, int64_t ldg, int w, T* __restrict__ r, 
     if (lane == 0) s_red[warp] = defect;
     __syncthreads();
     if (tid == 0) { double d = 0.0; for (int i = 0; i < CT / 32; ++i) d = fmax(d, s_red[i]); status[3] = d; }
-    // Right-looking (outer-product) Cholesky with ONE block barrier per step: step j updates the trailing
-    // upper triangle with the UNSCALED row j, S[r][c] -= conj(S[j][r]) S[j][c] / d_j, so no thread has to wait
-    // for the scaled pivot row; the rows are scaled by 1 / sqrt(d_j) once at the end.  32 x 32 thread tile.
-    {
-        const int tx = lane, ty = warp;
+    // Right-looking (outer-product) Cholesky with ONE barrier per step: step j updates the trailing upper
+    // triangle with the UNSCALED row j, S[r][c] -= conj(S[j][r]) S[j][c] / d_j, so no thread has to wait for the
+    // scaled pivot row; the rows are scaled by 1 / sqrt(d_j) once at the end.  Only the first 256 threads
+    // (a 16 x 16 tile, named barrier) take part: the trailing block is at most a few thousand entries and a
+    // 1024-thread barrier per step would cost more than the update itself.
+    if (tid < 256) {
+        const int tx = tid & 15, ty = tid >> 4;
         for (int j = 0; j < w; ++j) {
             const double d = (double)rc_real(S[j * w + j]);
             if (tid == 0) { s_piv[j] = d; if (!(d > 0.0)) s_bad = 1; }
             const RealOf<T> id = (RealOf<T>)(1.0 / ((d > 0.0) ? d : 1.0));
-            for (int rr = j + 1 + ty; rr < w; rr += 32) {
+            for (int rr = j + 1 + ty; rr < w; rr += 16) {
                 const T f = rc_conj(S[j * w + rr]) * id;
-                for (int cc = j + 1 + tx; cc < w; cc += 32)
+                for (int cc = j + 1 + tx; cc < w; cc += 16)
                     if (cc >= rr) S[rr * w + cc] = S[rr * w + cc] - f * S[j * w + cc];
             }
-            __syncthreads();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
+    __syncthreads();
     // scale the rows: R[j][c] = S[j][c] / sqrt(d_j); diagonal real positive
     for (int e = tid; e < w * w; e += CT) {
         int i = e / w, j = e - i * w;

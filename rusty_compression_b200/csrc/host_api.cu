@@ -423,6 +423,14 @@ rc_matrix* gaussian_new(rc_ctx* c, int dtype, int64_t rows, int64_t cols, uint64
 template <class T>
 rc_matrix* matmat_impl(rc_ctx* c, const rc_matrix* a, const rc_matrix* x) {
     RC_REQUIRE(a->cols == x->rows, "matmat: operator has %lld columns, X has %lld rows", (long long)a->cols, (long long)x->rows);
+    if (a->op_matmat) {       // matrix-free operator: the caller's device callback (MatMat of src/types.rs:58-71)
+        MatPtr y(mat_new(c, a->dtype, a->rows, x->cols));
+        int rc = a->op_matmat(a->op_user, P<T>(x), x->ld, x->cols, y->data, y->ld, (void*)c->stream);
+        if (rc != 0) RC_THROW(RC_LINALG_ERROR, "operator matmat callback failed (%d)", rc);
+        c->launches++;
+        inherit_shard(y.get(), a);
+        return y.release();
+    }
     MatPtr y(mat_mul<T>(c, RC_OP_N, a, RC_OP_N, x));
     inherit_shard(y.get(), a);
     return y.release();
@@ -431,7 +439,16 @@ rc_matrix* matmat_impl(rc_ctx* c, const rc_matrix* a, const rc_matrix* x) {
 template <class T>
 rc_matrix* conj_matmat_impl(rc_ctx* c, const rc_matrix* a, const rc_matrix* x) {
     RC_REQUIRE(a->rows == x->rows, "conj_matmat: operator has %lld rows, X has %lld rows", (long long)a->rows, (long long)x->rows);
-    MatPtr z(mat_mul<T>(c, RC_OP_H, a, RC_OP_N, x));
+    MatPtr z;
+    if (a->op_matmat) {       // ConjMatMat of src/types.rs:88-101 through the caller's callback
+        RC_REQUIRE(a->op_conj_matmat, "operator has no conj_matmat callback");
+        z.reset(mat_new(c, a->dtype, a->cols, x->cols));
+        int rc = a->op_conj_matmat(a->op_user, P<T>(x), x->ld, x->cols, z->data, z->ld, (void*)c->stream);
+        if (rc != 0) RC_THROW(RC_LINALG_ERROR, "operator conj_matmat callback failed (%d)", rc);
+        c->launches++;
+    } else {
+        z.reset(mat_mul<T>(c, RC_OP_H, a, RC_OP_N, x));
+    }
     if (mat_sharded(a)) {
         // reduce the dense payload row by row when padded; ld == cols for the common case
         if (z->ld == z->cols) comm_allreduce_sum(c, z->data, (size_t)z->rows * z->cols, z->dtype);
@@ -915,10 +932,25 @@ rc_status rc_matrix_wrap_device(rc_ctx* c, rc_dtype dt, void* dptr, int64_t rows
         *out = m;
     });
 }
+/* Matrix-free operator handle: the crate's plugin API (MatVec / ConjMatVec / MatMat / ConjMatMat implemented by
+ * the caller, src/types.rs:40-101) for operators that are never materialised. */
+rc_status rc_operator_create(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t cols, rc_matmat_fn matmat, rc_matmat_fn conj_matmat,
+                             void* user, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(dt >= 0 && dt <= 3 && rows > 0 && cols > 0 && matmat, "bad arguments");
+        rc_matrix* m = new rc_matrix();
+        m->ctx = c; m->dtype = dt; m->rows = rows; m->cols = cols; m->ld = cols; m->data = nullptr; m->owns = false;
+        m->id = rc_next_matrix_id();
+        m->op_matmat = matmat; m->op_conj_matmat = conj_matmat; m->op_user = user;
+        *out = m;
+    });
+}
 rc_status rc_matrix_to_host(rc_ctx* c, const rc_matrix* m, void* host) {
     if (!c || !m) return RC_INVALID_ARGUMENT;
     return guard(c, [&] {
         if (m->rows * m->cols == 0) return;
+        RC_REQUIRE(!m->op_matmat, "a matrix-free operator has no entries to copy");
         RC_REQUIRE(host, "null host pointer");
         const size_t es = rc_dtype_size(m->dtype);
         RC_CUDA(cudaMemcpy2DAsync(host, m->cols * es, m->data, m->ld * es, m->cols * es, m->rows, cudaMemcpyDeviceToHost, c->stream));
@@ -930,9 +962,20 @@ rc_status rc_matrix_to_device(rc_ctx* c, const rc_matrix* m, void* dptr) {
     if (!c || !m) return RC_INVALID_ARGUMENT;
     return guard(c, [&] {
         if (m->rows * m->cols == 0) return;
+        RC_REQUIRE(!m->op_matmat, "a matrix-free operator has no entries to copy");
         RC_REQUIRE(dptr, "null device pointer");
         const size_t es = rc_dtype_size(m->dtype);
         RC_CUDA(cudaMemcpy2DAsync(dptr, m->cols * es, m->data, m->ld * es, m->cols * es, m->rows, cudaMemcpyDeviceToDevice, c->stream));
+    });
+}
+/* dst <- src (device to device, same shape and scalar type; either side may be a wrapped buffer with its own
+ * leading dimension) -- what an operator callback needs to hand a product computed elsewhere back to the library. */
+rc_status rc_matrix_copy(rc_ctx* c, const rc_matrix* src, rc_matrix* dst) {
+    if (!c || !src || !dst) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        check_same(src, dst);
+        RC_REQUIRE(src->rows == dst->rows && src->cols == dst->cols, "rc_matrix_copy: shapes differ");
+        RC_DISPATCH(src->dtype, k_copy<T>(c, P<T>(dst), dst->ld, P<T>(src), src->ld, src->rows, src->cols));
     });
 }
 rc_status rc_matrix_free(rc_matrix* m) { mat_free(m); return RC_OK; }

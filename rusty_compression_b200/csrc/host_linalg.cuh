@@ -47,7 +47,10 @@ struct MatPtr {   // RAII owner used while a routine can still throw
     rc_matrix* operator->() const { return m; }
     rc_matrix* get() const { return m; }
 };
-template <class T> inline T* P(const rc_matrix* m) { return reinterpret_cast<T*>(m->data); }
+template <class T> inline T* P(const rc_matrix* m) {
+    if (m->op_matmat) RC_THROW(RC_INVALID_ARGUMENT, "a matrix-free operator handle was passed where a dense matrix is required");
+    return reinterpret_cast<T*>(m->data);
+}
 inline bool mat_sharded(const rc_matrix* m) { return m->global_rows > 0 && m->ctx->nranks > 1; }
 inline void inherit_shard(rc_matrix* dst, const rc_matrix* src) {
     dst->global_rows = src->global_rows;

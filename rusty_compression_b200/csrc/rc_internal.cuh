@@ -75,6 +75,10 @@ struct rc_matrix {
     uint64_t id = 0;
     rc_matrix* companion = nullptr;
     uint64_t companion_op_id = 0;
+    // matrix-free operator (rc_operator_create): no data, products go through the caller's callbacks
+    int (*op_matmat)(void*, const void*, int64_t, int64_t, void*, int64_t, void*) = nullptr;
+    int (*op_conj_matmat)(void*, const void*, int64_t, int64_t, void*, int64_t, void*) = nullptr;
+    void* op_user = nullptr;
 };
 
 inline size_t rc_dtype_size(int dt) {
