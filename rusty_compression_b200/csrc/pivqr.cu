@@ -20,7 +20,7 @@ namespace {
 // NT threads per CTA: 256 for the multi-CTA (wide) case, 1024 when one CTA holds the whole
 // matrix in shared memory (small factors such as the w x w R of a sketch).
 
-struct Cand {
+struct __align__(16) Cand {
     double val;
     int lpos;   // logical position (tie-break: smaller wins)
     int phys;
@@ -65,37 +65,46 @@ __device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ c32 ld_cg(const c32* p) { float2 v = __ldcg(reinterpret_cast<const float2*>(p)); return c32(v.x, v.y); }
 __device__ __forceinline__ c64 ld_cg(const c64* p) { double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return c64(v.x, v.y); }
 
-// W: p x n column-major (ld = ldw), resident in L2 for the k x n factors of the path (42 MB at
-// config 3).  Work arrays: vn (n doubles), lpos (n ints), slots: 2 * gridDim.x Cand + 2 * gridDim.x
-// ints (displaced column).  One CTA of NT threads per SM; every warp owns the columns
-// c = gw (mod GW) and updates CU of them at a time, so CU independent load -> dot -> shuffle-reduce
-// -> update chains are in flight per warp (the step is latency-bound, not bandwidth-bound).
+// Wide factors (the k x n factor b = Q^H A of compute_from_range_estimate, C^H in two_sided_id): one CTA of NT
+// threads per SM; CTA b owns the columns c = b (mod gridDim.x) and keeps as many of them as fit RESIDENT IN
+// SHARED MEMORY for the whole factorisation (all of them at config 5, 80 % at config 3), the rest stay in
+// global memory (L2).  One grid-wide sync per step: before it every CTA publishes its best candidate (norm,
+// logical position) AND that candidate's column to a global staging slot, so after the sync everybody reads
+// the winning column from the winner's slot -- no second sync to fetch a column that lives in another SM's
+// shared memory.  Every warp updates CU of its columns at a time (CU independent load -> dot ->
+// shuffle-reduce -> update chains in flight; the step is latency-bound, not bandwidth-bound).
 template <class T, int NT, int CU>
 __global__ void __launch_bounds__(NT)
-pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __restrict__ vn,
-             int* __restrict__ lpos, int* __restrict__ ind, T* __restrict__ vbuf, T* __restrict__ tau_out,
-             T* __restrict__ diag, Cand* __restrict__ slots, int* __restrict__ slots_disp) {
+pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int cap, int nlmax,
+             int* __restrict__ ind, T* __restrict__ vbuf, T* __restrict__ tau_out, T* __restrict__ diag,
+             Cand* __restrict__ slots, int* __restrict__ slots_disp, T* __restrict__ stage) {
     constexpr int NW = NT / 32;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* xs = reinterpret_cast<T*>(smem_raw);     // pivot column / reflector, p entries
+    T* xs = reinterpret_cast<T*>(smem_raw);                  // pivot column / reflector, p entries
+    T* scol = xs + p;                                        // cap resident columns, p entries each
+    double* vn = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(scol + (size_t)cap * p) + 7) & ~(uintptr_t)7);
+    int* lpos = reinterpret_cast<int*>(vn + nlmax);
     __shared__ Cand s_cand[NW];
     __shared__ int s_disp[NW];
     __shared__ double s_red[NW];
-    __shared__ Cand s_win;
+    __shared__ Cand s_win, s_bbest;
     __shared__ int s_windisp;
     __shared__ T s_hs[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gw = blockIdx.x * NW + warp, GW = gridDim.x * NW;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int nl = (b < n) ? (n - b + G - 1) / G : 0;         // columns owned by this CTA: c = li * G + b
+    auto colp = [&](int li) -> T* { return (li < cap) ? scol + (size_t)li * p : W + (int64_t)(li * G + b) * ldw; };
 
-    // initial norms and identity logical order
-    for (int c = gw; c < n; c += GW) {
-        const T* col = W + (int64_t)c * ldw;
+    // resident columns -> shared memory; initial norms and identity logical order
+    for (int li = warp; li < nl; li += NW) {
+        const T* src = W + (int64_t)(li * G + b) * ldw;
+        T* dst = colp(li);
         double a = 0.0;
-        for (int r = lane; r < p; r += 32) a += rc_abs2(col[r]);
+        for (int r = lane; r < p; r += 32) { T v = src[r]; if (li < cap) dst[r] = v; a += rc_abs2(v); }
         a = rc_warp_sum(a);
-        if (lane == 0) { vn[c] = sqrt(a); lpos[c] = c; }
+        if (lane == 0) { vn[li] = sqrt(a); lpos[li] = li * G + b; }
     }
     __syncthreads();
 
@@ -103,12 +112,12 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
         // (a) local candidates over owned, not yet pivoted columns
         Cand best; best.val = -1.0; best.lpos = 0x7fffffff; best.phys = -1;
         int disp = -1;
-        for (int c = gw + lane * GW; c < n; c += 32 * GW) {
-            int lp = lpos[c];
+        for (int li = tid; li < nl; li += NT) {
+            int lp = lpos[li];
             if (lp >= i) {
-                Cand cnd; cnd.val = vn[c]; cnd.lpos = lp; cnd.phys = c;
+                Cand cnd; cnd.val = vn[li]; cnd.lpos = lp; cnd.phys = li * G + b;
                 if (better(cnd, best)) best = cnd;
-                if (lp == i) disp = c;
+                if (lp == i) disp = li * G + b;
             }
         }
         best = warp_best(best);
@@ -117,45 +126,55 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
         if (lane == 0) { s_cand[warp] = best; s_disp[warp] = disp; }
         __syncthreads();
         if (warp == 0) {
-            Cand b; b.val = -1.0; b.lpos = 0x7fffffff; b.phys = -1;
+            Cand bb; bb.val = -1.0; bb.lpos = 0x7fffffff; bb.phys = -1;
             int d = -1;
-            if (lane < NW) { b = s_cand[lane]; d = s_disp[lane]; }
-            b = warp_best(b);
+            if (lane < NW) { bb = s_cand[lane]; d = s_disp[lane]; }
+            bb = warp_best(bb);
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, m));
             if (lane == 0) {
-                slots[(i & 1) * gridDim.x + blockIdx.x] = b;
-                slots_disp[(i & 1) * gridDim.x + blockIdx.x] = d;
+                s_bbest = bb;
+                slots[(i & 1) * G + b] = bb;
+                slots_disp[(i & 1) * G + b] = d;
             }
+        }
+        __syncthreads();
+        // publish this CTA's best column (rows i .. p-1) next to its candidate
+        if (s_bbest.phys >= 0) {
+            const T* src = colp(s_bbest.phys / G);
+            T* dst = stage + ((size_t)(i & 1) * G + b) * p;
+            for (int r = i + tid; r < p; r += NT) dst[r] = src[r];
         }
         // (b) one grid-wide sync per step
         grid.sync();
         // (c) global winner (every CTA reduces the same slots -> same answer)
         if (warp == 0) {
-            Cand b; b.val = -1.0; b.lpos = 0x7fffffff; b.phys = -1;
+            Cand bb; bb.val = -1.0; bb.lpos = 0x7fffffff; bb.phys = -1;
             int d = -1;
-            for (int s = lane; s < (int)gridDim.x; s += 32) {
-                Cand o = slots[(i & 1) * gridDim.x + s];
-                if (better(o, b)) b = o;
-                d = max(d, slots_disp[(i & 1) * gridDim.x + s]);
+            for (int s = lane; s < G; s += 32) {      // written by other SMs: bypass L1
+                const int4 raw = __ldcg(reinterpret_cast<const int4*>(slots + (i & 1) * G + s));
+                Cand o;
+                o.val = __hiloint2double(raw.y, raw.x); o.lpos = raw.z; o.phys = raw.w;
+                if (better(o, bb)) bb = o;
+                d = max(d, __ldcg(slots_disp + (i & 1) * G + s));
             }
-            b = warp_best(b);
+            bb = warp_best(bb);
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, m));
-            if (lane == 0) { s_win = b; s_windisp = d; }
+            if (lane == 0) { s_win = bb; s_windisp = d; }
         }
         __syncthreads();
         const int pv = s_win.phys;          // physical pivot column
         const int pv_lpos = s_win.lpos;     // where it sat logically
         const int dc = s_windisp;           // physical column sitting at logical position i
         // (d) logical swap, done by the owners
-        if (lane == 0) {
-            if (dc >= 0 && dc != pv && (dc % GW) == gw) lpos[dc] = pv_lpos;
-            if ((pv % GW) == gw) { lpos[pv] = i; }
+        if (tid == 0) {
+            if (dc >= 0 && dc != pv && (dc % G) == b) lpos[dc / G] = pv_lpos;
+            if ((pv % G) == b) lpos[pv / G] = i;
         }
-        if (blockIdx.x == 0 && tid == 0) ind[i] = pv;
-        // (e) reflector from the pivot column (rows i..p-1), redundantly per CTA
-        const T* pcol = W + (int64_t)pv * ldw;
+        if (b == 0 && tid == 0) ind[i] = pv;
+        // (e) reflector from the staged pivot column (rows i..p-1), redundantly per CTA
+        const T* pcol = stage + ((size_t)(i & 1) * G + (pv % G)) * p;
         double a = 0.0;
         for (int r = i + tid; r < p; r += NT) {
             T v = ld_cg(pcol + r);
@@ -176,7 +195,7 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
         const T tau = s_hs[0], scale = s_hs[1], beta = s_hs[2];
         for (int r = i + 1 + tid; r < p; r += NT) xs[r] = xs[r] * scale;
         __syncthreads();
-        if (blockIdx.x == 0) {
+        if (b == 0) {
             T* vcol = vbuf + (int64_t)i * p;
             for (int r = tid; r < p; r += NT) vcol[r] = (r < i) ? rc_zero<T>() : (r == i ? rc_one<T>() : xs[r]);
             if (tid == 0) { tau_out[i] = tau; diag[i] = beta; }
@@ -184,15 +203,15 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
         // (f) trailing update of owned columns + exact partial norms, CU columns per pass
         const T ctau = rc_conj(tau);
         using A = typename AccOf<T>::type;
-        for (int c0 = gw; c0 < n; c0 += GW * CU) {
+        for (int l0 = warp; l0 < nl; l0 += NW * CU) {
             T* col[CU];
             bool act[CU];
             bool any = false;
 #pragma unroll
             for (int j = 0; j < CU; ++j) {
-                const int c = c0 + j * GW;
-                act[j] = (c < n) && (lpos[min(c, n - 1)] > i);      // warp-uniform
-                col[j] = W + (int64_t)min(c, n - 1) * ldw;
+                const int li = l0 + j * NW;
+                act[j] = (li < nl) && (lpos[min(li, nl - 1)] > i);      // warp-uniform
+                col[j] = colp(min(li, nl - 1));
                 any |= act[j];
             }
             if (!any) continue;
@@ -230,15 +249,21 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, double* __res
             if (lane == 0) {
 #pragma unroll
                 for (int j = 0; j < CU; ++j)
-                    if (act[j]) { col[j][i] = ci[j] - f[j]; vn[c0 + j * GW] = sqrt(nrm[j]); }
+                    if (act[j]) { col[j][i] = ci[j] - f[j]; vn[l0 + j * NW] = sqrt(nrm[j]); }
             }
         }
-        __syncthreads();   // xs is rewritten next step; lpos/vn written by lane 0 are read by the warp
+        __syncthreads();   // xs is rewritten next step; lpos/vn written by lane 0 are read by the block
     }
     // final logical order for the never-pivoted columns (n > p)
-    for (int c = gw + lane * GW; c < n; c += 32 * GW) {
-        int lp = lpos[c];
-        if (lp >= kk) ind[lp] = c;
+    for (int li = tid; li < nl; li += NT) {
+        int lp = lpos[li];
+        if (lp >= kk) ind[lp] = li * G + b;
+    }
+    // resident columns back to global memory (gather_r_kernel reads the factored W)
+    for (int li = warp; li < min(nl, cap); li += NW) {
+        T* dst = W + (int64_t)(li * G + b) * ldw;
+        const T* src = scol + (size_t)li * p;
+        for (int r = lane; r < p; r += 32) dst[r] = src[r];
     }
 }
 
@@ -409,17 +434,23 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
     } else {
         constexpr int NT = 1024, CU = std::is_same<T, c64>::value ? 2 : 4;   // c64 x 4 columns spills at 64 registers
         constexpr int NW = NT / 32;
-        size_t smem = (size_t)p * sizeof(T);
-        RC_REQUIRE(smem + 4096 <= lim, "pivoted_qr: %lld rows exceed the shared-memory column buffer", (long long)p);
+        RC_REQUIRE((size_t)p * sizeof(T) + 16384 <= lim, "pivoted_qr: %lld rows exceed the shared-memory column buffer", (long long)p);
+        int64_t want = (n + NW * 2 - 1) / (NW * 2);       // at least ~2 columns per warp
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, c->sm_count));
+        int nlmax = (int)((n + grid - 1) / grid);
+        // resident columns per CTA: whatever fits next to the reflector and the norm / position tables
+        size_t fixed = (size_t)p * sizeof(T) + (size_t)nlmax * (sizeof(double) + sizeof(int)) + 64;
+        int cap = (int)std::min<int64_t>(nlmax, (int64_t)((lim - 6144 - fixed) / ((size_t)p * sizeof(T))));
+        if (cap < 0) cap = 0;
+        size_t smem = fixed + (size_t)cap * p * sizeof(T);
         RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T, NT, CU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pivqr_kernel<T, NT, CU>, NT, smem));
         RC_REQUIRE(per_sm >= 1, "pivoted_qr: kernel does not fit on an SM");
-        int64_t want = (n + NW * 2 - 1) / (NW * 2);       // at least ~2 columns per warp
-        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, c->sm_count));
         DevBuf<Cand> slots(c, (size_t)2 * grid);
         DevBuf<int> slots_disp(c, (size_t)2 * grid);
-        void* args[] = {&wc, &ldw, &pi, &ni, &kk, &vn.p, &lpos.p, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p};
+        DevBuf<T> stage(c, (size_t)2 * grid * p);
+        void* args[] = {&wc, &ldw, &pi, &ni, &kk, &cap, &nlmax, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p, &stage.p};
         RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T, NT, CU>, dim3(grid), dim3(NT), args, smem, c->stream));
         RC_COUNT_LAUNCH(c);
     }

@@ -94,7 +94,10 @@ def test_dmma_tma_gemm_matches_generic_and_numpy(api, dtype, shape):
     assert relerr(z_fast, np.conj(a.T).dot(y)) < 1e-13 and relerr(z_gen, np.conj(a.T).dot(y)) < 1e-13
 
 
-@pytest.mark.parametrize("shape", [(4096, 1024, 74), (1000, 516, 10), (777, 1028, 138), (2048, 512, 266), (130, 4096, 20)])
+@pytest.mark.parametrize("shape", [(4096, 1024, 74), (1000, 516, 10), (777, 1028, 138), (2048, 512, 266), (130, 4096, 20),
+                                   # more work items than SMs (every CTA crosses item boundaries, with and without
+                                   # column chunks): the regime in which a too-early release of the raw A slot showed
+                                   (4096, 128, 2048), (8192, 4096, 320), (32768, 256, 64), (20000, 96, 200)])
 def test_tcgen05_tf32x3_gemm_matches_f64_reference(api, shape):
     """f32 Y = A X on tcgen05 (kind::tf32, 3-product split, TMEM accumulators; gemm_tf32.cu) against a
     float64 reference and against the SIMT kernel: f32-level accuracy, far inside the 1e-4 of north_star."""
@@ -123,7 +126,7 @@ def test_tcgen05_tf32x3_gemm_matches_f64_reference(api, shape):
     assert relerr(z_tc, want_t) < 5e-6, relerr(z_tc, want_t)
 
 
-@pytest.mark.parametrize("shape", [(2048, 512, 74), (1000, 258, 20)])
+@pytest.mark.parametrize("shape", [(2048, 512, 74), (1000, 258, 20), (4096, 64, 1024), (4096, 1024, 266)])
 def test_c32_runs_on_tcgen05_through_real_expansion(api, shape):
     """c32 contractions reuse the tcgen05 TF32x3 kernels through the exact real expansion."""
     m, n, l = shape
