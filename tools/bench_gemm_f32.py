@@ -6,7 +6,10 @@ import torch
 from rusty_compression_b200 import api
 ctx = api.default_context()
 stream = torch.cuda.Stream(); ctx.set_stream(stream.cuda_stream)
-for (m, n, l) in [(32768, 32768, 64), (65536, 8192, 266), (65536, 8192, 74)]:
+shapes = [(32768, 32768, 64), (65536, 8192, 266), (65536, 8192, 74)]
+if len(sys.argv) > 1:
+    shapes = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]]
+for (m, n, l) in shapes:
     a = api.DeviceMatrix.random_gaussian((m, n), np.float32, 1)
     x = api.DeviceMatrix.random_gaussian((n, l), np.float32, 2)
     for impl in ((0,) if os.environ.get('RC_SKIP_SIMT') else (0, 1)):
