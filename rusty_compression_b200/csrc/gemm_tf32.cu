@@ -195,15 +195,14 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                    const __grid_constant__ CUtensorMap tmBlo, Tf32Params prm) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    __shared__ __align__(8) unsigned long long bars[2 * MAX_RS + 2 * MAX_MS + 2 * MAX_BS + 4];
+    __shared__ __align__(8) unsigned long long bars[2 * MAX_RS + 2 * MAX_MS + MAX_BS + 4];
     __shared__ uint32_t tmem_base_smem;
     const uint32_t rawfull0 = smem_u32(&bars[0]);                          // raw A tile landed
     const uint32_t rawempty0 = smem_u32(&bars[MAX_RS]);                    // raw A tile consumed by the splitter
     const uint32_t split0 = smem_u32(&bars[2 * MAX_RS]);                   // A_hi / A_lo written
     const uint32_t aempty0 = smem_u32(&bars[2 * MAX_RS + MAX_MS]);         // MMAs that read A_hi / A_lo are done
     const uint32_t bfull0 = smem_u32(&bars[2 * MAX_RS + 2 * MAX_MS]);      // B tiles landed
-    const uint32_t bempty0 = smem_u32(&bars[2 * MAX_RS + 2 * MAX_MS + MAX_BS]);
-    const uint32_t accf0 = smem_u32(&bars[2 * MAX_RS + 2 * MAX_MS + 2 * MAX_BS]);      // accumulator buffer full (2)
+    const uint32_t accf0 = smem_u32(&bars[2 * MAX_RS + 2 * MAX_MS + MAX_BS]);          // accumulator buffer full (2)
     const uint32_t acce0 = accf0 + 16;                                                 // accumulator buffer drained (2)
 
     constexpr int npad = NPADC;
@@ -216,7 +215,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (tid == 0) {
         for (int s = 0; s < RS; ++s) { mbar_init(rawfull0 + 8 * s, 1); mbar_init(rawempty0 + 8 * s, 4); }
         for (int s = 0; s < MS; ++s) { mbar_init(split0 + 8 * s, 4); mbar_init(aempty0 + 8 * s, 1); }
-        for (int s = 0; s < BS; ++s) { mbar_init(bfull0 + 8 * s, 1); mbar_init(bempty0 + 8 * s, 1); }
+        for (int s = 0; s < BS; ++s) mbar_init(bfull0 + 8 * s, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -339,12 +339,15 @@ void pivoted_qr_impl(rc_ctx* c, const rc_matrix* arr, bool input_is_conj_transpo
     } else {
         k_transpose<T>(c, wc.p, p, P<T>(arr), arr->ld, p, n, false);
     }
+    rc_trace(c, "  pivoted_qr: column-major copy");
     DevBuf<T> vbuf(c, (size_t)p * kk), tau(c, (size_t)kk);
     DevBuf<int> dind(c, (size_t)n);
     MatPtr r(mat_new(c, dtype, kk, n));
     pivqr_factor<T>(c, wc.p, p, p, n, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
+    rc_trace(c, "  pivoted_qr: factor + gather R");
     MatPtr q(mat_new(c, dtype, p, ncq));
     pivqr_form_q<T>(c, vbuf.p, tau.p, p, kk, ncq, P<T>(q.get()), q->ld);
+    rc_trace(c, "  pivoted_qr: form Q");
     download_ind(c, dind.p, n, out.ind);
     out.q.reset(q.release());
     out.r.reset(r.release());
@@ -568,27 +571,35 @@ rc_matrix* sample_adaptive_impl(rc_ctx* c, const rc_matrix* a, double rel_tol_in
             qbuf.reset(q2.release()); bbuf.reset(b2.release());
             cur = grown;
         }
+        rc_trace(c, nullptr);
         if (r > 0) {                                                             // :250-252
             DevBuf<T> t(c, (size_t)r * s);
             gemm<T>(c, RC_OP_H, RC_OP_N, r, s, m, P<T>(qbuf.get()), qbuf->ld, P<T>(y.get()), y->ld, t.p, s, rc_one<T>(), rc_zero<T>());
             if (mat_sharded(a)) comm_allreduce_sum(c, t.p, (size_t)r * s, a->dtype);
             gemm<T>(c, RC_OP_N, RC_OP_N, m, s, r, P<T>(qbuf.get()), qbuf->ld, t.p, s, P<T>(y.get()), y->ld, rc_make<T>(-1.0, 0.0), rc_one<T>());
         }
+        rc_trace(c, "adaptive: Y -= Q (Q^H Y)");
         QrParts qq;
         pivoted_qr_impl<T>(c, y.get(), false, -1, true, qq);                     // :254
+        rc_trace(c, "adaptive: pivoted QR of Y");
         const int64_t sq = qq.q->cols;
         MatPtr z(conj_matmat_impl<T>(c, a, qq.q.get()));                          // :256-260  (A^H q)
+        rc_trace(c, "adaptive: A^H q");
         k_transpose<T>(c, P<T>(bbuf.get()) + r * bbuf->ld, bbuf->ld, P<T>(z.get()), z->ld, n, sq, true);
         k_copy<T>(c, P<T>(qbuf.get()) + r, qbuf->ld, P<T>(qq.q.get()), qq.q->ld, m, sq);   // :262
         r += sq;
         omega = next_omega(om);                                                  // :265
+        rc_trace(c, "adaptive: append B, Q, draw Omega");
         y.reset(matmat_impl<T>(c, a, omega));                                    // :266  A Omega
+        rc_trace(c, "adaptive: A Omega");
         {
             DevBuf<T> t(c, (size_t)r * s);
             gemm<T>(c, RC_OP_N, RC_OP_N, r, s, n, P<T>(bbuf.get()), bbuf->ld, P<T>(omega), omega->ld, t.p, s, rc_one<T>(), rc_zero<T>());
             gemm<T>(c, RC_OP_N, RC_OP_N, m, s, r, P<T>(qbuf.get()), qbuf->ld, t.p, s, P<T>(y.get()), y->ld, rc_make<T>(-1.0, 0.0), rc_one<T>());
         }
+        rc_trace(c, "adaptive: Y -= Q (B Omega)");
         max_norm = (R)max_col_norm_impl<T>(c, y.get()) * tol_factor;             // :269
+        rc_trace(c, "adaptive: max_col_norm");
         hist_rank.push_back((uint64_t)r);
         hist_res.push_back((double)(max_norm / operator_norm));                  // :270
     }
@@ -618,10 +629,14 @@ rc_matrix* ah_range(rc_ctx* c, const rc_matrix* op, const rc_matrix* range) {
 template <class T>
 void qr_from_range_impl(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, QrParts& out) {
     RC_REQUIRE(range->rows == op->rows, "range estimate and operator row counts differ");
+    rc_trace(c, nullptr);
     MatPtr z(ah_range<T>(c, op, range));                         // A^H Q  (n x k)
+    rc_trace(c, "qr_from_range: A^H Q");
     QrParts qb;
     pivoted_qr_impl<T>(c, z.get(), true, -1, false, qb);         // pivoted QR of b = (A^H Q)^H, :315-316
+    rc_trace(c, "qr_from_range: pivoted QR of b");
     out.q.reset(mat_mul<T>(c, RC_OP_N, range, RC_OP_N, qb.q.get()));   // :319
+    rc_trace(c, "qr_from_range: Q q_b");
     inherit_shard(out.q.get(), range);
     out.r.reset(qb.r.release());
     out.ind = qb.ind;

@@ -73,13 +73,18 @@ __device__ __forceinline__ c64 ld_cg(const c64* p) { double2 v = __ldcg(reinterp
 // the winning column from the winner's slot -- no second sync to fetch a column that lives in another SM's
 // shared memory.  Every warp updates CU of its columns at a time (CU independent load -> dot ->
 // shuffle-reduce -> update chains in flight; the step is latency-bound, not bandwidth-bound).
-template <class T, int NT, int CU>
+template <class T, int NT, int LPC, int CU>
 __global__ void __launch_bounds__(NT)
 pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int cap, int nlmax,
              int* __restrict__ ind, T* __restrict__ vbuf, T* __restrict__ tau_out, T* __restrict__ diag,
-             Cand* __restrict__ slots, int* __restrict__ slots_disp, T* __restrict__ stage) {
+             Cand* __restrict__ slots, int* __restrict__ slots_disp, T* __restrict__ stage,
+             long long* __restrict__ prof) {
     constexpr int NW = NT / 32;
     cg::grid_group grid = cg::this_grid();
+    // optional phase timer (option "trace"): cycles of block 0 spent in each phase, summed over the steps
+    const bool timing = (prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t_prev = 0;
+#define RC_PHASE(k) do { if (timing) { long long t_now = clock64(); prof[k] += t_now - t_prev; t_prev = t_now; } } while (0)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* xs = reinterpret_cast<T*>(smem_raw);                  // pivot column / reflector, p entries
     T* scol = xs + p;                                        // cap resident columns, p entries each
@@ -108,6 +113,7 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int cap, int 
     }
     __syncthreads();
 
+    if (timing) t_prev = clock64();
     for (int i = 0; i < kk; ++i) {
         // (a) local candidates over owned, not yet pivoted columns
         Cand best; best.val = -1.0; best.lpos = 0x7fffffff; best.phys = -1;
@@ -145,23 +151,37 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int cap, int 
             T* dst = stage + ((size_t)(i & 1) * G + b) * p;
             for (int r = i + tid; r < p; r += NT) dst[r] = src[r];
         }
+        RC_PHASE(0);      // candidates + publish
         // (b) one grid-wide sync per step
         grid.sync();
-        // (c) global winner (every CTA reduces the same slots -> same answer)
-        if (warp == 0) {
-            Cand bb; bb.val = -1.0; bb.lpos = 0x7fffffff; bb.phys = -1;
-            int d = -1;
-            for (int s = lane; s < G; s += 32) {      // written by other SMs: bypass L1
-                const int4 raw = __ldcg(reinterpret_cast<const int4*>(slots + (i & 1) * G + s));
-                Cand o;
-                o.val = __hiloint2double(raw.y, raw.x); o.lpos = raw.z; o.phys = raw.w;
-                if (better(o, bb)) bb = o;
-                d = max(d, __ldcg(slots_disp + (i & 1) * G + s));
-            }
-            bb = warp_best(bb);
+        RC_PHASE(1);      // grid sync
+        // (c) global winner (every CTA reduces the same slots -> same answer): one slot per thread (written by
+        // other SMs: L1 bypassed), so the L2 round trip is paid once, then two levels of warp reductions
+        {
+            const int nsw = (G + 31) / 32;           // warps that hold slots
+            if (warp < nsw) {
+                Cand bb; bb.val = -1.0; bb.lpos = 0x7fffffff; bb.phys = -1;
+                int d = -1;
+                if (tid < G) {
+                    const int4 raw = __ldcg(reinterpret_cast<const int4*>(slots + (i & 1) * G + tid));
+                    bb.val = __hiloint2double(raw.y, raw.x); bb.lpos = raw.z; bb.phys = raw.w;
+                    d = __ldcg(slots_disp + (i & 1) * G + tid);
+                }
+                bb = warp_best(bb);
 #pragma unroll
-            for (int m = 16; m > 0; m >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, m));
-            if (lane == 0) { s_win = bb; s_windisp = d; }
+                for (int m = 16; m > 0; m >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, m));
+                if (lane == 0) { s_cand[warp] = bb; s_disp[warp] = d; }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                Cand bb; bb.val = -1.0; bb.lpos = 0x7fffffff; bb.phys = -1;
+                int d = -1;
+                if (lane < nsw) { bb = s_cand[lane]; d = s_disp[lane]; }
+                bb = warp_best(bb);
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, m));
+                if (lane == 0) { s_win = bb; s_windisp = d; }
+            }
         }
         __syncthreads();
         const int pv = s_win.phys;          // physical pivot column
@@ -173,6 +193,7 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int cap, int 
             if ((pv % G) == b) lpos[pv / G] = i;
         }
         if (b == 0 && tid == 0) ind[i] = pv;
+        RC_PHASE(2);      // winner
         // (e) reflector from the staged pivot column (rows i..p-1), redundantly per CTA
         const T* pcol = stage + ((size_t)(i & 1) * G + (pv % G)) * p;
         double a = 0.0;
@@ -200,60 +221,123 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int cap, int 
             for (int r = tid; r < p; r += NT) vcol[r] = (r < i) ? rc_zero<T>() : (r == i ? rc_one<T>() : xs[r]);
             if (tid == 0) { tau_out[i] = tau; diag[i] = beta; }
         }
-        // (f) trailing update of owned columns + exact partial norms, CU columns per pass
+        RC_PHASE(3);      // reflector
+        // (f) trailing update of owned columns + exact partial norms.  LPC lanes share a column (the rows of a
+        // k x n factor are few: 10-20 per lane), so a warp works on (32 / LPC) * CU columns at once and the
+        // dependent chain per column is one load pass, a log2(LPC)-step reduction, one update pass.  Dots and
+        // norms are accumulated in the working precision: every step recomputes the norms from scratch (no
+        // downdating), which is already tighter than ?geqp3, and the f32 -> f64 conversions made this loop
+        // issue-bound for single precision (22 000 of 36 000 cycles per step at config 3).
         const T ctau = rc_conj(tau);
-        using A = typename AccOf<T>::type;
-        for (int l0 = warp; l0 < nl; l0 += NW * CU) {
-            T* col[CU];
-            bool act[CU];
-            bool any = false;
+        {
+            constexpr int CPW = 32 / LPC;
+            const int sl = lane % LPC, sc = lane / LPC;
+            using R = RealOf<T>;
+            const int nres = min(nl, cap);           // resident columns: this loop; the others: the loop below
+            for (int q0 = 0; warp + q0 * NW < nres; q0 += CU * CPW) {
+                T* col[CU];
+                bool act[CU];
+                int lis[CU];
 #pragma unroll
-            for (int j = 0; j < CU; ++j) {
-                const int li = l0 + j * NW;
-                act[j] = (li < nl) && (lpos[min(li, nl - 1)] > i);      // warp-uniform
-                col[j] = colp(min(li, nl - 1));
-                any |= act[j];
+                for (int j = 0; j < CU; ++j) {
+                    const int li = warp + (q0 + j * CPW + sc) * NW;
+                    lis[j] = li;
+                    act[j] = (li < nres) && (lpos[min(li, nl - 1)] > i);
+                    col[j] = scol + (size_t)min(li, nres - 1) * p;
+                }
+                T part[CU];
+#pragma unroll
+                for (int j = 0; j < CU; ++j) part[j] = rc_zero<T>();
+                for (int r = i + 1 + sl; r < p; r += LPC) {
+                    const T xv = xs[r];
+#pragma unroll
+                    for (int j = 0; j < CU; ++j)
+                        if (act[j]) part[j] = rc_cfma(xv, col[j][r], part[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < CU; ++j) {
+#pragma unroll
+                    for (int m = LPC / 2; m > 0; m >>= 1) part[j] = part[j] + rc_shfl_xor(part[j], m);
+                }
+                T ci[CU], f[CU];
+                R nrm[CU];
+#pragma unroll
+                for (int j = 0; j < CU; ++j) {
+                    ci[j] = act[j] ? col[j][i] : rc_zero<T>();
+                    f[j] = ctau * (ci[j] + part[j]);
+                    nrm[j] = R(0);
+                }
+                for (int r = i + 1 + sl; r < p; r += LPC) {
+                    const T xv = xs[r];
+#pragma unroll
+                    for (int j = 0; j < CU; ++j)
+                        if (act[j]) {
+                            T v = col[j][r] - f[j] * xv;
+                            col[j][r] = v;
+                            nrm[j] += rc_real(v) * rc_real(v) + rc_imag(v) * rc_imag(v);
+                        }
+                }
+#pragma unroll
+                for (int j = 0; j < CU; ++j) {
+#pragma unroll
+                    for (int m = LPC / 2; m > 0; m >>= 1) nrm[j] += __shfl_xor_sync(0xffffffffu, nrm[j], m);
+                }
+                if (sl == 0) {
+#pragma unroll
+                    for (int j = 0; j < CU; ++j)
+                        if (act[j]) { col[j][i] = ci[j] - f[j]; vn[lis[j]] = sqrt((double)nrm[j]); }
+                }
             }
-            if (!any) continue;
-            A part[CU];
+            // Columns that did not fit into shared memory live in global memory (L2).  One column per warp at
+            // a time with all its rows PREFETCHED INTO REGISTERS (RG per lane, loads issued back to back): the
+            // column costs one L2 round trip instead of one per row iteration -- mixed into the loop above they
+            // stretched the update phase from ~5 000 to 21 000 cycles per step at config 3.
+            constexpr int RG = sizeof(T) == 4 ? 10 : (sizeof(T) == 8 ? 8 : 4);
+            for (int li = cap + ((warp - cap % NW + NW) % NW); li < nl; li += NW) {
+                if (lpos[li] <= i) continue;                       // warp-uniform
+                T* col = W + (int64_t)(li * G + b) * ldw;
+                const int nrows = p - (i + 1);
+                T part = rc_zero<T>();
+                R nrm = R(0);
+                if (nrows <= 32 * RG) {
+                    T v[RG];
 #pragma unroll
-            for (int j = 0; j < CU; ++j) part[j] = rc_zero<A>();
-            for (int r = i + 1 + lane; r < p; r += 32) {
-                const A xv = rc_widen(xs[r]);
+                    for (int u = 0; u < RG; ++u) { const int r = i + 1 + lane + 32 * u; v[u] = (r < p) ? col[r] : rc_zero<T>(); }
+                    const T ci = col[i];
 #pragma unroll
-                for (int j = 0; j < CU; ++j)
-                    if (act[j]) part[j] = rc_cfma(xv, rc_widen(col[j][r]), part[j]);
-            }
+                    for (int u = 0; u < RG; ++u) { const int r = i + 1 + lane + 32 * u; if (r < p) part = rc_cfma(xs[r], v[u], part); }
+                    part = rc_warp_sum(part);
+                    const T f = ctau * (ci + part);
 #pragma unroll
-            for (int j = 0; j < CU; ++j) part[j] = rc_warp_sum(part[j]);
-            T ci[CU], f[CU];
-            double nrm[CU];
-#pragma unroll
-            for (int j = 0; j < CU; ++j) {
-                ci[j] = act[j] ? col[j][i] : rc_zero<T>();
-                f[j] = ctau * rc_narrow<T>(rc_widen(ci[j]) + part[j]);
-                nrm[j] = 0.0;
-            }
-            for (int r = i + 1 + lane; r < p; r += 32) {
-                const T xv = xs[r];
-#pragma unroll
-                for (int j = 0; j < CU; ++j)
-                    if (act[j]) {
-                        T v = col[j][r] - f[j] * xv;
-                        col[j][r] = v;
-                        nrm[j] += rc_abs2(v);
+                    for (int u = 0; u < RG; ++u) {
+                        const int r = i + 1 + lane + 32 * u;
+                        if (r < p) {
+                            const T nv = v[u] - f * xs[r];
+                            col[r] = nv;
+                            nrm += rc_real(nv) * rc_real(nv) + rc_imag(nv) * rc_imag(nv);
+                        }
                     }
-            }
-#pragma unroll
-            for (int j = 0; j < CU; ++j) nrm[j] = rc_warp_sum(nrm[j]);
-            if (lane == 0) {
-#pragma unroll
-                for (int j = 0; j < CU; ++j)
-                    if (act[j]) { col[j][i] = ci[j] - f[j]; vn[l0 + j * NW] = sqrt(nrm[j]); }
+                    nrm = rc_warp_sum(nrm);
+                    if (lane == 0) { col[i] = ci - f; vn[li] = sqrt((double)nrm); }
+                } else {
+                    for (int r = i + 1 + lane; r < p; r += 32) part = rc_cfma(xs[r], col[r], part);
+                    part = rc_warp_sum(part);
+                    const T ci = col[i];
+                    const T f = ctau * (ci + part);
+                    for (int r = i + 1 + lane; r < p; r += 32) {
+                        const T nv = col[r] - f * xs[r];
+                        col[r] = nv;
+                        nrm += rc_real(nv) * rc_real(nv) + rc_imag(nv) * rc_imag(nv);
+                    }
+                    nrm = rc_warp_sum(nrm);
+                    if (lane == 0) { col[i] = ci - f; vn[li] = sqrt((double)nrm); }
+                }
             }
         }
         __syncthreads();   // xs is rewritten next step; lpos/vn written by lane 0 are read by the block
+        RC_PHASE(4);      // trailing update
     }
+#undef RC_PHASE
     // final logical order for the never-pivoted columns (n > p)
     for (int li = tid; li < nl; li += NT) {
         int lp = lpos[li];
@@ -415,15 +499,13 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
     int kk = (int)std::min(p, n);
     RC_REQUIRE(p > 0 && n > 0, "pivoted_qr: empty matrix");
     size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
-    DevBuf<double> vn(c, (size_t)n);
-    DevBuf<int> lpos(c, (size_t)n);
     DevBuf<T> diag(c, (size_t)kk);
     int pi = (int)p, ni = (int)n;
     size_t smem_all = ((size_t)p + (size_t)p * n + 1) * sizeof(T) + (size_t)n * (sizeof(double) + sizeof(int)) + 16;
     if (smem_all + 8192 <= lim && n <= 2048) {
         // small factor: one CTA, matrix resident in shared memory
         constexpr int NTS = 1024;
-        if (p <= 128) {
+        if (p <= 256) {
             RC_CUDA(cudaFuncSetAttribute(pivqr_small_kernel<T, NTS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
             pivqr_small_kernel<T, NTS, 8><<<1, NTS, smem_all, c->stream>>>(wc, ldw, pi, ni, kk, ind, vbuf, tau, diag.p);
         } else {
@@ -432,8 +514,9 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
         }
         RC_CHECK_LAUNCH(c);
     } else {
-        constexpr int NT = 1024, CU = std::is_same<T, c64>::value ? 2 : 4;   // c64 x 4 columns spills at 64 registers
+        constexpr int NT = 1024;
         constexpr int NW = NT / 32;
+        constexpr int CUMAX = std::is_same<T, c64>::value ? 2 : 4;     // c64 x 4 columns per lane group spills at 64 registers
         RC_REQUIRE((size_t)p * sizeof(T) + 16384 <= lim, "pivoted_qr: %lld rows exceed the shared-memory column buffer", (long long)p);
         int64_t want = (n + NW * 2 - 1) / (NW * 2);       // at least ~2 columns per warp
         int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, c->sm_count));
@@ -443,15 +526,30 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
         int cap = (int)std::min<int64_t>(nlmax, (int64_t)((lim - 6144 - fixed) / ((size_t)p * sizeof(T))));
         if (cap < 0) cap = 0;
         size_t smem = fixed + (size_t)cap * p * sizeof(T);
-        RC_CUDA(cudaFuncSetAttribute(pivqr_kernel<T, NT, CU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pivqr_kernel<T, NT, CU>, NT, smem));
-        RC_REQUIRE(per_sm >= 1, "pivoted_qr: kernel does not fit on an SM");
+        // lanes per column: ~10-20 rows per lane; columns in flight per warp: enough for one pass over its columns
+        const int lpc = p <= 160 ? 8 : (p <= 320 ? 16 : 32);
+        const int per_warp = (nlmax + NW - 1) / NW;
+        const bool wide_cu = per_warp > 32 / lpc;
+        void* kernel = nullptr;
+#define RC_PICK(L) kernel = wide_cu ? (void*)pivqr_kernel<T, NT, L, CUMAX> : (void*)pivqr_kernel<T, NT, L, 1>
+        if (lpc == 8) { RC_PICK(8); } else if (lpc == 16) { RC_PICK(16); } else { RC_PICK(32); }
+#undef RC_PICK
+        RC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DevBuf<Cand> slots(c, (size_t)2 * grid);
         DevBuf<int> slots_disp(c, (size_t)2 * grid);
         DevBuf<T> stage(c, (size_t)2 * grid * p);
-        void* args[] = {&wc, &ldw, &pi, &ni, &kk, &cap, &nlmax, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p, &stage.p};
-        RC_CUDA(cudaLaunchCooperativeKernel((void*)pivqr_kernel<T, NT, CU>, dim3(grid), dim3(NT), args, smem, c->stream));
+        DevBuf<long long> prof;
+        long long* prof_p = nullptr;
+        if (c->trace) { prof.alloc(c, 8); RC_CUDA(cudaMemsetAsync(prof.p, 0, 64, c->stream)); prof_p = prof.p; }
+        void* args[] = {&wc, &ldw, &pi, &ni, &kk, &cap, &nlmax, &ind, &vbuf, &tau, &diag.p, &slots.p, &slots_disp.p, &stage.p, &prof_p};
+        RC_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(NT), args, smem, c->stream));
+        if (c->trace) {
+            long long h[8];
+            RC_CUDA(cudaMemcpyAsync(h, prof.p, 64, cudaMemcpyDeviceToHost, c->stream));
+            RC_CUDA(cudaStreamSynchronize(c->stream));
+            fprintf(stderr, "[rc trace]     pivqr %d x %d, %d CTAs, %d resident cols/CTA: cycles per step: candidates+publish %lld, grid sync %lld, "
+                            "winner %lld, reflector %lld, update %lld\n", pi, ni, grid, cap, h[0] / kk, h[1] / kk, h[2] / kk, h[3] / kk, h[4] / kk);
+        }
         RC_COUNT_LAUNCH(c);
     }
     int64_t total = (int64_t)kk * n;
