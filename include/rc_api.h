@@ -167,6 +167,11 @@ rc_status rc_decaying_spectrum_matrix(rc_ctx* ctx, rc_dtype dtype, int64_t rows,
 rc_status rc_tall_shard_matrix(rc_ctx* ctx, rc_dtype dtype, int64_t rows, int64_t cols, int64_t r0,
                                double decade_every, uint64_t seed, int64_t row_offset,
                                int64_t m_total, rc_matrix** out);
+/* Bench/test input of BASELINE config 5: A_ij = exp(i kappa |x_i - y_j|) / |x_i - y_j| for x_i
+ * uniform in [0,1]^3 and y_j uniform in [0,1]^3 + (shift, 0, 0) (Philox-seeded, so row shards regenerate their
+ * own rows via `row_offset`); real scalar types take the real part.  Generated on device. */
+rc_status rc_helmholtz_kernel_matrix(rc_ctx* ctx, rc_dtype dtype, int64_t rows, int64_t cols, uint64_t seed,
+                                     double kappa, double shift, int64_t row_offset, rc_matrix** out);
 
 /* RelDiff::{rel_diff_fro, rel_diff_l2} (src/types.rs:162-204): ||first - second|| / ||second||. */
 rc_status rc_rel_diff_fro(rc_ctx* ctx, const rc_matrix* first, const rc_matrix* second, double* out);

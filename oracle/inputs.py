@@ -47,6 +47,22 @@ def helmholtz_kernel_matrix(m, n, dtype, seed=7, kappa=20.0, shift=1.5):
     return np.ascontiguousarray(a.astype(dtype))
 
 
+def helmholtz_kernel_matrix_philox(m, n, dtype, seed=7, kappa=20.0, shift=1.5, row_offset=0):
+    """Host mirror of the library's device generator rc_helmholtz_kernel_matrix: same kernel as
+    ``helmholtz_kernel_matrix`` but the points come from the Philox stream (coordinate d of point i = the
+    [0, 1) uniform of counter 3 i + d; stream 301 for x, 302 for y), so row shards regenerate their rows."""
+    from .philox import _uniform_pair
+    dtype = np.dtype(dtype)
+    ex = np.arange(3 * row_offset, 3 * (row_offset + m), dtype=np.uint64)
+    ey = np.arange(0, 3 * n, dtype=np.uint64)
+    x = _uniform_pair(ex, seed, 301)[1].reshape(m, 3)
+    y = _uniform_pair(ey, seed, 302)[1].reshape(n, 3)
+    y[:, 0] += shift
+    d = np.sqrt(((x[:, None, :] - y[None, :, :]) ** 2).sum(axis=2))
+    k = np.exp(1j * kappa * d) / d
+    return np.ascontiguousarray((k if dtype.kind == "c" else k.real).astype(dtype))
+
+
 def tall_shard_matrix(row0, rows, n, dtype, seed, m_total, r0=512, decade_every=64.0):
     """Config 4: rows [row0, row0+rows) of A = m^(-1/2) G diag(sigma) V^T with
     G_ij ~ N(0,1) from Philox keyed by (global row, j) and V (n x r0) a shared

@@ -58,6 +58,7 @@ extern "C" {
     pub fn rc_decaying_spectrum_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, r0: i64, decade_every: f64, seed: u64, row_offset: i64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_matrix_copy(ctx: *mut rc_ctx, src: *const rc_matrix, dst: *mut rc_matrix) -> c_int;
     pub fn rc_operator_create(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, matmat: rc_matmat_fn, conj_matmat: rc_matmat_fn, user: *mut c_void, out: *mut *mut rc_matrix) -> c_int;
+    pub fn rc_helmholtz_kernel_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, seed: u64, kappa: f64, shift: f64, row_offset: i64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_tall_shard_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, r0: i64, decade_every: f64, seed: u64, row_offset: i64, m_total: i64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_rel_diff_fro(ctx: *mut rc_ctx, first: *const rc_matrix, second: *const rc_matrix, out: *mut f64) -> c_int;
     pub fn rc_rel_diff_l2(ctx: *mut rc_ctx, first: *const rc_matrix, second: *const rc_matrix, out: *mut f64) -> c_int;

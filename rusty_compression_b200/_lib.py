@@ -55,6 +55,7 @@ SIGNATURES = {
     "rc_random_orthogonal_matrix": (c_int, [H, c_int, c_int64, c_int64, c_uint64, c_uint32, PH]),
     "rc_random_approximate_low_rank_matrix": (c_int, [H, c_int, c_int64, c_int64, c_double, c_double, c_uint64, PH]),
     "rc_decaying_spectrum_matrix": (c_int, [H, c_int, c_int64, c_int64, c_int64, c_double, c_uint64, c_int64, PH]),
+    "rc_helmholtz_kernel_matrix": (c_int, [H, c_int, c_int64, c_int64, c_uint64, c_double, c_double, c_int64, PH]),
     "rc_tall_shard_matrix": (c_int, [H, c_int, c_int64, c_int64, c_int64, c_double, c_uint64, c_int64, c_int64, PH]),
     "rc_rel_diff_fro": (c_int, [H, H, H, PD]),
     "rc_rel_diff_l2": (c_int, [H, H, H, PD]),

@@ -701,6 +701,15 @@ def decaying_spectrum_matrix(shape, dtype, seed, r0=512, decade_every=16.0, row_
     return DeviceMatrix(ctx, h)
 
 
+def helmholtz_kernel_matrix(shape, dtype, seed=7, kappa=20.0, shift=1.5, row_offset=0, ctx=None):
+    """Device-generated config-5 input; the host mirror is oracle.inputs.helmholtz_kernel_matrix_philox."""
+    ctx = ctx or default_context()
+    h = c_void_p()
+    ctx.check(ctx.lib.rc_helmholtz_kernel_matrix(ctx.h, DTYPE_CODE[np.dtype(dtype)], shape[0], shape[1], seed, kappa, shift,
+                                                 row_offset, ctypes.byref(h)))
+    return DeviceMatrix(ctx, h)
+
+
 def tall_shard_matrix(row_offset, rows, cols, dtype, seed, m_total, r0=512, decade_every=64.0, ctx=None):
     """Device-generated rows [row_offset, row_offset + rows) of the config-4 input."""
     ctx = ctx or default_context()

@@ -1092,6 +1092,21 @@ rc_status rc_tall_shard_matrix(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t col
     });
 }
 
+// BASELINE config 5 input: the "low-rank kernel matrix" exp(i kappa |x_i - y_j|) / |x_i - y_j| of
+// two well-separated unit boxes, generated on device (real dtypes take the real part).
+rc_status rc_helmholtz_kernel_matrix(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t cols, uint64_t seed, double kappa,
+                                     double shift, int64_t row_offset, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(rows > 0 && cols > 0 && shift > 1.0, "bad arguments (the boxes must not touch: shift > 1)");
+        RC_DISPATCH(dt, {
+            MatPtr a(mat_new(c, dt, rows, cols));
+            k_helmholtz<T>(c, P<T>(a.get()), rows, cols, a->ld, seed, kappa, shift, row_offset);
+            *out = a.release();
+        });
+    });
+}
+
 rc_status rc_rel_diff_fro(rc_ctx* c, const rc_matrix* a, const rc_matrix* b, double* out) {
     if (!c || !a || !b || !out) return RC_INVALID_ARGUMENT;
     return guard(c, [&] { check_same(a, b); RC_DISPATCH(a->dtype, *out = rel_diff_impl<T>(c, a, b)); });

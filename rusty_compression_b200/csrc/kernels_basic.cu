@@ -145,6 +145,34 @@ __global__ void gaussian_kernel(T* p, int64_t rows, int64_t cols, int64_t ld, ui
     }
 }
 
+// BASELINE config 5 input: A_ij = exp(i kappa |x_i - y_j|) / |x_i - y_j| for points in two unit
+// boxes a distance `shift` apart.  Point coordinate d of point i = the [0,1) uniform of Philox counter 3 i + d
+// (stream 301 for x, 302 for y), so any row shard regenerates its own points (oracle/inputs.py mirrors it).
+__global__ void helmholtz_points_kernel(double* pts, int64_t npts, int64_t first, uint64_t seed, uint32_t stream, double shift) {
+    int64_t n = npts * 3;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = e / 3; int d = (int)(e - i * 3);
+        uint32_t w[4];
+        uint64_t ctr = (uint64_t)((first + i) * 3 + d);
+        rc_philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), stream, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+        double u = ((double)(w[2] >> 5) * 67108864.0 + (double)(w[3] >> 6)) * 1.1102230246251565404e-16;   // [0, 1)
+        pts[e] = u + (d == 0 ? shift : 0.0);
+    }
+}
+template <class T>
+__global__ void helmholtz_fill_kernel(T* a, int64_t rows, int64_t cols, int64_t ld, const double* __restrict__ x,
+                                      const double* __restrict__ y, double kappa) {
+    int64_t n = rows * cols;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = e / cols, j = e - i * cols;
+        double dx = x[3 * i] - y[3 * j], dy = x[3 * i + 1] - y[3 * j + 1], dz = x[3 * i + 2] - y[3 * j + 2];
+        double d = sqrt(dx * dx + dy * dy + dz * dz);
+        double sn, cs;
+        sincos(kappa * d, &sn, &cs);
+        a[i * ld + j] = GaussStore<T>::make(cs / d, sn / d);
+    }
+}
+
 // Column norms^2: grid.x over 32-column strips, grid.y over row chunks; each warp-row of the
 // block walks rows, lanes map to consecutive columns (coalesced); partials via atomicAdd(double).
 template <class T>
@@ -283,6 +311,16 @@ template <class T> void k_gaussian(rc_ctx* c, T* p, int64_t rows, int64_t cols, 
     gaussian_kernel<T><<<nblocks_for(rows * cols), TB, 0, c->stream>>>(p, rows, cols, ld, seed, stream, row_offset);
     RC_CHECK_LAUNCH(c);
 }
+template <class T> void k_helmholtz(rc_ctx* c, T* a, int64_t rows, int64_t cols, int64_t ld, uint64_t seed, double kappa, double shift, int64_t row_offset) {
+    if (rows * cols == 0) return;
+    DevBuf<double> x(c, (size_t)rows * 3), y(c, (size_t)cols * 3);
+    helmholtz_points_kernel<<<nblocks_for(rows * 3), TB, 0, c->stream>>>(x.p, rows, row_offset, seed, 301u, 0.0);
+    RC_CHECK_LAUNCH(c);
+    helmholtz_points_kernel<<<nblocks_for(cols * 3), TB, 0, c->stream>>>(y.p, cols, 0, seed, 302u, shift);
+    RC_CHECK_LAUNCH(c);
+    helmholtz_fill_kernel<T><<<nblocks_for(rows * cols), TB, 0, c->stream>>>(a, rows, cols, ld, x.p, y.p, kappa);
+    RC_CHECK_LAUNCH(c);
+}
 template <class T> void k_col_norms2(rc_ctx* c, const T* a, int64_t lda, int64_t rows, int64_t cols, double* out) {
     RC_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * cols, c->stream));
     if (rows * cols == 0) return;
@@ -328,6 +366,7 @@ template <class T> void k_convert_real(rc_ctx* c, RealOf<T>* dst, const double* 
     template void k_sub<T>(rc_ctx*, T*, int64_t, const T*, int64_t, const T*, int64_t, int64_t, int64_t); \
     template void k_add<T>(rc_ctx*, T*, int64_t, const T*, int64_t, const T*, int64_t, int64_t, int64_t); \
     template void k_gaussian<T>(rc_ctx*, T*, int64_t, int64_t, int64_t, uint64_t, uint32_t, int64_t);     \
+    template void k_helmholtz<T>(rc_ctx*, T*, int64_t, int64_t, int64_t, uint64_t, double, double, int64_t); \
     template void k_col_norms2<T>(rc_ctx*, const T*, int64_t, int64_t, int64_t, double*);                 \
     template void k_fro2<T>(rc_ctx*, const T*, int64_t, int64_t, int64_t, double*);                       \
     template void k_diff_fro2<T>(rc_ctx*, const T*, int64_t, const T*, int64_t, int64_t, int64_t, double*); \

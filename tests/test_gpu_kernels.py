@@ -226,3 +226,16 @@ def test_svd_matches_gesdd(api, dtype, shape):
     assert relerr((u * s).dot(vt), a) < (2e-5 if single else 1e-12)
     assert np.max(np.abs(np.conj(u.T).dot(u) - np.eye(k))) < (2e-4 if single else 1e-10)
     assert np.max(np.abs(vt.dot(np.conj(vt.T)) - np.eye(k))) < (2e-4 if single else 1e-10)
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float32])
+def test_device_helmholtz_generator_matches_host_mirror(api, dtype):
+    """rc_helmholtz_kernel_matrix (config-5 input, generated on device) against oracle.inputs' Philox mirror,
+    including a row shard."""
+    from oracle.inputs import helmholtz_kernel_matrix_philox
+    want = helmholtz_kernel_matrix_philox(300, 200, dtype, seed=7)
+    got = api.helmholtz_kernel_matrix((300, 200), dtype, seed=7).to_numpy()
+    tol = 1e-12 if np.dtype(dtype).itemsize >= 16 else 1e-5
+    assert relerr(got, want) < tol
+    shard = api.helmholtz_kernel_matrix((100, 200), dtype, seed=7, row_offset=150).to_numpy()
+    assert relerr(shard, want[150:250]) < tol

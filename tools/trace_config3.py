@@ -9,9 +9,8 @@ if which == "3":
     a = api.decaying_spectrum_matrix((n, n), np.float32, 1235, r0=1024, decade_every=64.0)
     run = lambda: api.QR.compute_from_range_estimate(api.sample_range_adaptive(a, 1e-4, 64, seed=42, device=True)[0], a).compress(api.ADAPTIVE(1e-4)).column_id()
 else:
-    from oracle.inputs import helmholtz_kernel_matrix
     n = 16384
-    a = api.DeviceMatrix.from_numpy(helmholtz_kernel_matrix(n, n, np.complex128))
+    a = api.helmholtz_kernel_matrix((n, n), np.complex128)
     run = lambda: api.QR.compute_from_range_estimate(api.sample_range_by_rank(a, 128, 10, seed=42, device=True), a).compress(api.RANK(128)).column_id().two_sided_id()
 for _ in range(2):
     run()
