@@ -1473,12 +1473,32 @@ rc_status rc_column_id_two_sided_id(rc_ctx* c, const rc_column_id* id, rc_two_si
         // LQ::compute_from(C).row_id() (src/col_interp_decomp.rs:116-125; quirk Q10: uncompressed)
         std::unique_ptr<rc_two_sided_id> h(new rc_two_sided_id());
         RC_DISPATCH(id->c->dtype, {
+            // Row-sharded C: the m columns of C^H are spread over the ranks.  C is small
+            // (m x k), so it is all-gathered and the pivoted LQ / row ID run redundantly on every rank --
+            // identical pivots to the single-GPU run by construction (a tournament pivoting would not be);
+            // every rank keeps its own rows of the m x k factor X.
+            const rc_matrix* cm = id->c;
+            MatPtr cfull;
+            const bool sharded = mat_sharded(id->c);
+            if (sharded) {
+                RC_REQUIRE(id->c->rows * c->nranks == id->c->global_rows, "two_sided_id: row shards must have equal sizes");
+                cfull.reset(mat_new(c, id->c->dtype, id->c->global_rows, id->c->cols));
+                RC_REQUIRE(cfull->ld == id->c->ld, "two_sided_id: unexpected leading dimension");
+                comm_allgather(c, id->c->data, cfull->data, (size_t)id->c->rows * id->c->ld * sizeof(T));
+                cm = cfull.get();
+            }
             QrParts p;
-            pivoted_qr_impl<T>(c, id->c, true, -1, false, p);
+            pivoted_qr_impl<T>(c, cm, true, -1, false, p);
             MatPtr l(mat_conj_transpose<T>(c, p.r.get()));
             MatPtr q(mat_conj_transpose<T>(c, p.q.get()));
             rc_row_id rid;
             row_id_impl<T>(c, l.get(), q.get(), p.ind, &rid);
+            if (sharded) {
+                MatPtr xl(mat_slice<T>(c, rid.x, id->c->row_offset, id->c->row_offset + id->c->rows, 0, rid.x->cols));
+                inherit_shard(xl.get(), id->c);
+                mat_free(rid.x);
+                rid.x = xl.release();
+            }
             h->c = rid.x; h->x = rid.r; h->row_ind = rid.row_ind;
             MatPtr zc(mat_clone<T>(c, id->z));
             h->r = zc.release();

@@ -51,6 +51,9 @@ def main():
         cid = qr.column_id()
         c_full = gather_rows(cid.c)
         z, col_ind = cid.z, cid.col_ind
+        ts = cid.two_sided_id()                      # C is row-sharded: all-gathered, pivoted LQ replicated
+        tsc_full = gather_rows(ts.c)
+        ts_x, ts_r, ts_row_ind = ts.x, ts.r, ts.row_ind
         # --- adaptive sampler with the Philox stream
         qa, hist = api.sample_range_adaptive(op, 1e-4, 16, seed=7, ctx=ctx, device=True)
         qa_full = gather_rows(qa.to_numpy())
@@ -66,6 +69,13 @@ def main():
             e, e_ref = ref.rel_diff_fro(c_full.dot(z), a), ref.rel_diff_fro(cid_ref.to_mat(), a)
             if np.array_equal(col_ind[:k], cid_ref.col_ind[:k]):
                 assert abs(e - e_ref) <= tol * e_ref, (dtype, e, e_ref)
+                ts_ref = cid_ref.two_sided_id()
+                assert tsc_full.shape == (m, k) and len(ts_row_ind) == m
+                e2, e2_ref = ref.rel_diff_fro(tsc_full.dot(ts_x.dot(ts_r)), a), ref.rel_diff_fro(ts_ref.to_mat(), a)
+                if np.array_equal(ts_row_ind[:k], ts_ref.row_ind[:k]):
+                    assert abs(e2 - e2_ref) <= 10 * tol * e2_ref, (dtype, e2, e2_ref)
+                else:
+                    assert tol > 1e-6, "f64 row skeleton must match the unsharded LAPACK path"
             else:
                 assert tol > 1e-6, "f64 skeleton indices must match the unsharded LAPACK path"
             qa_ref, hist_ref = ref.sample_range_adaptive(a, 1e-4, 16, ref.OmegaStream(dtype, seed=7))
