@@ -297,6 +297,12 @@ rc_status rc_two_sided_id_to_mat(rc_ctx* ctx, const rc_two_sided_id* id, rc_matr
 rc_status rc_two_sided_id_apply(rc_ctx* ctx, const rc_two_sided_id* id, const rc_matrix* rhs,
                                 rc_matrix** out);
 rc_status rc_two_sided_id_free(rc_two_sided_id* id);
+/* Lengths of the index vectors (always the full n or m, quirk Q8: src/qr.rs:182, 306).  With row-sharded
+ * factors the local row count of c / x is not the length of row_ind. */
+size_t rc_column_id_col_ind_len(const rc_column_id* id);
+size_t rc_row_id_row_ind_len(const rc_row_id* id);
+size_t rc_two_sided_id_row_ind_len(const rc_two_sided_id* id);
+size_t rc_two_sided_id_col_ind_len(const rc_two_sided_id* id);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,10 @@ extern "C" {
     pub fn rc_random_orthogonal_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, seed: u64, stream: u32, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_random_approximate_low_rank_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, sigma_max: f64, sigma_min: f64, seed: u64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_decaying_spectrum_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, r0: i64, decade_every: f64, seed: u64, row_offset: i64, out: *mut *mut rc_matrix) -> c_int;
+    pub fn rc_column_id_col_ind_len(id: *const rc_column_id) -> usize;
+    pub fn rc_row_id_row_ind_len(id: *const rc_row_id) -> usize;
+    pub fn rc_two_sided_id_row_ind_len(id: *const rc_two_sided_id) -> usize;
+    pub fn rc_two_sided_id_col_ind_len(id: *const rc_two_sided_id) -> usize;
     pub fn rc_matrix_copy(ctx: *mut rc_ctx, src: *const rc_matrix, dst: *mut rc_matrix) -> c_int;
     pub fn rc_operator_create(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, matmat: rc_matmat_fn, conj_matmat: rc_matmat_fn, user: *mut c_void, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_helmholtz_kernel_matrix(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, seed: u64, kappa: f64, shift: f64, row_offset: i64, out: *mut *mut rc_matrix) -> c_int;

@@ -38,6 +38,10 @@ SIGNATURES = {
     "rc_matrix_create": (c_int, [H, c_int, c_int64, c_int64, PH]),
     "rc_matrix_from_host": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, PH]),
     "rc_matrix_wrap_device": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, PH]),
+    "rc_column_id_col_ind_len": (c_size_t, [H]),
+    "rc_row_id_row_ind_len": (c_size_t, [H]),
+    "rc_two_sided_id_row_ind_len": (c_size_t, [H]),
+    "rc_two_sided_id_col_ind_len": (c_size_t, [H]),
     "rc_matrix_copy": (c_int, [H, H, H]),
     "rc_operator_create": (c_int, [H, c_int, c_int64, c_int64, MATMAT_FN, MATMAT_FN, c_void_p, PH]),
     "rc_matrix_to_host": (c_int, [H, H, c_void_p]),

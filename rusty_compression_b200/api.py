@@ -344,11 +344,11 @@ class TwoSidedID(_Handle):
 
     @property
     def row_ind(self):
-        return _get_ind(self.ctx, self.ctx.lib.rc_two_sided_id_get_row_ind, self.h, self.c.shape[0])
+        return _get_ind(self.ctx, self.ctx.lib.rc_two_sided_id_get_row_ind, self.h, self.ctx.lib.rc_two_sided_id_row_ind_len(self.h))
 
     @property
     def col_ind(self):
-        return _get_ind(self.ctx, self.ctx.lib.rc_two_sided_id_get_col_ind, self.h, self.r.shape[1])
+        return _get_ind(self.ctx, self.ctx.lib.rc_two_sided_id_get_col_ind, self.h, self.ctx.lib.rc_two_sided_id_col_ind_len(self.h))
 
     def nrows(self):
         return self.c.shape[0]
@@ -379,7 +379,7 @@ class ColumnID(_Handle):
 
     @property
     def col_ind(self):
-        return _get_ind(self.ctx, self.ctx.lib.rc_column_id_get_col_ind, self.h, self.z.shape[1])
+        return _get_ind(self.ctx, self.ctx.lib.rc_column_id_get_col_ind, self.h, self.ctx.lib.rc_column_id_col_ind_len(self.h))
 
     def nrows(self):
         return self.c.shape[0]
@@ -413,7 +413,7 @@ class RowID(_Handle):
 
     @property
     def row_ind(self):
-        return _get_ind(self.ctx, self.ctx.lib.rc_row_id_get_row_ind, self.h, self.x.shape[0])
+        return _get_ind(self.ctx, self.ctx.lib.rc_row_id_get_row_ind, self.h, self.ctx.lib.rc_row_id_row_ind_len(self.h))
 
     def nrows(self):
         return self.x.shape[0]

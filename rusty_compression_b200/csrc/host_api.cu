@@ -1507,6 +1507,12 @@ rc_status rc_column_id_two_sided_id(rc_ctx* c, const rc_column_id* id, rc_two_si
         *out = h.release();
     });
 }
+/* lengths of the (always full-length, quirk Q8) index vectors: with row-sharded factors the local row count of
+ * c / x is not the length of row_ind */
+size_t rc_column_id_col_ind_len(const rc_column_id* id) { return id ? id->col_ind.size() : 0; }
+size_t rc_row_id_row_ind_len(const rc_row_id* id) { return id ? id->row_ind.size() : 0; }
+size_t rc_two_sided_id_row_ind_len(const rc_two_sided_id* id) { return id ? id->row_ind.size() : 0; }
+size_t rc_two_sided_id_col_ind_len(const rc_two_sided_id* id) { return id ? id->col_ind.size() : 0; }
 rc_status rc_column_id_free(rc_column_id* id) {
     if (id) { mat_free(id->c); mat_free(id->z); delete id; }
     return RC_OK;
