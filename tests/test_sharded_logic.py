@@ -100,3 +100,52 @@ def test_row_sharded_rsvd_matches_unsharded_oracle(tmp_path):
     # pivots of the final sketch agree with the unsharded LAPACK path
     y = a.dot(ref.pivoted_qr(np.conj(a.T).dot(ref.pivoted_qr(a.dot(omega))[0]))[0])
     assert np.array_equal(got["ind"], ref.pivoted_qr(y)[2])
+
+
+# ---- row-sharded column ID + two-sided ID (csrc/host_api.cu: rc_column_id_two_sided_id, sharded branch)
+def sharded_two_sided_id(a_local, omega, k):
+    """by-rank sampling (sharded pivoted QR of the sketch) -> b = Q^H A by all-reduce, pivoted QR of b replicated
+    -> C = Q (q_b R11) local rows, Z replicated -> C all-gathered, pivoted LQ + row ID replicated, every rank
+    keeps its own rows of X."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    q, _, _ = sharded_pivoted_qr(a_local.dot(omega), k)
+    b = np.conj(_allreduce(np.conj(a_local.T).dot(q)).T)               # k x n, replicated
+    qb, rb, ind = ref.pivoted_qr(b)
+    qr = ref.QR(q.dot(qb), rb, ind).compress(ref.RANK(k))              # q holds the local rows
+    cid = qr.column_id()                                               # C local rows, Z replicated
+    c_full = np.concatenate(_allgather(cid.c), axis=0)                 # all-gather of C (m x k)
+    rid = ref.LQ.compute_from(c_full).row_id()                         # replicated on every rank
+    rows = a_local.shape[0]
+    x_local = rid.x[rank * rows:(rank + 1) * rows]
+    return x_local, rid.r, cid.z, rid.row_ind, cid.col_ind
+
+
+def _worker_id(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, _ = decaying_spectrum_matrix(M, N, np.float64, seed=6, r0=64, decade_every=8.0)
+    omega = random_gaussian((N, K + P), np.float64, seed=43)
+    rows = M // world
+    x_local, xr, z, row_ind, col_ind = sharded_two_sided_id(a[rank * rows:(rank + 1) * rows], omega, K)
+    xs = _allgather(x_local)
+    if rank == 0:
+        np.savez(out, c=np.concatenate(xs, axis=0), x=xr, r=z, row_ind=row_ind, col_ind=col_ind)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_row_sharded_two_sided_id_matches_unsharded_oracle(tmp_path):
+    out = str(tmp_path / "sharded_id.npz")
+    mp.spawn(_worker_id, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    a, _ = decaying_spectrum_matrix(M, N, np.float64, seed=6, r0=64, decade_every=8.0)
+    omega = random_gaussian((N, K + P), np.float64, seed=43)
+    q_ref = ref.sample_range_by_rank(a, K, P, ref.OmegaStream(np.float64, blocks=[omega]))
+    ts_ref = ref.QR.compute_from_range_estimate(q_ref, a).compress(ref.RANK(K)).column_id().two_sided_id()
+    assert np.array_equal(got["col_ind"][:K], ts_ref.col_ind[:K])
+    assert np.array_equal(got["row_ind"][:K], ts_ref.row_ind[:K])
+    e = ref.rel_diff_fro(got["c"].dot(got["x"].dot(got["r"])), a)
+    e_ref = ref.rel_diff_fro(ts_ref.to_mat(), a)
+    assert abs(e - e_ref) <= 1e-8 * e_ref
