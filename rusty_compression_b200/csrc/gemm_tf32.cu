@@ -6,26 +6,24 @@
 // Reference role: MatMat::matmat for f32 operators (src/types.rs:58-71), the dominant cost of
 // configs 3 and 4.
 //
-// Structure (one CTA per SM, persistent over 128-row tiles of A):
-//   warp 0      TMA producer: raw f32 A tile [128 x 32] + pre-split X^T tiles (hi, lo) [N x 32],
-//               SWIZZLE_128B, 2-4-deep mbarrier ring
-//   warps 2-5   splitter: raw A tile (shared memory) -> A_hi, A_lo written straight into TENSOR MEMORY
-//               (tcgen05.st, one thread per tile row); the MMAs take A from TMEM, so the split tiles never
-//               go back through shared memory (the SS form of this kernel was shared-memory-bandwidth
-//               bound: 152 KB of smem traffic per 16 KB of A).  Splitting A on the fly avoids a
-//               pre-split copy that would double the HBM traffic of the pass.
-//   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma (3 products x 4 K-steps of 8, A from
-//               TMEM, B from shared memory) per stage, tcgen05.commit frees the rings' slots; accumulator
-//               double-buffered in TMEM
-//   warp 10     TMA producer of the X^T tiles (own ring)
-//   warps 6-9   epilogue: tcgen05.ld (32 lanes x 16 columns) -> registers -> global Y
+// Structure (one persistent CTA of 15 warps per SM; work item = 128 rows of A x one chunk of <= 96 columns):
+//   warp 0        TMA producer of the raw f32 A tiles [128 rows x 32 k], SWIZZLE_128B, 7-8-deep ring
+//   warp 10       TMA producer of the pre-split X^T tiles (hi, lo) [N x 32 k], own 4-deep ring (L2-resident)
+//   warps 2-5,    splitters, two groups taking alternate k-blocks: raw A tile (shared memory) -> A_hi, A_lo
+//   warps 11-14   written straight into TENSOR MEMORY (tcgen05.st, one thread per tile row); the MMAs take A
+//                 from TMEM, so the split tiles never go back through shared memory.  Splitting A on the fly
+//                 avoids a pre-split copy that would double the HBM traffic of the pass.
+//   warp 1        MMA issuer: the warp runs converged and one elected lane issues 12 tcgen05.mma per k-block
+//                 (3 products x 4 K-steps of 8; A from TMEM, B from shared memory); tcgen05.commit frees the
+//                 TMEM stage and the X slot; accumulator double-buffered in TMEM
+//   warps 6-9     epilogue: tcgen05.ld (32 lanes x 16 columns) -> FP32 promotion in registers -> global Y
 // X is tiny (n x l): it is transposed and split once by a prologue kernel so that both B operands
 // are K-major TMA tiles.
 //
 // TRANS mode (Z = A^T Y, reduction over the rows of A, split-K with a fixed-order reduction): the
-// raw tile arrives as four [32 k][32 i] boxes and the splitter transposes it while splitting, so
-// the MMA still sees K-major operands (an MN-major descriptor variant produced all-zero products
-// on this toolchain and was dropped).
+// raw tile arrives as four [32 k][32 i] boxes and the splitter transposes it through registers while
+// splitting, so the MMA still sees a K-major A (an MN-major descriptor variant produced all-zero
+// products on this toolchain and was dropped).
 #include <cuda.h>
 #include <cstdlib>
 #include "rc_internal.cuh"
