@@ -174,6 +174,7 @@ struct Tf32Params {
     int nchunks;
     int vec_store;        // y and ldy are 16-byte aligned: the epilogue may use float4 stores
     int agroup;           // raw A tiles requested per group (<= RS / 2)
+    uint32_t zero;        // always 0 at run time (opaque to ptxas): ties the raw-slot release to the loaded data
 };
 
 // KC k-blocks (KC * 32 values of K) are accumulated inside the tensor core before the partial sum is
@@ -390,8 +391,10 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 // are in registers.  (An arrive placed right after the loads issues behind the LDS *issue*, and
                 // when the load/store pipe is backed up by the epilogue's store burst the TMA refill of the slot
                 // overtook the loads: whole lane-quadrants of wrong rows on CTAs with more than one work item.)
+                // (and the barrier address carries a data dependence on the loaded values, so no scheduler may
+                // hoist the arrive above the loads' completion whatever it does with the tcgen05.st)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(rawempty0 + 8 * rs);
+                if (lane == 0) mbar_arrive(rawempty0 + 8 * rs + ((hi[0] ^ lo[31]) & prm.zero));
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -511,6 +514,7 @@ void launch_tf32(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmBhi, co
     while (cols < (uint32_t)(2 * NPADC + MS * A_TMEM_COLS)) cols <<= 1;
     prm.tmem_cols = cols;
     prm.agroup = 1;     // measured: 1 is best on B200 (2, 4, 8 are 0-4 % slower at 32768^2 x 64)
+    prm.zero = 0;
     prm.vec_store = ((reinterpret_cast<uintptr_t>(prm.y) & 15) == 0 && (prm.ldy & 3) == 0 && (prm.part_stride & 3) == 0) ? 1 : 0;
     RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<RS, MS, BS, NPADC, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(prm.m_tiles * prm.splits * prm.nchunks, c->sm_count);
