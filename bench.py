@@ -22,6 +22,11 @@ import sys
 import threading
 import time
 
+if "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+    # torch.distributed.run exports OMP_NUM_THREADS=1 unless the caller set it; the CPU baseline / reference arm
+    # (rank 0 only) must use all host cores, so undo that default before OpenBLAS is loaded
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -318,6 +323,13 @@ def main():
         sampler.start()
     ctx.reset_counters()
     launches_before = ctx.counter("kernel_launches")
+    if world > 1:
+        # The first multi-process run on a fresh box is ~35 % slow for its first second or so (NCCL channels,
+        # peer mappings and the second GPU's clocks come up lazily; measured 28 vs 21 ms per step): absorb it
+        # with extra untimed steps on top of the requested warm-up.
+        for _ in range(12):
+            step_device()
+        barrier()
     ms_step = timed(step_device, args.steps, args.warmup, on_start=sampler.mark)
     launches = (ctx.counter("kernel_launches") - launches_before) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop() if rank == 0 else None
