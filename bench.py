@@ -402,7 +402,7 @@ def main():
                 os.sched_setaffinity(0, all_cpus)          # the CPU baseline uses every host core
             except Exception:
                 pass
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:       # the CPU baseline is an N = 1 figure
             m_sample = CPU_SAMPLE_ROWS
             gf, sec = cpu_sample(m_sample, "gemm")
             gv, _ = cpu_sample(2048, "gemv")
