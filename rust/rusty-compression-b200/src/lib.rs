@@ -156,3 +156,62 @@ impl<A: RcScalar> ConjMatVec for DeviceMatrix<A> {
         self.conj_matmat_device(&xd).and_then(|y| y.to_array()).expect("rc_conj_matmat").column(0).to_owned()
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Matrix-free operators: the crate's plugin API proper (anything implementing MatVec / ConjMatVec,
+// src/types.rs:40-51, 77-81) for operators that are never materialised.  A user type that can launch
+// its products on a CUDA stream implements `DeviceOperator`; `OperatorHandle::new` turns it into an
+// `rc_matrix*` (rc_operator_create) that every operator-taking entry point of the C ABI accepts.
+
+/// Products of a user operator on DEVICE buffers (row-major, leading dimensions in elements),
+/// enqueued on `stream` (the cudaStream_t the library works on).  Return 0 on success.
+pub trait DeviceOperator<A: RcScalar> {
+    fn nrows(&self) -> usize;
+    fn ncols(&self) -> usize;
+    /// y (nrows x ncols_x) = A x,  x is ncols x ncols_x
+    unsafe fn matmat(&self, x: *const A, ldx: i64, ncols_x: i64, y: *mut A, ldy: i64, stream: *mut std::os::raw::c_void) -> c_int;
+    /// z (ncols x ncols_x) = A^H x,  x is nrows x ncols_x
+    unsafe fn conj_matmat(&self, x: *const A, ldx: i64, ncols_x: i64, z: *mut A, ldz: i64, stream: *mut std::os::raw::c_void) -> c_int;
+}
+
+pub struct OperatorHandle<A: RcScalar, Op: DeviceOperator<A>> {
+    ctx: Arc<Context>,
+    h: *mut sys::rc_matrix,
+    _op: Box<Op>,                       // the callbacks borrow it through `user`
+    _a: PhantomData<A>,
+}
+impl<A: RcScalar, Op: DeviceOperator<A>> Drop for OperatorHandle<A, Op> {
+    fn drop(&mut self) { unsafe { sys::rc_matrix_free(self.h); } }
+}
+
+unsafe extern "C" fn tramp_matmat<A: RcScalar, Op: DeviceOperator<A>>(user: *mut std::os::raw::c_void, x: *const std::os::raw::c_void,
+        ldx: i64, ncols: i64, y: *mut std::os::raw::c_void, ldy: i64, stream: *mut std::os::raw::c_void) -> c_int {
+    (&*(user as *const Op)).matmat(x as *const A, ldx, ncols, y as *mut A, ldy, stream)
+}
+unsafe extern "C" fn tramp_conj<A: RcScalar, Op: DeviceOperator<A>>(user: *mut std::os::raw::c_void, x: *const std::os::raw::c_void,
+        ldx: i64, ncols: i64, z: *mut std::os::raw::c_void, ldz: i64, stream: *mut std::os::raw::c_void) -> c_int {
+    (&*(user as *const Op)).conj_matmat(x as *const A, ldx, ncols, z as *mut A, ldz, stream)
+}
+
+impl<A: RcScalar, Op: DeviceOperator<A>> OperatorHandle<A, Op> {
+    pub fn new(ctx: &Arc<Context>, op: Op) -> Result<Self> {
+        let op = Box::new(op);
+        let mut h = ptr::null_mut();
+        ctx.check(unsafe {
+            sys::rc_operator_create(ctx.raw, A::DTYPE, op.nrows() as i64, op.ncols() as i64,
+                                    Some(tramp_matmat::<A, Op>), Some(tramp_conj::<A, Op>),
+                                    &*op as *const Op as *mut std::os::raw::c_void, &mut h)
+        })?;
+        Ok(Self { ctx: ctx.clone(), h, _op: op, _a: PhantomData })
+    }
+
+    /// SampleRange::sample_range_by_rank (src/random_sampling.rs:103-118) on the matrix-free operator.
+    pub fn sample_range_by_rank<R: Rng>(&self, k: usize, p: usize, rng: &mut R) -> Result<DeviceMatrix<A>> {
+        let mut q = ptr::null_mut();
+        self.ctx.check(unsafe { sys::rc_sample_range_by_rank(self.ctx.raw, self.h, k as i64, p as i64, ptr::null(), rng.next_u64(), &mut q) })?;
+        Ok(DeviceMatrix { ctx: self.ctx.clone(), h: q, _a: PhantomData })
+    }
+    /// Raw handle for the other operator-taking entry points (rc_sample_range_power_iteration,
+    /// rc_sample_range_adaptive, rc_qr_compute_from_range_estimate, rc_svd_compute_from_range_estimate).
+    pub fn raw(&self) -> *const sys::rc_matrix { self.h }
+}
