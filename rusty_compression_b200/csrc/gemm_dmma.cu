@@ -7,12 +7,14 @@
 //     6-deep mbarrier ring; 8 consumer warps (4 x 2) own a 64 x BN tile, BN in {16..96};
 //   * fragment addressing is chosen so that every shared-memory read is bank-conflict free
 //     under the 128B swizzle: k-slot t of MMA h reads k = 8*kg + 2t + h (A and B agree), and in
-//     NN mode MMA row g is tile row 4*(g&1) + (g>>1);
+//     NN mode MMA row g is tile row 4*(g&1) + (g>>1); every fragment address is one of six per-lane
+//     constants plus an immediate (no spills at 96 registers: 2.53 -> 2.43 ms NN, 2.66 -> 2.48 ms TN);
 //   * persistent CTAs (2 per SM) walk (split, n-chunk, m-tile) work items; split-K partials are
 //     reduced in a fixed order (deterministic).
 // c64 reuses the same kernels through an exact real expansion (see gemm_dmma_c64).
 #include <cuda.h>
 #include "rc_internal.cuh"
+#include "splitk_reduce.cuh"
 
 namespace {
 
@@ -110,16 +112,199 @@ struct DmmaParams {
     uint32_t zero;        // always 0 at run time (opaque to ptxas): ties the stage release to the loaded data
 };
 
-template <int BN, bool TRANS_A>
-__global__ void __launch_bounds__(NTHREADS, 2)
-dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DmmaParams prm) {
+// ---- DMMA consumer warps -------------------------------------------------------------------------------
+// Shared-memory addressing.  A box is [16 k][16 doubles] with 128-byte rows, 16-byte chunk index XOR (k & 7).
+// For lane (g, t4), slot h of MMA kg reads k = 8 kg + kk_h with kk_h = 2 t4 + h, and column 8 gj + g of
+// 8-column group gj sits at   (gj >> 1) * 2048 + kg * 1024 + (L_h ^ ((gj & 1) << 6)),
+//   L_h = kk_h * 128 + (((g >> 1) ^ kk_h) << 4) + ((g & 1) << 3),
+// so all the B (and transposed-A) fragment addresses of a warp are four lane constants plus immediates.
+//
+// TAILW (0, 2 or 4) = number of valid columns in the LAST 8-column group of this warp's tile when the output
+// is ragged (N = BN - 8 + TAILW, e.g. l = 74 -> BN = 80, TAILW = 2); 0 for a warp whose groups are all full.
+// An m8n8k4 DMMA on that group would spend a full 16 pipe cycles per sub-partition on 2 (4) useful columns;
+// the warps that own it (column half 1) instead form those columns with plain DFMAs on the A fragments they
+// already hold: lane (g, t4) keeps the partial sum over its own k slots and the four t4 lanes are summed once
+// in the epilogue.  2 * TAILW DFMAs (2 cycles each) replace 2 DMMAs (16 cycles each) per (8 rows x 8 k); the
+// FP64 pipe runs the two back to back without a switching penalty (tools/micro/mix_fp64.cu: 16 DMMA + 8 DFMA
+// = 277 cycles against 321 for 20 DMMA).  The column half of a warp is (warp ^ (warp >> 2)) & 1, so that every
+// SM sub-partition (warp & 3) hosts one warp of each kind per CTA: with half = warp & 1 the lighter warps all
+// sat on sub-partitions 1 and 3 and the kernel was exactly as fast as without the tail path.
+// The two kinds of warp run separate instantiations of this function, so neither carries the other's registers.
+template <int BN, bool TRANS_A, int TAILW>
+__device__ __forceinline__ void dmma_consumer(const DmmaParams& prm, const uint32_t smem_base, const uint32_t full0,
+                                              const uint32_t empty0, const int* tile_ring, const int warp, const int lane) {
     constexpr int WM = BM / 4, WN = BN / 2;          // warp tile
     constexpr int RG = WM / 8, CG = WN / 8;
+    constexpr int CGD = (TAILW > 0) ? CG - 1 : CG;   // column groups on the DMMA pipe
+    constexpr int TW = (TAILW > 0) ? TAILW : 2;
+    constexpr int A_BYTES = BM * BK * 8;
+    constexpr int STAGE_BYTES = A_BYTES + BK * BN * 8;
+    constexpr int STAGES = stages_for(BN);
+    static_assert(RG == 2, "the address tables below assume two row groups per warp");
+
+    const int g = lane >> 2, t4 = lane & 3;
+    const int w1 = (warp ^ (warp >> 2)) & 1;         // column half (see above)
+    const int wm0 = (warp >> 1) * WM, wn0 = w1 * WN;
+    const int rho = 4 * (g & 1) + (g >> 1);          // NN: MMA row g <-> tile row rho (conflict-free LDS.128)
+    uint32_t L[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int kk = 2 * t4 + h;
+        L[h] = (uint32_t)(kk * 128 + (((g >> 1) ^ kk) << 4) + ((g & 1) << 3));
+    }
+    // A fragments.  NN: row = wm0 + 8 i + rho, one LDS.128 at row * 128 + (((4 kg + t4) ^ rho) << 4).
+    //               TN: column group gj = wm0 / 8 + i (wm0 / 8 is even) of the [16 k][16 i] boxes.
+    uint32_t aoff[4];
+    if (!TRANS_A) {
+        aoff[0] = (uint32_t)((wm0 + rho) * 128 + ((t4 ^ rho) << 4));
+        aoff[1] = aoff[0] ^ 64u;                      // kg = 1
+        aoff[2] = aoff[3] = 0;
+    } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) aoff[2 * h + i] = (uint32_t)((warp >> 1) * 2048) + (L[h] ^ (uint32_t)(i << 6));
+    }
+    // B fragments: group gj = w1 * CG + j; offset = boff[h][j & 1] + (j >> 1) * 2048 + kg * 1024 (see above).
+    uint32_t boff[2][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp) {
+            const int gj = w1 * CG + jp;              // group of j = jp; j = jp + 2 q adds q * 2048
+            boff[h][jp] = (uint32_t)((gj >> 1) * 2048) + (L[h] ^ (uint32_t)((gj & 1) << 6));
+        }
+    // tail columns BN - 8 + 2 c2 (+1): box BN / 16 - 1, chunk (4 + c2) ^ kk_h
+    uint32_t toff[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int kk = 2 * t4 + h;
+        toff[h] = (uint32_t)((BN / 16 - 1) * 2048 + kk * 128 + ((4 ^ kk) << 4));
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int seq = 0;; ++seq) {
+        mbar_wait(full0 + 8 * stage, phase);             // first stage of the next tile (or the sentinel)
+        const int t = tile_ring[seq & 7];
+        if (t < 0) break;
+        const int mt = t % prm.m_tiles;
+        const int rest = t / prm.m_tiles;
+        const int nc = rest % prm.n_chunks, sp = rest / prm.n_chunks;
+        const int m0 = mt * BM, n0 = nc * BN;
+        const int kbeg = sp * prm.k_chunk;
+        const int kend = min(prm.K, kbeg + prm.k_chunk);
+        double acc[RG][CGD > 0 ? CGD : 1][2];
+        double tacc[RG][TW];
+#pragma unroll
+        for (int i = 0; i < RG; ++i) {
+#pragma unroll
+            for (int j = 0; j < CGD; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+            for (int c = 0; c < TW; ++c) tacc[i][c] = 0.0;
+        }
+
+        for (int k0 = kbeg; k0 < kend; k0 += BK) {
+            if (k0 != kbeg) mbar_wait(full0 + 8 * stage, phase);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+            uint32_t dep = 0;
+#pragma unroll
+            for (int kg = 0; kg < BK / 8; ++kg) {
+                double a[RG][2], b[CGD > 0 ? CGD : 1][2], bt[2][TW];
+                if (!TRANS_A) {
+#pragma unroll
+                    for (int i = 0; i < RG; ++i) lds128(sa + aoff[kg] + i * 1024, a[i][0], a[i][1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < RG; ++i)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) a[i][h] = lds64(sa + aoff[2 * h + i] + kg * 1024);
+                }
+#pragma unroll
+                for (int j = 0; j < CGD; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) b[j][h] = lds64(sb + boff[h][j & 1] + (j >> 1) * 2048 + kg * 1024);
+                if (TAILW > 0) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int c2 = 0; c2 < TW / 2; ++c2)
+                            lds128(sb + (toff[h] ^ (uint32_t)(c2 << 4)) + kg * 1024, bt[h][2 * c2], bt[h][2 * c2 + 1]);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < RG; ++i)
+#pragma unroll
+                        for (int j = 0; j < CGD; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i][h], b[j][h]);
+                if (TAILW > 0) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < RG; ++i)
+#pragma unroll
+                            for (int c = 0; c < TW; ++c) tacc[i][c] = fma(a[i][h], bt[h][c], tacc[i][c]);
+                    dep |= (uint32_t)__double2loint(bt[1][TW - 1]);
+                }
+                dep |= (uint32_t)__double2loint(a[RG - 1][1]);
+                if (CGD > 0) dep |= (uint32_t)__double2loint(b[CGD > 0 ? CGD - 1 : 0][1]);
+            }
+            // Release the stage only once the fragments are in registers: the barrier address carries a
+            // data dependence on the last loads (dep & 0 at run time).  Without it the arrive issues right
+            // behind the LDS *issue* and a TMA refill could, in principle, overtake loads that are still
+            // queued in a backed-up load/store pipe.
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * stage + (dep & prm.zero));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        // ---- epilogue: accumulators -> global (direct or split partial)
+        double* out = prm.d + (int64_t)sp * prm.part_stride;
+        if (TAILW > 0) {          // sum the four k-slot partials of the tail columns (fixed order), whole warp
+#pragma unroll
+            for (int i = 0; i < RG; ++i)
+#pragma unroll
+                for (int c = 0; c < TW; ++c) {
+                    double v = tacc[i][c];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    tacc[i][c] = v;
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < RG; ++i) {
+            const int row = m0 + wm0 + i * 8 + (TRANS_A ? g : rho);
+            if (row >= prm.M) continue;
+#pragma unroll
+            for (int j = 0; j < CGD; ++j) {
+                const int col = n0 + wn0 + j * 8 + 2 * t4;
+                double* p = out + (int64_t)row * prm.ldd + col;
+                if (col + 1 < prm.N) {
+                    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    else { p[0] = acc[i][j][0]; p[1] = acc[i][j][1]; }
+                } else if (col < prm.N) {
+                    p[0] = acc[i][j][0];
+                }
+            }
+            if (TAILW > 0) {      // every lane of the quad holds all the sums: lane t4 writes tail column t4
+                const int col = n0 + BN - 8 + t4;
+                if (t4 < TW && col < prm.N) {
+                    double v = tacc[i][0];
+#pragma unroll
+                    for (int c = 1; c < TW; ++c) v = (t4 == c) ? tacc[i][c] : v;
+                    out[(int64_t)row * prm.ldd + col] = v;
+                }
+            }
+        }
+    }
+}
+
+template <int BN, bool TRANS_A, int TAIL>
+__global__ void __launch_bounds__(NTHREADS, 2)
+dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DmmaParams prm) {
     constexpr int A_BYTES = BM * BK * 8;             // 8 KB
     constexpr int B_BYTES = BK * BN * 8;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int STAGES = stages_for(BN);
-    static_assert(BN % 16 == 0 && WN % 8 == 0, "BN must be a multiple of 16");
+    static_assert(BN % 16 == 0, "BN must be a multiple of 16");
 
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -140,12 +325,12 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
 
     const int total = prm.m_tiles * prm.n_chunks * prm.splits;
-    int stage = 0;
-    uint32_t phase = 0;
 
     if (warp == NCW) {
         // ===================== TMA producer (one elected lane) =====================
         if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
             // Dynamic tile scheduler: an atomic counter hands out work items, so SMs that finish early
             // take more (a static round-robin over 2 CTAs/SM left ~13% of the SM-time idle in the tail).
             for (int seq = 0;; ++seq) {
@@ -180,109 +365,10 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
+    } else if (TAIL > 0 && ((warp ^ (warp >> 2)) & 1)) {
+        dmma_consumer<BN, TRANS_A, TAIL>(prm, smem_base, full0, empty0, tile_ring, warp, lane);   // owns the ragged last group
     } else {
-        // ===================== DMMA consumers =====================
-        const int g = lane >> 2, t4 = lane & 3;
-        const int wm0 = (warp >> 1) * WM, wn0 = (warp & 1) * WN;
-        const int rho = 4 * (g & 1) + (g >> 1);          // NN: MMA row g <-> tile row rho (conflict-free LDS.128)
-        for (int seq = 0;; ++seq) {
-            mbar_wait(full0 + 8 * stage, phase);             // first stage of the next tile (or the sentinel)
-            const int t = tile_ring[seq & 7];
-            if (t < 0) break;
-            const int mt = t % prm.m_tiles;
-            const int rest = t / prm.m_tiles;
-            const int nc = rest % prm.n_chunks, sp = rest / prm.n_chunks;
-            const int m0 = mt * BM, n0 = nc * BN;
-            const int kbeg = sp * prm.k_chunk;
-            const int kend = min(prm.K, kbeg + prm.k_chunk);
-            double acc[RG][CG][2];
-#pragma unroll
-            for (int i = 0; i < RG; ++i)
-#pragma unroll
-                for (int j = 0; j < CG; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-            for (int k0 = kbeg; k0 < kend; k0 += BK) {
-                if (k0 != kbeg) mbar_wait(full0 + 8 * stage, phase);
-                const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                uint32_t dep = 0;
-#pragma unroll
-                for (int kg = 0; kg < BK / 8; ++kg) {
-                    double a[RG][2], b[CG][2];
-                    if (!TRANS_A) {
-#pragma unroll
-                        for (int i = 0; i < RG; ++i) {
-                            const int row = wm0 + i * 8 + rho;
-                            const int chunk = (kg * 4 + t4) ^ (row & 7);
-                            lds128(sa + row * 128 + (chunk << 4), a[i][0], a[i][1]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < RG; ++i) {
-                            const int col = wm0 + i * 8 + g;               // i index within BM
-                            const int box = col >> 4, cb = col & 15;
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const int k = kg * 8 + 2 * t4 + h;
-                                a[i][h] = lds64(sa + box * 2048 + k * 128 + ((((cb >> 1) ^ (k & 7))) << 4) + ((cb & 1) << 3));
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < CG; ++j) {
-                        const int col = wn0 + j * 8 + g;
-                        const int box = col >> 4, cb = col & 15;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int k = kg * 8 + 2 * t4 + h;
-                            b[j][h] = lds64(sb + box * 2048 + k * 128 + ((((cb >> 1) ^ (k & 7))) << 4) + ((cb & 1) << 3));
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int i = 0; i < RG; ++i)
-#pragma unroll
-                            for (int j = 0; j < CG; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i][h], b[j][h]);
-                    dep |= (uint32_t)__double2loint(a[RG - 1][1]) | (uint32_t)__double2loint(b[CG - 1][1]);
-                }
-                // Release the stage only once the fragments are in registers: the barrier address carries a
-                // data dependence on the last loads (dep & 0 at run time).  Without it the arrive issues right
-                // behind the LDS *issue* and a TMA refill could, in principle, overtake loads that are still
-                // queued in a backed-up load/store pipe.
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty0 + 8 * stage + (dep & prm.zero));
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
-            // ---- epilogue: accumulators -> global (direct or split partial)
-            double* out = prm.d + (int64_t)sp * prm.part_stride;
-#pragma unroll
-            for (int i = 0; i < RG; ++i) {
-                const int row = m0 + wm0 + i * 8 + (TRANS_A ? g : rho);
-                if (row >= prm.M) continue;
-#pragma unroll
-                for (int j = 0; j < CG; ++j) {
-                    const int col = n0 + wn0 + j * 8 + 2 * t4;
-                    double* p = out + (int64_t)row * prm.ldd + col;
-                    if (col + 1 < prm.N) {
-                        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
-                        else { p[0] = acc[i][j][0]; p[1] = acc[i][j][1]; }
-                    } else if (col < prm.N) {
-                        p[0] = acc[i][j][0];
-                    }
-                }
-            }
-        }
-    }
-}
-
-__global__ void dmma_reduce_kernel(int64_t M, int64_t N, int splits, const double* __restrict__ part, int64_t ldp,
-                                   int64_t part_stride, double* __restrict__ c, int64_t ldc) {
-    int64_t n = M * N;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t i = e / N, j = e - i * N;
-        double s = 0.0;
-        for (int z = 0; z < splits; ++z) s += part[(int64_t)z * part_stride + i * ldp + j];
-        c[i * ldc + j] = s;
+        dmma_consumer<BN, TRANS_A, 0>(prm, smem_base, full0, empty0, tile_ring, warp, lane);
     }
 }
 
@@ -297,32 +383,39 @@ __global__ void combine_conj_kernel(int64_t n, int64_t l, const double* __restri
     }
 }
 
-template <int BN, bool TRANS_A>
+template <int BN, bool TRANS_A, int TAIL>
 void launch_dmma(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, const DmmaParams& prm) {
     constexpr int STAGE_BYTES = BM * BK * 8 + BK * BN * 8;
     size_t smem = (size_t)stages_for(BN) * STAGE_BYTES + 1024;
     static bool configured = false;
     if (!configured) {
-        RC_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel<BN, TRANS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RC_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel<BN, TRANS_A, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int total = prm.m_tiles * prm.n_chunks * prm.splits;
     int grid = std::min(total, 2 * c->sm_count);
     RC_CUDA(cudaMemsetAsync(prm.tile_counter, 0, sizeof(int), c->stream));
-    dmma_gemm_kernel<BN, TRANS_A><<<grid, NTHREADS, smem, c->stream>>>(tmA, tmB, prm);
+    dmma_gemm_kernel<BN, TRANS_A, TAIL><<<grid, NTHREADS, smem, c->stream>>>(tmA, tmB, prm);
     RC_CHECK_LAUNCH(c);
 }
 
-template <bool TRANS_A>
+template <bool TRANS_A, int TAIL>
 void dispatch_bn(rc_ctx* c, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const DmmaParams& prm) {
     switch (bn) {
-        case 16: launch_dmma<16, TRANS_A>(c, tmA, tmB, prm); break;
-        case 32: launch_dmma<32, TRANS_A>(c, tmA, tmB, prm); break;
-        case 48: launch_dmma<48, TRANS_A>(c, tmA, tmB, prm); break;
-        case 64: launch_dmma<64, TRANS_A>(c, tmA, tmB, prm); break;
-        case 80: launch_dmma<80, TRANS_A>(c, tmA, tmB, prm); break;
-        default: launch_dmma<96, TRANS_A>(c, tmA, tmB, prm); break;
+        case 16: launch_dmma<16, TRANS_A, TAIL>(c, tmA, tmB, prm); break;
+        case 32: launch_dmma<32, TRANS_A, TAIL>(c, tmA, tmB, prm); break;
+        case 48: launch_dmma<48, TRANS_A, TAIL>(c, tmA, tmB, prm); break;
+        case 64: launch_dmma<64, TRANS_A, TAIL>(c, tmA, tmB, prm); break;
+        case 80: launch_dmma<80, TRANS_A, TAIL>(c, tmA, tmB, prm); break;
+        default: launch_dmma<96, TRANS_A, TAIL>(c, tmA, tmB, prm); break;
     }
+}
+
+template <bool TRANS_A>
+void dispatch_tail(rc_ctx* c, int bn, int tail, const CUtensorMap& tmA, const CUtensorMap& tmB, const DmmaParams& prm) {
+    if (tail == 2) dispatch_bn<TRANS_A, 2>(c, bn, tmA, tmB, prm);
+    else if (tail == 4) dispatch_bn<TRANS_A, 4>(c, bn, tmA, tmB, prm);
+    else dispatch_bn<TRANS_A, 0>(c, bn, tmA, tmB, prm);
 }
 
 }  // namespace
@@ -376,14 +469,11 @@ bool gemm_dmma_f64(rc_ctx* c, bool a_transposed, int64_t M, int64_t N, int64_t K
         part.alloc(c, (size_t)splits * M * ldp);
         prm.d = part.p; prm.ldd = ldp; prm.part_stride = M * ldp;
     }
-    if (a_transposed) dispatch_bn<true>(c, bn, tmA, tmB, prm);
-    else dispatch_bn<false>(c, bn, tmA, tmB, prm);
-    if (splits > 1) {
-        int64_t n = M * N;
-        int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-        dmma_reduce_kernel<<<nb, 256, 0, c->stream>>>(M, N, splits, part.p, prm.ldd, prm.part_stride, C, ldc);
-        RC_CHECK_LAUNCH(c);
-    }
+    // ragged output (N = bn - 8 + 2 or + 4, single chunk): the last column group goes to the DFMA tail path
+    const int tail = (n_chunks == 1 && c->dmma_tail && (bn - N == 6 || bn - N == 4)) ? (int)(N - (bn - 8)) : 0;
+    if (a_transposed) dispatch_tail<true>(c, bn, tail, tmA, tmB, prm);
+    else dispatch_tail<false>(c, bn, tail, tmA, tmB, prm);
+    if (splits > 1) rc_splitk::reduce<double>(c, M, N, splits, part.p, prm.ldd, prm.part_stride, C, ldc);
     c->gemm_flops += 2 * M * N * K;
     return true;
 }

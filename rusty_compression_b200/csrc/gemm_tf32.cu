@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include "rc_internal.cuh"
+#include "splitk_reduce.cuh"
 
 namespace {
 
@@ -531,17 +532,6 @@ void dispatch_tf32(rc_ctx* c, int npad, const CUtensorMap& tmA, const CUtensorMa
     }
 }
 
-__global__ void tf32_reduce_kernel(int64_t M, int N, int splits, const float* __restrict__ part, int64_t ldp, int64_t part_stride,
-                                   float* __restrict__ z, int64_t ldz) {
-    int64_t n = M * N;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t i = e / N; int j = (int)(e - i * N);
-        float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += part[(int64_t)sp * part_stride + i * ldp + j];   // fixed order
-        z[i * ldz + j] = s;
-    }
-}
-
 }  // namespace
 
 // Y (M x N, ldy) = A (M x K, lda) * X (K x N, ldx), f32, 3xTF32 on tcgen05.  Returns false when the
@@ -616,12 +606,7 @@ bool gemm_tf32x3_f32_tn(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float*
         prm.y = part.p; prm.ldy = nrows; prm.part_stride = M * (int64_t)nrows;
     }
     dispatch_tf32<true>(c, npad, tmA, tmBhi, tmBlo, prm);
-    if (splits > 1) {
-        int64_t n = M * N;
-        int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-        tf32_reduce_kernel<<<nb, 256, 0, c->stream>>>(M, (int)N, splits, part.p, nrows, prm.part_stride, Z, ldz);
-        RC_CHECK_LAUNCH(c);
-    }
+    if (splits > 1) rc_splitk::reduce<float>(c, M, N, splits, part.p, nrows, prm.part_stride, Z, ldz);
     c->gemm_flops += 2 * M * N * K;
     return true;
 }

@@ -171,28 +171,32 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
     lds = rc_pad_ld(dtype, w);
     DevBuf<T> g(c, (size_t)w * lds), r1(c, (size_t)w * lds), rinv1(c, (size_t)w * lds), r2(c, (size_t)w * lds);
     DevBuf<double> status(c, 8);
-    double h[4];
+    double h[8];
     const bool single = (dtype == RC_F32 || dtype == RC_C32);
     const double max_ratio = single ? 2.0e2 : 1.0e6;
-    auto gram_chol = [&](const T* x, int64_t ldx, T* rr, T* ri) -> bool {
+    auto gram_chol = [&](const T* x, int64_t ldx, T* rr, T* ri, double* st) -> bool {
         if (sharded && lds != w) RC_CUDA(cudaMemsetAsync(g.p, 0, sizeof(T) * w * lds, c->stream));   // padding is summed too
         gemm<T>(c, RC_OP_H, RC_OP_N, w, w, m, x, ldx, x, ldx, g.p, lds, rc_one<T>(), rc_zero<T>());
         if (sharded) comm_allreduce_sum(c, g.p, (size_t)w * lds, dtype);      // one all-reduce of the Gram matrix
-        if (!chol_inv<T>(c, g.p, lds, w, rr, ri, lds, status.p)) return false;
-        RC_CUDA(cudaMemcpyAsync(h, status.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        RC_CUDA(cudaStreamSynchronize(c->stream));
-        return h[0] == 0.0 && h[1] > 0.0;
+        return chol_inv<T>(c, g.p, lds, w, rr, ri, lds, st);
     };
-    if (!gram_chol(y, ldy, r1.p, rinv1.p) || h[2] / h[1] > max_ratio) { c->cholqr_fallbacks++; return false; }
-    rc_trace(c, "  cholqr2: gram + chol #1");
+    // Both rounds are enqueued back to back and their status words are read with ONE host synchronisation at
+    // the end (a sync after each Cholesky left the GPU idle for a launch round trip twice per panel).  If round 1
+    // broke down, round 2 ran on garbage: its loops are data independent, nothing it wrote is used, and Y is
+    // untouched for the Householder fallback.
+    if (!gram_chol(y, ldy, r1.p, rinv1.p, status.p)) return false;
     q1.alloc(c, (size_t)m * lds);
     gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, y, ldy, rinv1.p, lds, q1.p, lds, rc_one<T>(), rc_zero<T>());
-    rc_trace(c, "  cholqr2: q1 = Y rinv1");
     rinv2.alloc(c, (size_t)w * lds);
-    if (!gram_chol(q1.p, lds, r2.p, rinv2.p) || h[3] > 0.25) { c->cholqr_fallbacks++; return false; }
-    rc_trace(c, "  cholqr2: gram + chol #2");
+    if (!gram_chol(q1.p, lds, r2.p, rinv2.p, status.p + 4)) return false;
     rfac.alloc(c, (size_t)w * lds);
     gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, r2.p, lds, r1.p, lds, rfac.p, lds, rc_one<T>(), rc_zero<T>());
+    RC_CUDA(cudaMemcpyAsync(h, status.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    const bool ok1 = h[0] == 0.0 && h[1] > 0.0 && h[2] / h[1] <= max_ratio;      // round 1: no breakdown, diag(R1) ratio
+    const bool ok2 = h[4] == 0.0 && h[5] > 0.0 && h[7] <= 0.25;                  // round 2: Gram matrix of q1 close to I
+    if (!(ok1 && ok2)) { c->cholqr_fallbacks++; return false; }
+    rc_trace(c, "  cholqr2: 2 x (gram + chol), q1 = Y rinv1");
     c->cholqr_used++;
     return true;
 }
@@ -860,6 +864,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
     if (!c || !key) return RC_INVALID_ARGUMENT;
     return guard(c, [&] {
         if (!strcmp(key, "gemm_impl")) c->gemm_impl = (int)v;
+        else if (!strcmp(key, "dmma_tail")) c->dmma_tail = (int)v;
         else if (!strcmp(key, "true_power_iteration")) c->true_power_iteration = (int)v;
         else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;
         else if (!strcmp(key, "reuse_range_b")) c->reuse_range_b = (int)v;

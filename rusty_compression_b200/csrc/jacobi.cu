@@ -61,12 +61,13 @@ jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int max_s
                 }
                 alpha = rc_warp_sum(alpha); beta = rc_warp_sum(beta);
                 gre = rc_warp_sum(gre); gim = rc_warp_sum(gim);
-                double gabs = hypot(gre, gim);
+                // real scalars: gamma is real, no hypot (a ~200-cycle call at the head of the rotation chain)
+                const double gabs = ScalarTraits<T>::is_complex ? hypot(gre, gim) : fabs(gre);
                 if (gabs == 0.0 || gabs <= tol * sqrt(alpha * beta)) continue;
                 if (lane == 0) s_rot = 1;
                 double zeta = (beta - alpha) / (2.0 * gabs);
                 double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                double cs = rsqrt(1.0 + t * t), sn = cs * t;
                 // e^{-i theta} = conj(gamma)/|gamma|
                 double er = gre / gabs, ei = -gim / gabs;
                 T ph = rc_make<T>(er, ei);
