@@ -355,7 +355,7 @@ def main():
         pj = os.path.join(ROOT, "profiles", "dominant_kernel.json")
         if os.path.exists(pj):
             prof = json.load(open(pj))
-        roofline = {"bound": "tensor", "kernel": "dmma_gemm_kernel<80,false> (FP64 tensor pipe, DMMA.8x8x4, TMA-fed)",
+        roofline = {"bound": "tensor", "kernel": "dmma_gemm_kernel<80,false,2> (FP64 tensor pipe, DMMA.8x8x4 + DFMA tail, TMA-fed)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "peak_source": "own-measured DMMA microbenchmark (rc_peaks); MEASURED_PEAKS.json has no FP64 figure",
                     "own_measured_peaks": peaks, "traffic": prof.get("dram_bytes_per_launch"),
@@ -364,7 +364,7 @@ def main():
                     "hbm_frac_of_measured": (m * n * 8 + (n + m) * l * 8) / (ms_nn * 1e-3) / 1e9 / hbm_peak,
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src,
                     "ms_per_launch": ms_nn,
-                    "tn_kernel": {"kernel": "dmma_gemm_kernel<80,true> + split-K reduce (Z = A^T Y)",
+                    "tn_kernel": {"kernel": "dmma_gemm_kernel<80,true,2> + split-K reduce (Z = A^T Y)",
                                   "ms_per_launch": ms_tn, "achieved": gemm_flops / (ms_tn * 1e-3) / 1e12,
                                   "frac": gemm_flops / (ms_tn * 1e-3) / 1e12 / peak}}
 
