@@ -81,7 +81,11 @@ const char* rc_last_error_string(rc_ctx* ctx);
 /* Tuning / test knobs.  Keys: "gemm_impl" (0 auto, 1 generic SIMT tiles only),
  * "true_power_iteration" (0 = reference semantics incl. quirk Q1, 1 = textbook iteration),
  * "qr_mode" (0 = Cholesky-QR2 fast path for well-conditioned tall panels with automatic
- * fallback to Householder TSQR, 1 = Householder TSQR always). */
+ * fallback to Householder TSQR, 1 = Householder TSQR always),
+ * "reuse_range_b" (1 = compute_from_range_estimate reuses the B = Q^H A the adaptive sampler built),
+ * "dmma_tail" (1 = a ragged last 8-column group of the FP64 tensor-pipe GEMM is formed with DFMAs,
+ * 0 = padded DMMA; same results up to summation order in those columns), "trace" (1 = stage timer
+ * on stderr; synchronises at every mark). */
 rc_status rc_ctx_set_option(rc_ctx* ctx, const char* key, int64_t value);
 /* Counters: "kernel_launches" (own kernels launched so far), "gemm_flops", "h2d_bytes",
  * "d2h_bytes", "cholqr_used", "cholqr_fallbacks".  rc_ctx_reset_counters zeroes them. */

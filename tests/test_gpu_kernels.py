@@ -94,6 +94,34 @@ def test_dmma_tma_gemm_matches_generic_and_numpy(api, dtype, shape):
     assert relerr(z_fast, np.conj(a.T).dot(y)) < 1e-13 and relerr(z_gen, np.conj(a.T).dot(y)) < 1e-13
 
 
+@pytest.mark.parametrize("l", [2, 4, 10, 12, 26, 44, 74, 76, 90, 92])
+def test_dmma_ragged_last_column_group_on_dfma_tail(api, l):
+    """l % 8 in {2, 4} with a single column chunk: the last 8-column group is formed with DFMAs by the warps that
+    own it (gemm_dmma.cu, TAILW); checked column by column against numpy and against the all-DMMA path, for
+    Y = A X, Z = A^T Y (split-K) and the c64 real expansion, with row counts that leave partial 64-row tiles."""
+    ctx = api.default_context()
+    m, n = 1000 + l, 520
+    a, x, y = rnd((m, n), np.float64, 7), rnd((n, l), np.float64, 8), rnd((m, l), np.float64, 9)
+    az, xz = rnd((m, n // 2), np.complex128, 10), rnd((n // 2, l), np.complex128, 11)
+    op, opz = api.DeviceMatrix.from_numpy(a), api.DeviceMatrix.from_numpy(az)
+    out = {}
+    try:
+        for tail in (0, 1):
+            ctx.set_option("dmma_tail", tail)
+            out[tail] = (op.matmat(x).to_numpy(), op.conj_matmat(y).to_numpy(), opz.matmat(xz).to_numpy())
+    finally:
+        ctx.set_option("dmma_tail", 1)
+    refs = (a.dot(x), a.T.dot(y), az.dot(xz))
+    for tail in (0, 1):
+        for got, want in zip(out[tail], refs):
+            assert got.shape == want.shape
+            scale = np.max(np.abs(want))
+            assert np.max(np.abs(got - want)) < 1e-13 * scale * np.sqrt(max(m, n)), (tail, l)
+    # columns outside the tail group are produced by the same DMMA sequence in both modes
+    keep = (l - 1) // 8 * 8
+    assert np.array_equal(out[0][0][:, :keep], out[1][0][:, :keep])
+
+
 @pytest.mark.parametrize("shape", [(4096, 1024, 74), (1000, 516, 10), (777, 1028, 138), (2048, 512, 266), (130, 4096, 20),
                                    # more work items than SMs (every CTA crosses item boundaries, with and without
                                    # column chunks): the regime in which a too-early release of the raw A slot showed
