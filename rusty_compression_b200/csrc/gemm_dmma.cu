@@ -13,6 +13,7 @@
 //     reduced in a fixed order (deterministic).
 // c64 reuses the same kernels through an exact real expansion (see gemm_dmma_c64).
 #include <cuda.h>
+#include <atomic>
 #include "rc_internal.cuh"
 #include "splitk_reduce.cuh"
 
@@ -387,10 +388,12 @@ template <int BN, bool TRANS_A, int TAIL>
 void launch_dmma(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, const DmmaParams& prm) {
     constexpr int STAGE_BYTES = BM * BK * 8 + BK * BN * 8;
     size_t smem = (size_t)stages_for(BN) * STAGE_BYTES + 1024;
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in shared-memory size is a per-device function attribute: remember it per device, not per process
+    static std::atomic<unsigned long long> configured{0};
+    const unsigned long long bit = 1ull << (c->device & 63);
+    if (!(configured.load(std::memory_order_relaxed) & bit)) {
         RC_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel<BN, TRANS_A, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.fetch_or(bit, std::memory_order_relaxed);
     }
     int total = prm.m_tiles * prm.n_chunks * prm.splits;
     int grid = std::min(total, 2 * c->sm_count);
