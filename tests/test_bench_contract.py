@@ -62,3 +62,18 @@ def test_cuda_arm_refuses_to_run_without_a_device():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CPU fallback" in r.stderr
+
+
+def test_profile_tools_read_the_committed_launch_list():
+    """tools/step_breakdown.py and tools/stage_roofline.py over profiles/r1_launches_final.csv (the ncu launch list of
+    the final build): the kernel's share of the step and the binding roof quoted in DESIGN.md come from these."""
+    csv_path = os.path.join(ROOT, "profiles", "r1_launches_final.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "step_breakdown.py"), csv_path],
+                         capture_output=True, text=True, check=True).stdout
+    assert "dmma_gemm_kernel" in out.splitlines()[1]          # the dominant kernel leads the list
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stage_roofline.py"), csv_path],
+                         capture_output=True, text=True, check=True).stdout
+    rows = [l for l in out.splitlines() if l.startswith("Y = A Omega") and "x3" in l]
+    assert len(rows) == 1 and "(0.9" in rows[0]               # three passes, ~0.90 of the FP64 pipe
+    shares = [float(l.split("%")[0].split()[-1]) for l in out.split("aggregated by stage kind")[1].splitlines() if "%" in l]
+    assert abs(sum(shares) - 100.0) < 0.5
