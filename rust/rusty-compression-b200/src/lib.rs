@@ -19,6 +19,9 @@ use std::os::raw::c_int;
 use std::ptr;
 use std::sync::Arc;
 
+pub mod decomp;
+pub use decomp::{compute_svd, pivoted_lq, pivoted_qr, DeviceColumnID, DeviceLQ, DeviceQR, DeviceRowID, DeviceSVD, DeviceTwoSidedID};
+
 /// Scalars the library is built for (src/types.rs:9).
 pub trait RcScalar: Scalar { const DTYPE: c_int; }
 impl RcScalar for f32 { const DTYPE: c_int = sys::RC_F32; }
@@ -26,7 +29,7 @@ impl RcScalar for f64 { const DTYPE: c_int = sys::RC_F64; }
 impl RcScalar for c32 { const DTYPE: c_int = sys::RC_C32; }
 impl RcScalar for c64 { const DTYPE: c_int = sys::RC_C64; }
 
-pub struct Context { raw: *mut sys::rc_ctx }
+pub struct Context { pub(crate) raw: *mut sys::rc_ctx }
 unsafe impl Send for Context {}
 impl Context {
     pub fn new(device: i32) -> Arc<Self> {
@@ -35,7 +38,7 @@ impl Context {
         assert_eq!(st, sys::RC_OK, "rc_ctx_create failed (no B200 visible?)");
         Arc::new(Context { raw })
     }
-    fn check(&self, st: c_int) -> Result<()> {
+    pub(crate) fn check(&self, st: c_int) -> Result<()> {
         match st {
             sys::RC_OK => Ok(()),
             sys::RC_COMPRESSION_ERROR => Err(RustyCompressionError::CompressionError),
@@ -52,7 +55,7 @@ impl Context {
 }
 impl Drop for Context { fn drop(&mut self) { unsafe { sys::rc_ctx_destroy(self.raw); } } }
 
-pub struct DeviceMatrix<A: RcScalar> { ctx: Arc<Context>, h: *mut sys::rc_matrix, _a: PhantomData<A> }
+pub struct DeviceMatrix<A: RcScalar> { pub(crate) ctx: Arc<Context>, pub(crate) h: *mut sys::rc_matrix, _a: PhantomData<A> }
 impl<A: RcScalar> Drop for DeviceMatrix<A> { fn drop(&mut self) { unsafe { sys::rc_matrix_free(self.h); } } }
 
 impl<A: RcScalar> DeviceMatrix<A> {
@@ -64,8 +67,8 @@ impl<A: RcScalar> DeviceMatrix<A> {
                                                     a.ncols() as i64, rs, cs, &mut h) })?;
         Ok(DeviceMatrix { ctx: ctx.clone(), h, _a: PhantomData })
     }
-    fn from_raw(ctx: &Arc<Context>, h: *mut sys::rc_matrix) -> Self { DeviceMatrix { ctx: ctx.clone(), h, _a: PhantomData } }
-    fn download(ctx: &Arc<Context>, h: *const sys::rc_matrix) -> Result<Array2<A>> {
+    pub(crate) fn from_raw(ctx: &Arc<Context>, h: *mut sys::rc_matrix) -> Self { DeviceMatrix { ctx: ctx.clone(), h, _a: PhantomData } }
+    pub(crate) fn download(ctx: &Arc<Context>, h: *const sys::rc_matrix) -> Result<Array2<A>> {
         let (r, c) = unsafe { (sys::rc_matrix_rows(h) as usize, sys::rc_matrix_cols(h) as usize) };
         let mut out = Array2::<A>::zeros((r, c));
         ctx.check(unsafe { sys::rc_matrix_to_host(ctx.raw, h, out.as_mut_ptr() as *mut _) })?;
