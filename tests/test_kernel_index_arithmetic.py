@@ -82,3 +82,26 @@ def test_fragment_loads_are_bank_conflict_free(trans):
                         off = direct_a_nn_offset((warp >> 1) * 16 + i * 8 + rho, kg * 4 + t4)
                         chunks.add((off % 128) // 16)
                     assert len(chunks) == 8
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 64, 74, 129])
+def test_jacobi_round_robin_schedule_visits_every_pair_once_per_sweep(n):
+    """jacobi_kernel (csrc/jacobi.cu): round r, slot k rotates the pair (a, b) below; within a round the pairs are
+    disjoint (one warp each, no races on columns), over a sweep every unordered pair of the n columns appears once."""
+    npad = n + (n & 1)
+    half = npad // 2
+    seen = set()
+    for rnd in range(npad - 1):
+        cols = set()
+        for k in range(half):
+            if k == 0:
+                a, b = npad - 1, rnd
+            else:
+                a, b = (rnd + k) % (npad - 1), (rnd - k + (npad - 1)) % (npad - 1)
+            p, q = min(a, b), max(a, b)
+            assert p != q and p not in cols and q not in cols
+            cols.update((p, q))
+            if q < n:                      # the padding column of an odd n is skipped
+                assert (p, q) not in seen
+                seen.add((p, q))
+    assert len(seen) == n * (n - 1) // 2
