@@ -82,6 +82,8 @@ const char* rc_last_error_string(rc_ctx* ctx);
  * "true_power_iteration" (0 = reference semantics incl. quirk Q1, 1 = textbook iteration),
  * "qr_mode" (0 = Cholesky-QR2 fast path for well-conditioned tall panels with automatic
  * fallback to Householder TSQR, 1 = Householder TSQR always),
+ * "pivot_precision" (1, the default = pivot decisions on f32 / c32 inputs are taken in double precision -- the sequence
+ * ?geqp3 picks in double on the same single-precision data; 0 = working precision),
  * "reuse_range_b" (1 = compute_from_range_estimate reuses the B = Q^H A the adaptive sampler built),
  * "dmma_tail" (1 = a ragged last 8-column group of the FP64 tensor-pipe GEMM is formed with DFMAs,
  * 0 = padded DMMA; same results up to summation order in those columns), "trace" (1 = stage timer
@@ -217,6 +219,11 @@ rc_status rc_sample_range_adaptive(rc_ctx* ctx, const rc_matrix* a, double rel_t
  * PivotedQR::pivoted_qr (src/pivoted_qr.rs:11-31, 81-184) under QRTraits::compute_from
  * (src/qr.rs:214, 251-253): A P = Q R, q m x k', r k' x n upper trapezoidal, k' = min(m, n). */
 rc_status rc_qr_compute_from(rc_ctx* ctx, const rc_matrix* arr, rc_qr** out);
+/* QR{q, r, ind} built from parts: the struct has pub fields (src/qr.rs:31-40), so a caller of the crate can assemble
+ * one and call column_id() / compress() / to_mat() on it.  q is m x k, r is k x n, ind has length n; the matrices
+ * are copied. */
+rc_status rc_qr_new(rc_ctx* ctx, const rc_matrix* q, const rc_matrix* r, const uint64_t* ind, size_t n,
+                    rc_qr** out);
 /* QRTraits::compute_from_range_estimate (src/qr.rs:221-224, 311-323). */
 rc_status rc_qr_compute_from_range_estimate(rc_ctx* ctx, const rc_matrix* range, const rc_matrix* op,
                                             rc_qr** out);
@@ -235,6 +242,9 @@ rc_status rc_qr_free(rc_qr* qr);
 
 /* PivotedQR::pivoted_lq (src/pivoted_qr.rs:32-41), LQTraits (src/qr.rs:54-139, 326-405). */
 rc_status rc_lq_compute_from(rc_ctx* ctx, const rc_matrix* arr, rc_lq** out);
+/* LQ{l, q, ind} from parts (pub fields, src/qr.rs:42-51): l is m x k, q is k x n, ind has length m. */
+rc_status rc_lq_new(rc_ctx* ctx, const rc_matrix* l, const rc_matrix* q, const uint64_t* ind, size_t n,
+                    rc_lq** out);
 rc_status rc_lq_compress_rank(rc_ctx* ctx, const rc_lq* lq, int64_t max_rank, rc_lq** out);
 rc_status rc_lq_compress_tolerance(rc_ctx* ctx, const rc_lq* lq, double tol, rc_lq** out);
 rc_status rc_lq_to_mat(rc_ctx* ctx, const rc_lq* lq, rc_matrix** out);          /* src/qr.rs:73-78 */
@@ -250,6 +260,10 @@ rc_status rc_lq_free(rc_lq* lq);
 /* ================================================================ SVD
  * ComputeSVD::compute_svd (src/compute_svd.rs:8-35) under SVDTraits::compute_from (src/svd.rs:103). */
 rc_status rc_svd_compute_from(rc_ctx* ctx, const rc_matrix* arr, rc_svd** out);
+/* SVD{u, s, vt} from parts (pub fields, src/svd.rs:13-20): u is m x k, s has k real entries (passed as double,
+ * A::Real widened), vt is k x n. */
+rc_status rc_svd_new(rc_ctx* ctx, const rc_matrix* u, const double* s, size_t ns, const rc_matrix* vt,
+                     rc_svd** out);
 /* SVDTraits::compute_from_range_estimate (src/svd.rs:110-113, 171-183). */
 rc_status rc_svd_compute_from_range_estimate(rc_ctx* ctx, const rc_matrix* range, const rc_matrix* op,
                                              rc_svd** out);

@@ -435,6 +435,13 @@ template <class A>
 class QR {
   public:
     QR(Context ctx, rc_qr* h) : ctx_(std::move(ctx)), h_(h, [](rc_qr* p) { rc_qr_free(p); }) {}
+    // `QR { q, r, ind }` from parts: the crate's struct has pub fields (:31-40)
+    static QR make(const Matrix<A>& q, const Matrix<A>& r, const std::vector<size_t>& ind) {
+        std::vector<uint64_t> iv = detail::to_u64(ind);
+        rc_qr* h = nullptr;
+        q.context().check(rc_qr_new(q.context().raw(), q.raw(), r.raw(), iv.data(), iv.size(), &h));
+        return QR(q.context(), h);
+    }
     static QR compute_from(const Matrix<A>& arr) {                                           // :214, 251-253
         rc_qr* h = nullptr;
         arr.context().check(rc_qr_compute_from(arr.context().raw(), arr.raw(), &h));
@@ -489,6 +496,13 @@ template <class A>
 class LQ {
   public:
     LQ(Context ctx, rc_lq* h) : ctx_(std::move(ctx)), h_(h, [](rc_lq* p) { rc_lq_free(p); }) {}
+    // `LQ { l, q, ind }` from parts (pub fields, :42-51)
+    static LQ make(const Matrix<A>& l, const Matrix<A>& q, const std::vector<size_t>& ind) {
+        std::vector<uint64_t> iv = detail::to_u64(ind);
+        rc_lq* h = nullptr;
+        l.context().check(rc_lq_new(l.context().raw(), l.raw(), q.raw(), iv.data(), iv.size(), &h));
+        return LQ(l.context(), h);
+    }
     static LQ compute_from(const Matrix<A>& arr) {                                           // :135, 354-362
         rc_lq* h = nullptr;
         arr.context().check(rc_lq_compute_from(arr.context().raw(), arr.raw(), &h));
@@ -539,6 +553,13 @@ class SVD {
   public:
     using Real = typename ScalarTraits<A>::Real;
     SVD(Context ctx, rc_svd* h) : ctx_(std::move(ctx)), h_(h, [](rc_svd* p) { rc_svd_free(p); }) {}
+    // `SVD { u, s, vt }` from parts (pub fields, :13-20)
+    static SVD make(const Matrix<A>& u, const std::vector<Real>& s, const Matrix<A>& vt) {
+        std::vector<double> sv(s.begin(), s.end());
+        rc_svd* h = nullptr;
+        u.context().check(rc_svd_new(u.context().raw(), u.raw(), sv.data(), sv.size(), vt.raw(), &h));
+        return SVD(u.context(), h);
+    }
     static SVD compute_from(const Matrix<A>& arr) {                                          // :103, 165-169
         rc_svd* h = nullptr;
         arr.context().check(rc_svd_compute_from(arr.context().raw(), arr.raw(), &h));

@@ -245,9 +245,10 @@ class ColumnID:
     def dot(self, rhs):
         return self.c.dot(self.z.dot(rhs))                          # :141, :152
 
-    def two_sided_id(self):
-        """src/col_interp_decomp.rs:116-125 (quirk Q10: uncompressed LQ of C)."""
-        row_id = LQ.compute_from(self.c).row_id()
+    def two_sided_id(self, order=None):
+        """src/col_interp_decomp.rs:116-125 (quirk Q10: uncompressed LQ of C).  ``order``: replay with a prescribed
+        pivot order (tie adjudication in the parity tests, see ``pivoted_qr_with_order``)."""
+        row_id = LQ.compute_from(self.c, order=order).row_id()
         return TwoSidedID(c=row_id.x, x=row_id.r, r=self.z,
                           row_ind=row_id.row_ind, col_ind=self.col_ind)
 
@@ -273,9 +274,9 @@ class RowID:
     def dot(self, rhs):
         return self.x.dot(self.r.dot(rhs))                          # :141, :152
 
-    def two_sided_id(self):
-        """src/row_interp_decomp.rs:120-130."""
-        col_id = QR.compute_from(self.r).column_id()
+    def two_sided_id(self, order=None):
+        """src/row_interp_decomp.rs:120-130.  ``order``: see ``ColumnID.two_sided_id``."""
+        col_id = QR.compute_from(self.r, order=order).column_id()
         return TwoSidedID(c=self.x, x=col_id.c, r=col_id.z,
                           row_ind=self.row_ind, col_ind=col_id.col_ind)
 
@@ -349,16 +350,16 @@ class QR:
         return self.compress_qr_rank(ctype.rank)
 
     @staticmethod
-    def compute_from(arr):
-        """:251-253"""
-        return QR(*pivoted_qr(arr))
+    def compute_from(arr, order=None):
+        """:251-253.  ``order`` (test infrastructure, not in the crate): replay with a prescribed pivot order."""
+        return QR(*(pivoted_qr(arr) if order is None else pivoted_qr_with_order(arr, order)))
 
     @staticmethod
-    def compute_from_range_estimate(rng_q, op, route="gemm"):
+    def compute_from_range_estimate(rng_q, op, route="gemm", order=None):
         """:311-323   b = (A^H Q)^H ; pivoted QR of b ; q <- Q q_b"""
         op = _as_op(op, route)
         b = conj_t(op.conj_matmat(rng_q))
-        qb, rb, ind = pivoted_qr(b)
+        qb, rb, ind = pivoted_qr(b) if order is None else pivoted_qr_with_order(b, order)
         return QR(rng_q.dot(qb), rb, ind)
 
     def column_id(self):
@@ -419,9 +420,9 @@ class LQ:
         return self.compress_lq_rank(ctype.rank)
 
     @staticmethod
-    def compute_from(arr):
-        """:354-362"""
-        q, r, ind = pivoted_qr(conj_t(arr))
+    def compute_from(arr, order=None):
+        """:354-362.  ``order``: see ``QR.compute_from``."""
+        q, r, ind = pivoted_qr(conj_t(arr)) if order is None else pivoted_qr_with_order(conj_t(arr), order)
         return LQ(conj_t(r), conj_t(q), ind)
 
     def row_id(self):
@@ -634,21 +635,29 @@ def range_residual(a, q):
     return np.linalg.norm(a - q.dot(conj_t(q).dot(a))) / np.linalg.norm(a)
 
 
-def pivot_gaps(arr, ind):
-    """Relative gap between the chosen pivot norm and the runner-up at every step
-    of a pivoted QR with pivot order ``ind`` (f64 Householder replay).  Used to
-    adjudicate bit-exactness of skeleton indices: a mismatch only counts where
-    the gap exceeds 1e-6 (north_star)."""
-    wide = np.complex128 if np.iscomplexobj(arr) else np.float64
-    w = np.array(arr, dtype=wide)[:, np.asarray(ind)]
+def _wide_dtype(arr):
+    return np.complex128 if np.iscomplexobj(arr) else np.float64
+
+
+def pivot_gaps(arr, ind, upto=None):
+    """Signed relative gap at every step of a pivoted QR of ``arr`` that takes its pivots in the order
+    ``ind`` (double-precision Householder replay; single-precision inputs are widened exactly):
+
+        gap[j] = (norm of the chosen column - largest norm among the other candidates) / norm of the chosen column
+
+    evaluated on the trailing matrix of step j.  gap[j] > 0: the choice was the maximum, by that margin;
+    gap[j] < 0: another column was larger by |gap[j]|.  Used to adjudicate bit-exactness of skeleton indices:
+    a choice only counts as wrong where the gap exceeds 1e-6 (north_star)."""
+    w = np.array(arr, dtype=_wide_dtype(arr))[:, np.asarray(ind)]
     m, n = w.shape
-    k = min(m, n)
+    k = min(m, n) if upto is None else min(m, n, int(upto))
     gaps = np.full(k, np.inf)
+    tiny = np.finfo(np.float64).tiny
     for j in range(k):
         norms = np.linalg.norm(w[j:, j:], axis=0)
         if len(norms) > 1:
             others = np.max(norms[1:])
-            gaps[j] = (norms[0] - others) / max(norms[0], np.finfo(np.float64).tiny)
+            gaps[j] = (norms[0] - others) / max(norms[0], others, tiny)
         x = w[j:, j].copy()
         nx = np.linalg.norm(x)
         if nx == 0:
@@ -659,3 +668,69 @@ def pivot_gaps(arr, ind):
         v = x / np.linalg.norm(x)
         w[j:, j:] -= 2.0 * np.outer(v, np.conj(v).dot(w[j:, j:]))
     return gaps
+
+
+def pivot_sequence_f64(arr):
+    """the pivot sequence ?geqp3 picks when its norms are carried in DOUBLE precision on the given
+    input -- dgeqp3 / zgeqp3 on the exactly widened f32 / c32 data (identical to ``pivoted_qr(arr)[2]`` for
+    f64 / c64).  sgeqp3's own downdated norms are only good to ~sqrt(eps_f32) before its safeguard fires, so with
+    thousands of candidate columns its sequence is not reproducible at the 1e-6 gap the contract names; this
+    one is, and it is the sequence the CUDA path is held to."""
+    return pivoted_qr(np.asarray(arr).astype(_wide_dtype(arr)))[2]
+
+
+def pivoted_qr_with_order(arr, ind):
+    """The factorisation ?geqp3 returns when it takes its pivots in the order ``ind``: unpivoted Householder QR
+    (?geqrf + ?orgqr/?ungqr) of ``arr[:, ind]``, in the working precision, same post-processing as ``pivoted_qr``
+    (src/pivoted_qr.rs:100-114).  Lets a parity test continue past a numerical tie: the oracle is replayed with the
+    choice the device made at the tied step instead of skipping everything that follows."""
+    arr = np.asarray(arr)
+    ind = np.asarray(ind, dtype=np.int64)
+    m, n = arr.shape
+    k = min(m, n)
+    mat = np.asfortranarray(arr[:, ind])
+    geqrf = _lapack("geqrf", arr.dtype)
+    qr, tau, _work, info = geqrf(mat)
+    if info != 0:
+        raise PivotedQRError(f"geqrf info={info}")
+    r = np.triu(qr[:k, :])
+    orgqr = _lapack("orgqr", arr.dtype)
+    qfull, _work, info = orgqr(np.asfortranarray(qr[:, :k]), tau)
+    if info != 0:
+        raise PivotedQRError(f"orgqr info={info}")
+    return np.ascontiguousarray(qfull[:, :k]), np.ascontiguousarray(r), ind.copy()
+
+
+def check_pivot_sequence(arr, got, upto=None, tie=1e-6):
+    """Adjudicates a pivot sequence ``got`` (first ``upto`` steps) produced for the input ``arr`` against the contract
+    "bit-exact wherever the pivot norm gap exceeds ``tie`` relative".
+
+    Every step of ``got`` is replayed in double precision and must have picked a column whose trailing norm is the
+    maximum or within ``tie`` of it -- a complete check (every step, not only the first mismatch), which is what
+    makes it possible to continue after a tie instead of skipping.  Returns a report
+
+        {"identical": got == want on the first `upto` steps (want = pivot_sequence_f64(arr)),
+         "first_divergence": None | (step, |gap| at that step),
+         "ties": [(step, gap) for the steps where the choice was not the strict maximum],
+         "min_gap": the smallest signed gap over the checked steps}
+
+    and raises AssertionError naming the first step that violates the contract."""
+    got = np.asarray(got, dtype=np.int64)
+    m, n = np.asarray(arr).shape
+    k = min(m, n) if upto is None else min(m, n, int(upto))
+    want = pivot_sequence_f64(arr)
+    identical = bool(np.array_equal(got[:k], want[:k]))
+    report = {"identical": identical, "first_divergence": None, "ties": [], "min_gap": np.inf}
+    if identical:
+        return report
+    assert sorted(got.tolist()) == list(range(n)), "pivot vector is not a permutation"
+    gaps = pivot_gaps(arr, got, upto=k)
+    j0 = int(np.nonzero(got[:k] != want[:k])[0][0])
+    report["first_divergence"] = (j0, float(abs(gaps[j0])))
+    report["ties"] = [(int(j), float(g)) for j, g in enumerate(gaps) if g < 0]
+    report["min_gap"] = float(np.min(gaps))
+    bad = np.nonzero(gaps < -tie)[0]
+    assert len(bad) == 0, (f"pivot sequence violates the contract: first divergence from the double-precision ?geqp3 "
+                           f"sequence at step {j0} (gap {abs(gaps[j0]):.3e}); step {int(bad[0])} picked a column whose norm "
+                           f"is {abs(gaps[int(bad[0])]):.3e} (relative) below the maximum, limit {tie:.1e}")
+    return report

@@ -74,6 +74,7 @@ extern "C" {
     pub fn rc_sample_range_power_iteration(ctx: *mut rc_ctx, a: *const rc_matrix, k: i64, p: i64, it_count: i64, omega: *const rc_matrix, seed: u64, q: *mut *mut rc_matrix) -> c_int;
     pub fn rc_sample_range_adaptive(ctx: *mut rc_ctx, a: *const rc_matrix, rel_tol: f64, sample_size: i64, omega_blocks: *const rc_matrix, seed: u64, max_rank: i64, q: *mut *mut rc_matrix, hist_rank: *mut u64, hist_res: *mut f64, hist_cap: usize, hist_len: *mut usize) -> c_int;
     pub fn rc_qr_compute_from(ctx: *mut rc_ctx, arr: *const rc_matrix, out: *mut *mut rc_qr) -> c_int;
+    pub fn rc_qr_new(ctx: *mut rc_ctx, q: *const rc_matrix, r: *const rc_matrix, ind: *const u64, n: usize, out: *mut *mut rc_qr) -> c_int;
     pub fn rc_qr_compute_from_range_estimate(ctx: *mut rc_ctx, range: *const rc_matrix, op: *const rc_matrix, out: *mut *mut rc_qr) -> c_int;
     pub fn rc_qr_compress_rank(ctx: *mut rc_ctx, qr: *const rc_qr, max_rank: i64, out: *mut *mut rc_qr) -> c_int;
     pub fn rc_qr_compress_tolerance(ctx: *mut rc_ctx, qr: *const rc_qr, tol: f64, out: *mut *mut rc_qr) -> c_int;
@@ -87,6 +88,7 @@ extern "C" {
     pub fn rc_qr_get_ind(qr: *const rc_qr, out: *mut u64, n: usize) -> c_int;
     pub fn rc_qr_free(qr: *mut rc_qr) -> c_int;
     pub fn rc_lq_compute_from(ctx: *mut rc_ctx, arr: *const rc_matrix, out: *mut *mut rc_lq) -> c_int;
+    pub fn rc_lq_new(ctx: *mut rc_ctx, l: *const rc_matrix, q: *const rc_matrix, ind: *const u64, n: usize, out: *mut *mut rc_lq) -> c_int;
     pub fn rc_lq_compress_rank(ctx: *mut rc_ctx, lq: *const rc_lq, max_rank: i64, out: *mut *mut rc_lq) -> c_int;
     pub fn rc_lq_compress_tolerance(ctx: *mut rc_ctx, lq: *const rc_lq, tol: f64, out: *mut *mut rc_lq) -> c_int;
     pub fn rc_lq_to_mat(ctx: *mut rc_ctx, lq: *const rc_lq, out: *mut *mut rc_matrix) -> c_int;
@@ -99,6 +101,7 @@ extern "C" {
     pub fn rc_lq_get_ind(lq: *const rc_lq, out: *mut u64, n: usize) -> c_int;
     pub fn rc_lq_free(lq: *mut rc_lq) -> c_int;
     pub fn rc_svd_compute_from(ctx: *mut rc_ctx, arr: *const rc_matrix, out: *mut *mut rc_svd) -> c_int;
+    pub fn rc_svd_new(ctx: *mut rc_ctx, u: *const rc_matrix, s: *const f64, ns: usize, vt: *const rc_matrix, out: *mut *mut rc_svd) -> c_int;
     pub fn rc_svd_compute_from_range_estimate(ctx: *mut rc_ctx, range: *const rc_matrix, op: *const rc_matrix, out: *mut *mut rc_svd) -> c_int;
     pub fn rc_svd_compress_rank(ctx: *mut rc_ctx, svd: *const rc_svd, max_rank: i64, out: *mut *mut rc_svd) -> c_int;
     pub fn rc_svd_compress_tolerance(ctx: *mut rc_ctx, svd: *const rc_svd, tol: f64, out: *mut *mut rc_svd) -> c_int;

@@ -47,6 +47,13 @@ macro_rules! new_matrix {
 }
 
 impl<A: RcScalar> DeviceQR<A> {
+    /// `QR { q, r, ind }` assembled from parts (the reference's struct has pub fields, src/qr.rs:31-40).
+    pub fn from_parts(q: &DeviceMatrix<A>, r: &DeviceMatrix<A>, ind: &[usize]) -> Result<Self> {
+        let iv: Vec<u64> = ind.iter().map(|&i| i as u64).collect();
+        let mut h = ptr::null_mut();
+        q.ctx.check(unsafe { sys::rc_qr_new(q.ctx.raw, q.h, r.h, iv.as_ptr(), iv.len(), &mut h) })?;
+        Ok(Self::from_raw(&q.ctx, h))
+    }
     /// QRTraits::compute_from (src/qr.rs:214, 251-253)
     pub fn compute_from(arr: &DeviceMatrix<A>) -> Result<Self> {
         let mut h = ptr::null_mut();
@@ -92,6 +99,13 @@ impl<A: RcScalar> DeviceQR<A> {
 }
 
 impl<A: RcScalar> DeviceLQ<A> {
+    /// `LQ { l, q, ind }` assembled from parts (pub fields, src/qr.rs:42-51).
+    pub fn from_parts(l: &DeviceMatrix<A>, q: &DeviceMatrix<A>, ind: &[usize]) -> Result<Self> {
+        let iv: Vec<u64> = ind.iter().map(|&i| i as u64).collect();
+        let mut h = ptr::null_mut();
+        l.ctx.check(unsafe { sys::rc_lq_new(l.ctx.raw, l.h, q.h, iv.as_ptr(), iv.len(), &mut h) })?;
+        Ok(Self::from_raw(&l.ctx, h))
+    }
     /// LQTraits::compute_from (src/qr.rs:135, 354-362)
     pub fn compute_from(arr: &DeviceMatrix<A>) -> Result<Self> {
         let mut h = ptr::null_mut();

@@ -72,6 +72,9 @@ SIGNATURES = {
     "rc_sample_range_adaptive": (c_int, [H, H, c_double, c_int64, H, c_uint64, c_int64, PH, PU64, PD, c_size_t,
                                          POINTER(c_size_t)]),
     "rc_qr_compute_from": (c_int, [H, H, PH]),
+    "rc_qr_new": (c_int, [H, H, H, PU64, c_size_t, PH]),
+    "rc_lq_new": (c_int, [H, H, H, PU64, c_size_t, PH]),
+    "rc_svd_new": (c_int, [H, H, PD, c_size_t, H, PH]),
     "rc_qr_compute_from_range_estimate": (c_int, [H, H, H, PH]),
     "rc_qr_compress_rank": (c_int, [H, H, c_int64, PH]),
     "rc_qr_compress_tolerance": (c_int, [H, H, c_double, PH]),

@@ -479,6 +479,16 @@ class QR(_Handle):
         return self._call_new(self.ctx.lib.rc_qr_column_id, ColumnID)
 
     @staticmethod
+    def new(q, r, ind, ctx=None):
+        """`QR { q, r, ind }` from parts (pub fields, src/qr.rs:31-40)."""
+        qd = _as_dev(q, ctx)
+        rd = _as_dev(r, qd.ctx)
+        p, pp = _u64(ind)
+        h = c_void_p()
+        qd.ctx.check(qd.ctx.lib.rc_qr_new(qd.ctx.h, qd.h, rd.h, pp, len(p), ctypes.byref(h)))
+        return QR(qd.ctx, h)
+
+    @staticmethod
     def compute_from(arr, ctx=None):
         d = _as_dev(arr, ctx)
         h = c_void_p()
@@ -530,6 +540,16 @@ class LQ(_Handle):
 
     def row_id(self):
         return self._call_new(self.ctx.lib.rc_lq_row_id, RowID)
+
+    @staticmethod
+    def new(l, q, ind, ctx=None):
+        """`LQ { l, q, ind }` from parts (pub fields, src/qr.rs:42-51)."""
+        ld = _as_dev(l, ctx)
+        qd = _as_dev(q, ld.ctx)
+        p, pp = _u64(ind)
+        h = c_void_p()
+        ld.ctx.check(ld.ctx.lib.rc_lq_new(ld.ctx.h, ld.h, qd.h, pp, len(p), ctypes.byref(h)))
+        return LQ(ld.ctx, h)
 
     @staticmethod
     def compute_from(arr, ctx=None):
@@ -585,6 +605,17 @@ class SVD(_Handle):
         if isinstance(ctype, ADAPTIVE):
             return self.compress_svd_tolerance(ctype.tol)
         return self.compress_svd_rank(ctype.rank)
+
+    @staticmethod
+    def new(u, s, vt, ctx=None):
+        """`SVD { u, s, vt }` from parts (pub fields, src/svd.rs:13-20)."""
+        ud = _as_dev(u, ctx)
+        vd = _as_dev(vt, ud.ctx)
+        sv = np.ascontiguousarray(np.asarray(s, dtype=np.float64))
+        h = c_void_p()
+        ud.ctx.check(ud.ctx.lib.rc_svd_new(ud.ctx.h, ud.h, sv.ctypes.data_as(ctypes.POINTER(c_double)), len(sv), vd.h,
+                                           ctypes.byref(h)))
+        return SVD(ud.ctx, h)
 
     @staticmethod
     def compute_from(arr, ctx=None):

@@ -21,7 +21,12 @@ namespace {
 template <class F>
 rc_status guard(rc_ctx* ctx, F&& f) {
     try {
-        f();
+        if (ctx && ctx->stream) {
+            DeviceGuard dg(ctx->device);
+            f();
+        } else {
+            f();
+        }
         return RC_OK;
     } catch (const RcError& e) {
         if (ctx) ctx->err = e.msg;
@@ -314,6 +319,26 @@ void pivoted_qr_impl(rc_ctx* c, const rc_matrix* arr, bool input_is_conj_transpo
     const int64_t kk = std::min(p, n);
     if (ncq < 0 || ncq > kk) ncq = kk;
     const bool sharded = !input_is_conj_transposed && mat_sharded(arr);
+    // Single-precision inputs of moderate size are factored entirely in double (input widened exactly, Q and R
+    // rounded back once): the pivot sequence is then ?geqp3's in double precision on the same f32 / c32 data, for
+    // tall inputs too (whose reduction to R would otherwise carry f32 roundoff into the deep pivot norms).  Larger
+    // single-precision inputs keep the unpivoted reduction in working precision and only pivot in double (pivqr.cu).
+    using W = typename AccOf<T>::type;
+    if constexpr (!std::is_same<T, W>::value) {
+        if (c->pivot_f64 && !sharded && p * n <= (int64_t)1 << 20) {
+            MatPtr wide(mat_new(c, dtype | 1, arr->rows, arr->cols));
+            k_cast<W, T>(c, P<W>(wide.get()), wide->ld, P<T>(arr), arr->ld, arr->rows, arr->cols);
+            QrParts ow;
+            pivoted_qr_impl<W>(c, wide.get(), input_is_conj_transposed, ncq, true, ow);
+            MatPtr q(mat_new(c, dtype, ow.q->rows, ow.q->cols)), r(mat_new(c, dtype, ow.r->rows, ow.r->cols));
+            k_cast<T, W>(c, P<T>(q.get()), q->ld, P<W>(ow.q.get()), ow.q->ld, q->rows, q->cols);
+            k_cast<T, W>(c, P<T>(r.get()), r->ld, P<W>(ow.r.get()), ow.r->ld, r->rows, r->cols);
+            out.q.reset(q.release());
+            out.r.reset(r.release());
+            out.ind = std::move(ow.ind);
+            return;
+        }
+    }
     const int64_t p_global = sharded ? arr->global_rows : p;
 
     if (p_global >= n && (p >= n || sharded)) {
@@ -454,13 +479,24 @@ rc_matrix* conj_matmat_impl(rc_ctx* c, const rc_matrix* a, const rc_matrix* x) {
         if (rc != 0) RC_THROW(RC_LINALG_ERROR, "operator conj_matmat callback failed (%d)", rc);
         c->launches++;
     } else {
-        z.reset(mat_mul<T>(c, RC_OP_H, a, RC_OP_N, x));
+        z.reset(mat_new(c, a->dtype, a->cols, x->cols));
+        // the row padding (ld > cols: e.g. l = 74 in f32 gives ld = 76) travels through the all-reduce below, so it
+        // is zeroed instead of reducing 8192 rows one collective at a time
+        if (mat_sharded(a) && z->ld != z->cols)
+            RC_CUDA(cudaMemsetAsync(z->data, 0, (size_t)z->rows * z->ld * rc_dtype_size(z->dtype), c->stream));
+        gemm<T>(c, RC_OP_H, RC_OP_N, a->cols, x->cols, a->rows, P<T>(a), a->ld, P<T>(x), x->ld, P<T>(z.get()), z->ld,
+                rc_one<T>(), rc_zero<T>());
     }
     if (mat_sharded(a)) {
-        // reduce the dense payload row by row when padded; ld == cols for the common case
-        if (z->ld == z->cols) comm_allreduce_sum(c, z->data, (size_t)z->rows * z->cols, z->dtype);
-        else for (int64_t i = 0; i < z->rows; ++i)
-            comm_allreduce_sum(c, (char*)z->data + (size_t)i * z->ld * rc_dtype_size(z->dtype), (size_t)z->cols, z->dtype);
+        if (a->op_matmat && z->ld != z->cols) {
+            // a callback wrote only the payload: pack, reduce once, unpack
+            DevBuf<T> dense(c, (size_t)z->rows * z->cols);
+            k_copy<T>(c, dense.p, z->cols, P<T>(z.get()), z->ld, z->rows, z->cols);
+            comm_allreduce_sum(c, dense.p, (size_t)z->rows * z->cols, z->dtype);
+            k_copy<T>(c, P<T>(z.get()), z->ld, dense.p, z->cols, z->rows, z->cols);
+        } else {
+            comm_allreduce_sum(c, z->data, (size_t)z->rows * z->ld, z->dtype);      // ONE all-reduce of the n x l partials
+        }
     }
     return z.release();
 }
@@ -810,6 +846,8 @@ rc_status rc_ctx_create(int device, rc_ctx** out) {
     if (!out) return RC_INVALID_ARGUMENT;
     *out = nullptr;
     rc_ctx* c = new rc_ctx();
+    int caller_device = -1;
+    cudaGetDevice(&caller_device);
     rc_status st = guard(c, [&] {
         int ndev = 0;
         RC_CUDA(cudaGetDeviceCount(&ndev));
@@ -829,6 +867,7 @@ rc_status rc_ctx_create(int device, rc_ctx** out) {
         uint64_t thresh = ~0ull;
         RC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     });
+    if (caller_device >= 0 && caller_device != device) cudaSetDevice(caller_device);   // leave the caller's device as it was
     if (st != RC_OK) { fprintf(stderr, "rc_ctx_create: %s\n", c->err.c_str()); delete c; return st; }
     *out = c;
     return RC_OK;
@@ -836,11 +875,13 @@ rc_status rc_ctx_create(int device, rc_ctx** out) {
 
 rc_status rc_ctx_destroy(rc_ctx* c) {
     if (!c) return RC_OK;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    try { comm_destroy(c); } catch (...) {}
-    if (c->tile_counter) cudaFree(c->tile_counter);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
+    {
+        DeviceGuard dg(c->device);
+        cudaStreamSynchronize(c->stream);
+        try { comm_destroy(c); } catch (...) {}
+        if (c->tile_counter) cudaFree(c->tile_counter);
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+    }
     delete c;
     return RC_OK;
 }
@@ -867,6 +908,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
         else if (!strcmp(key, "dmma_tail")) c->dmma_tail = (int)v;
         else if (!strcmp(key, "true_power_iteration")) c->true_power_iteration = (int)v;
         else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;
+        else if (!strcmp(key, "pivot_precision")) c->pivot_f64 = (v != 0);
         else if (!strcmp(key, "reuse_range_b")) c->reuse_range_b = (int)v;
         else if (!strcmp(key, "trace")) c->trace = (int)v;
         else RC_THROW(RC_INVALID_ARGUMENT, "unknown option '%s'", key);
@@ -996,6 +1038,10 @@ rc_status rc_matrix_copy(rc_ctx* c, const rc_matrix* src, rc_matrix* dst) {
         check_same(src, dst);
         RC_REQUIRE(src->rows == dst->rows && src->cols == dst->cols, "rc_matrix_copy: shapes differ");
         RC_DISPATCH(src->dtype, k_copy<T>(c, P<T>(dst), dst->ld, P<T>(src), src->ld, src->rows, src->cols));
+        // dst's contents changed: anything cached against its identity (the adaptive sampler's B = Q^H A kept for
+        // compute_from_range_estimate, see ah_range) must not be matched any more
+        dst->id = rc_next_matrix_id();
+        if (dst->companion) { mat_free(dst->companion); dst->companion = nullptr; dst->companion_op_id = 0; }
     });
 }
 rc_status rc_matrix_free(rc_matrix* m) { mat_free(m); return RC_OK; }
@@ -1197,6 +1243,20 @@ rc_status rc_qr_compute_from(rc_ctx* c, const rc_matrix* arr, rc_qr** out) {
         *out = qr_from_parts(p);
     });
 }
+// QR { q, r, ind } assembled by the caller (pub fields, src/qr.rs:31-40)
+rc_status rc_qr_new(rc_ctx* c, const rc_matrix* q, const rc_matrix* r, const uint64_t* ind, size_t n, rc_qr** out) {
+    if (!c || !q || !r || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        check_same(q, r);
+        RC_REQUIRE(q->cols == r->rows, "QR: q has %lld columns, r has %lld rows", (long long)q->cols, (long long)r->rows);
+        RC_REQUIRE((int64_t)n == r->cols, "QR: ind has length %zu, r has %lld columns", n, (long long)r->cols);
+        std::unique_ptr<rc_qr> h(new rc_qr());
+        h->ind = vec_from(ind, n);
+        for (uint64_t v : h->ind) RC_REQUIRE(v < n, "QR: ind entry %llu out of range", (unsigned long long)v);
+        RC_DISPATCH(q->dtype, { MatPtr a(mat_clone<T>(c, q)); MatPtr b(mat_clone<T>(c, r)); h->q = a.release(); h->r = b.release(); });
+        *out = h.release();
+    });
+}
 rc_status rc_qr_compute_from_range_estimate(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, rc_qr** out) {
     if (!c || !range || !op || !out) return RC_INVALID_ARGUMENT;
     return guard(c, [&] {
@@ -1298,6 +1358,20 @@ rc_status rc_lq_compute_from(rc_ctx* c, const rc_matrix* arr, rc_lq** out) {
         *out = h.release();
     });
 }
+// LQ { l, q, ind } assembled by the caller (pub fields, src/qr.rs:42-51)
+rc_status rc_lq_new(rc_ctx* c, const rc_matrix* l, const rc_matrix* q, const uint64_t* ind, size_t n, rc_lq** out) {
+    if (!c || !l || !q || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        check_same(l, q);
+        RC_REQUIRE(l->cols == q->rows, "LQ: l has %lld columns, q has %lld rows", (long long)l->cols, (long long)q->rows);
+        RC_REQUIRE((int64_t)n == l->rows, "LQ: ind has length %zu, l has %lld rows", n, (long long)l->rows);
+        std::unique_ptr<rc_lq> h(new rc_lq());
+        h->ind = vec_from(ind, n);
+        for (uint64_t v : h->ind) RC_REQUIRE(v < n, "LQ: ind entry %llu out of range", (unsigned long long)v);
+        RC_DISPATCH(l->dtype, { MatPtr a(mat_clone<T>(c, l)); MatPtr b(mat_clone<T>(c, q)); h->l = a.release(); h->q = b.release(); });
+        *out = h.release();
+    });
+}
 rc_status rc_lq_compress_rank(rc_ctx* c, const rc_lq* lq, int64_t max_rank, rc_lq** out) {
     if (!c || !lq || !out) return RC_INVALID_ARGUMENT;
     return guard(c, [&] {
@@ -1367,6 +1441,19 @@ rc_status rc_svd_compute_from(rc_ctx* c, const rc_matrix* arr, rc_svd** out) {
         SvdParts p;
         RC_DISPATCH(arr->dtype, svd_impl<T>(c, arr, false, p));
         *out = svd_from_parts(p);
+    });
+}
+// SVD { u, s, vt } assembled by the caller (pub fields, src/svd.rs:13-20)
+rc_status rc_svd_new(rc_ctx* c, const rc_matrix* u, const double* s, size_t ns, const rc_matrix* vt, rc_svd** out) {
+    if (!c || !u || !vt || !out || (!s && ns)) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        check_same(u, vt);
+        RC_REQUIRE(u->cols == (int64_t)ns && vt->rows == (int64_t)ns, "SVD: u is %lld x %lld, s has %zu entries, vt is %lld x %lld",
+                   (long long)u->rows, (long long)u->cols, ns, (long long)vt->rows, (long long)vt->cols);
+        std::unique_ptr<rc_svd> h(new rc_svd());
+        h->s.assign(s, s + ns);
+        RC_DISPATCH(u->dtype, { MatPtr a(mat_clone<T>(c, u)); MatPtr b(mat_clone<T>(c, vt)); h->u = a.release(); h->vt = b.release(); });
+        *out = h.release();
     });
 }
 rc_status rc_svd_compute_from_range_estimate(rc_ctx* c, const rc_matrix* range, const rc_matrix* op, rc_svd** out) {

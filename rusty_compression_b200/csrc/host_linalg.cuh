@@ -31,7 +31,10 @@ inline rc_matrix* mat_new(rc_ctx* c, int dtype, int64_t rows, int64_t cols) {
 }
 inline void mat_free(rc_matrix* m) {
     if (!m) return;
-    if (m->owns && m->data) cudaFreeAsync(m->data, m->ctx->stream);
+    if (m->owns && m->data) {
+        DeviceGuard dg(m->ctx->device);      // the *_free entry points are not routed through guard()
+        cudaFreeAsync(m->data, m->ctx->stream);
+    }
     if (m->companion) mat_free(m->companion);
     delete m;
 }

@@ -43,6 +43,18 @@ __global__ void strided_kernel(T* dst, int64_t ldd, const T* src, int64_t rs, in
     }
 }
 
+// precision change of a rows x cols block (f32 <-> f64, c32 <-> c64): pivot decisions on single-precision inputs
+// are taken in double (DESIGN.md "pivot parity")
+template <class D, class S>
+__global__ void cast_kernel(D* dst, int64_t ldd, const S* src, int64_t lds, int64_t rows, int64_t cols) {
+    int64_t n = rows * cols;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = e / cols, j = e - i * cols;
+        const S v = src[i * lds + j];
+        dst[i * ldd + j] = rc_make<D>((double)rc_real(v), (double)rc_imag(v));
+    }
+}
+
 // 32x32 smem-tiled transpose (coalesced both ways), optional conjugation.
 template <class T>
 __global__ void transpose_kernel(T* dst, int64_t ldd, const T* src, int64_t lds, int64_t rows, int64_t cols, bool conj) {
@@ -351,6 +363,16 @@ template <class T> void k_convert_real(rc_ctx* c, RealOf<T>* dst, const double* 
     convert_real_kernel<RealOf<T>><<<nblocks_for(n), TB, 0, c->stream>>>(dst, src, n);
     RC_CHECK_LAUNCH(c);
 }
+
+template <class D, class S> void k_cast(rc_ctx* c, D* dst, int64_t ldd, const S* src, int64_t lds, int64_t rows, int64_t cols) {
+    if (rows * cols == 0) return;
+    cast_kernel<D, S><<<nblocks_for(rows * cols), TB, 0, c->stream>>>(dst, ldd, src, lds, rows, cols);
+    RC_CHECK_LAUNCH(c);
+}
+template void k_cast<double, float>(rc_ctx*, double*, int64_t, const float*, int64_t, int64_t, int64_t);
+template void k_cast<float, double>(rc_ctx*, float*, int64_t, const double*, int64_t, int64_t, int64_t);
+template void k_cast<c64, c32>(rc_ctx*, c64*, int64_t, const c32*, int64_t, int64_t, int64_t);
+template void k_cast<c32, c64>(rc_ctx*, c32*, int64_t, const c64*, int64_t, int64_t, int64_t);
 
 #define INST(T)                                                                                          \
     template void k_fill<T>(rc_ctx*, T*, int64_t, int64_t, int64_t, T);                                   \

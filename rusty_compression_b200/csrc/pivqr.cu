@@ -494,8 +494,8 @@ __global__ void form_q_kernel(const T* __restrict__ vbuf, const T* __restrict__ 
 }  // namespace
 
 template <class T>
-void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int64_t ldr, int* ind,
-                  T* vbuf, T* tau) {
+static void pivqr_factor_native(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int64_t ldr, int* ind,
+                                T* vbuf, T* tau) {
     int kk = (int)std::min(p, n);
     RC_REQUIRE(p > 0 && n > 0, "pivoted_qr: empty matrix");
     size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
@@ -556,6 +556,30 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
     int nb = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
     gather_r_kernel<T><<<nb, 256, 0, c->stream>>>(wc, ldw, kk, ni, ind, diag.p, r, ldr);
     RC_CHECK_LAUNCH(c);
+}
+
+// Single-precision inputs are factored in double (option "pivot_precision" = 1, the default): the f32 / c32 data is
+// widened exactly, every pivot decision -- trailing updates included -- is taken with double-precision arithmetic,
+// and R, the reflectors and tau are rounded back once at the end.  The pivot sequence is then the one ?geqp3 picks
+// in double precision on the same single-precision input (sgeqp3's own downdated norms are only good to
+// ~sqrt(eps_f32), so "bit-exact wherever the gap exceeds 1e-6" is only attainable against that sequence).
+template <class T>
+void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int64_t ldr, int* ind,
+                  T* vbuf, T* tau) {
+    using W = typename AccOf<T>::type;
+    if constexpr (!std::is_same<T, W>::value) {
+        if (c->pivot_f64) {
+            const int64_t kk = std::min(p, n);
+            DevBuf<W> wc2(c, (size_t)p * n), r2(c, (size_t)kk * n), v2(c, (size_t)p * kk), tau2(c, (size_t)kk);
+            k_cast<W, T>(c, wc2.p, p, wc, ldw, n, p);                  // column-major: n columns of p entries
+            pivqr_factor_native<W>(c, wc2.p, p, p, n, r2.p, n, ind, v2.p, tau2.p);
+            k_cast<T, W>(c, r, ldr, r2.p, n, kk, n);
+            k_cast<T, W>(c, vbuf, p, v2.p, p, kk, p);
+            k_cast<T, W>(c, tau, kk, tau2.p, kk, 1, kk);
+            return;
+        }
+    }
+    pivqr_factor_native<T>(c, wc, ldw, p, n, r, ldr, ind, vbuf, tau);
 }
 
 template <class T>

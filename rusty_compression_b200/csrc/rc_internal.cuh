@@ -51,6 +51,7 @@ struct rc_ctx {
     int trace = 0;                // option "trace": print wall time between rc_trace() marks (stream-synchronising)
     double trace_t0 = 0.0;
     int reuse_range_b = 1;        // reuse B = Q^H A of the adaptive sampler in compute_from_range_estimate
+    int pivot_f64 = 1;            // 1: pivot decisions on f32 / c32 inputs are taken in double (pivqr.cu, pivoted_qr_impl)
     int qr_mode = 0;              // 0 auto (Cholesky-QR2 fast path with Householder-TSQR fallback), 1 TSQR only
     int64_t cholqr_used = 0, cholqr_fallbacks = 0, range_b_reused = 0;
     // counters
@@ -80,6 +81,20 @@ struct rc_matrix {
     int (*op_matmat)(void*, const void*, int64_t, int64_t, void*, int64_t, void*) = nullptr;
     int (*op_conj_matmat)(void*, const void*, int64_t, int64_t, void*, int64_t, void*) = nullptr;
     void* op_user = nullptr;
+};
+
+// Every entry point runs with the context's device current and restores the caller's device on exit: a host
+// process with several contexts (one per GPU) or a framework that switches devices between calls (torch) must
+// not see kernels, stream operations or cudaFuncSetAttribute land on the wrong device.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = (cudaSetDevice(device) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
 inline size_t rc_dtype_size(int dt) {
@@ -149,6 +164,8 @@ template <class T> void k_col_norms2(rc_ctx*, const T* a, int64_t lda, int64_t r
 // sum of |a_ij|^2 ; and sum of |a_ij - b_ij|^2 (double, device scalars)
 template <class T> void k_fro2(rc_ctx*, const T* a, int64_t lda, int64_t rows, int64_t cols, double* out);
 template <class T> void k_diff_fro2(rc_ctx*, const T* a, int64_t lda, const T* b, int64_t ldb, int64_t rows, int64_t cols, double* out);
+// dst = (D) src, elementwise (f32 <-> f64, c32 <-> c64)
+template <class D, class S> void k_cast(rc_ctx*, D* dst, int64_t ldd, const S* src, int64_t lds, int64_t rows, int64_t cols);
 // complex real-expansion helpers for the DMMA path (c64 only)
 void k_expand_rhs_c64(rc_ctx*, double* dst, int64_t ldd, const c64* x, int64_t ldx, int64_t rows, int64_t cols);
 // real <-> T conversions of device vectors (singular values)

@@ -30,6 +30,9 @@ static Matrix<A> eye(const Context& ctx, size_t n) {
 }
 
 template <class A>
+static Matrix<A> x_for_apply(const Context& ctx, size_t cols, A) { return Matrix<A>::random_gaussian(ctx, cols, 3, 5); }
+
+template <class A>
 static void factorization_tests(const Context& ctx, const char* name, double tol, size_t rows, size_t cols) {
     const std::string tag = std::string(name) + " " + std::to_string(rows) + "x" + std::to_string(cols) + ": ";
     auto mat = Matrix<A>::random_approximate_low_rank_matrix(ctx, rows, cols, 1.0, 1e-10, 17 + rows);
@@ -71,6 +74,11 @@ static void factorization_tests(const Context& ctx, const char* name, double tol
            tag + "compress_svd_tolerance error");
     expect(rel_diff_fro(svd.to_qr().to_mat(), mat) < tol * 10, tag + "svd.to_qr reconstruction");
 
+    // containers assembled from parts (pub fields of QR / LQ / SVD: src/qr.rs:31-51, src/svd.rs:13-20) behave like the originals
+    expect(rel_diff_fro(QR<A>::make(qr.get_q(), qr.get_r(), qr.get_ind()).to_mat(), mat) < tol, tag + "QR{q,r,ind} from parts");
+    expect(rel_diff_fro(LQ<A>::make(lq.get_l(), lq.get_q(), lq.get_ind()).to_mat(), mat) < tol, tag + "LQ{l,q,ind} from parts");
+    expect(rel_diff_fro(SVD<A>::make(svd.get_u(), svd.get_s(), svd.get_vt()).to_mat(), mat) < tol, tag + "SVD{u,s,vt} from parts");
+    expect(rel_diff_fro(rid.dot(x_for_apply(ctx, cols, A(0))), rid.to_mat().matmat(x_for_apply(ctx, cols, A(0)))) < tol * 100, tag + "RowID::dot");
     // Apply: ID * matrix equals to_mat * matrix
     auto x = Matrix<A>::random_gaussian(ctx, cols, 3, 5);
     expect(rel_diff_fro(cid.dot(x), cid.to_mat().matmat(x)) < tol * 100, tag + "ColumnID::dot");
@@ -91,8 +99,11 @@ static void permutation_known_answers(const Context& ctx) {               // src
     auto rowinv = apply_permutation(apply_permutation(mat, perm, MatrixPermutationMode::ROW), perm, MatrixPermutationMode::ROWINV).to_host();
     expect(rowinv == m, "ROWINV undoes ROW");
     bool threw = false;
-    try { invert_permutation_vector({0, 0, 1}); } catch (const InvalidArgument&) { threw = true; }
-    expect(threw, "invert_permutation_vector rejects a non-permutation");
+    // the crate indexes `inverse[elem]` unchecked against duplicates (src/permutation.rs:33-35): only an out-of-range
+    // entry panics there, which the ABI reports as RC_INVALID_ARGUMENT
+    try { invert_permutation_vector({0, 3, 1}); } catch (const InvalidArgument&) { threw = true; }
+    expect(threw, "invert_permutation_vector rejects an out-of-range entry");
+    expect(invert_permutation_vector({0, 0, 1}).size() == 3, "invert_permutation_vector accepts duplicates like the crate");
 }
 
 int main() {

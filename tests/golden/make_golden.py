@@ -70,6 +70,16 @@ def build_case(dtype):
     ts2 = rid.two_sided_id()
     out["ts2_col_ind"] = np.asarray(ts2.col_ind, dtype=np.int64)
     out["ts2_error"] = np.float64(ref.rel_diff_fro(ts2.to_mat(), a))
+    # --- next to every ?geqp3 sequence in the working precision (what the reference itself produces), the
+    #     sequence ?geqp3 picks in DOUBLE precision on the same input (`<key>_f64`: identical for f64 / c64) and the
+    #     signed per-step gaps of that sequence (`<key>_gaps`).  The CUDA path is held to the `_f64` sequence wherever
+    #     the gap exceeds 1e-6.
+    b = ref.conj_t(ref.DenseOperator(a).conj_matmat(q0))
+    for key, mat, upto in (("pqr_ind", a, None), ("plq_ind", ref.conj_t(a), None), ("sketch_ind", y, None),
+                           ("range_qr_ind", b, K), ("ts_row_ind", ref.conj_t(cid.c), K), ("ts2_col_ind", rid.r, K)):
+        seq = ref.pivot_sequence_f64(mat)
+        out[key + "_f64"] = np.asarray(seq, dtype=np.int64)
+        out[key + "_gaps"] = ref.pivot_gaps(mat, seq, upto=upto)
     # --- tolerance compression (src/qr.rs:187-200, src/svd.rs:87-101)
     tol = 1e-3
     out["qr_tol_rank"] = np.int64(qr.compress(ref.ADAPTIVE(tol)).rank())

@@ -84,24 +84,38 @@ def main():
             assert abs(ra - ra_ref) <= max(tol, 1e-8) * ra_ref + (5e-7 if tol > 1e-6 else 0.0), (dtype, ra, ra_ref)
             print(f"[multi-gpu x{world}] {np.dtype(dtype).name}: sv err {err_s:.2e}, rec {rec:.3e} (ref {rec_ref:.3e}), "
                   f"id err {e:.3e} (ref {e_ref:.3e}), adaptive rank {hist[-1][0]}", flush=True)
-    # --- config-4 shape at reduced m: row-sharded tall-skinny range finder, f32, rank 256 (+10): the sketch
-    #     (l = 266) is wider than one TSQR panel, so it goes through the panel path with all-reduced projections
-    from oracle.inputs import tall_shard_matrix
-    m, n, k, p = 16384, 1024, 256, 10
+    # --- config-4 shape: row-sharded tall-skinny range finder, f32, rank 256 (+10), n = 8192 (the sketch, l = 266, is wider
+    #     than one TSQR panel: panel path with all-reduced projections).  m = 2^19 by default (16 GiB of A, the size SURVEY
+    #     8(d) prescribes for the CPU side of config 4); RC_TEST_CONFIG4_ROWS overrides it.
+    m, n, k, p = int(os.environ.get("RC_TEST_CONFIG4_ROWS", 1 << 19)), 8192, 256, 10
     rows = m // world
-    a_loc = tall_shard_matrix(rank * rows, rows, n, np.float32, seed=9, m_total=m, r0=512, decade_every=64.0)
-    op = api.DeviceMatrix.from_numpy(a_loc, ctx=ctx).set_shard(m, rank * rows)
+    op = api.tall_shard_matrix(rank * rows, rows, n, np.float32, seed=9, m_total=m, r0=512, decade_every=64.0, ctx=ctx)
+    op.set_shard(m, rank * rows)
     q = api.sample_range_by_rank(op, k, p, seed=42, ctx=ctx, device=True)      # Omega regenerated from the shared Philox seed
     q_full = gather_rows(q.to_numpy())
-    a_full = gather_rows(a_loc)
+    a_full = gather_rows(op.to_numpy())
     if rank == 0:
         omega = random_gaussian((n, k + p), np.float32, seed=42)
         q_ref = ref.sample_range_by_rank(a_full, k, p, ref.OmegaStream(np.float32, blocks=[omega]))
+        # the reference path once more with the sketch formed in double and rounded once (an equally valid f32
+        # evaluation of Y = A Omega): how far the reference's OWN result moves under f32 roundoff of the sketch --
+        # the deep pivots of the 266-column sketch (trailing norms down to 7e-5 of the first) decide which 10 of the
+        # 266 directions are dropped, and they sit at eps_f32 * 1.4e4 relative.  This is the roundoff floor of the
+        # comparison; it is printed and the device is held to max(1e-4, 3 x floor).
+        y64 = np.zeros((m, k + p), dtype=np.float32)
+        for r0 in range(0, m, 1 << 16):
+            y64[r0:r0 + (1 << 16)] = a_full[r0:r0 + (1 << 16)].astype(np.float64).dot(omega.astype(np.float64)).astype(np.float32)
+        q_alt = ref.QR.compute_from(y64).compress(ref.RANK(k)).q
+        cols = np.arange(0, n, 8)                     # same checker, same column sample on every side (f64)
+        sub = np.ascontiguousarray(a_full[:, cols])
+        r, r_ref, r_alt = (ref.range_residual(sub, x) for x in (q_full, q_ref, q_alt))
+        floor = abs(r_alt - r_ref) / r_ref
         orth = np.max(np.abs(q_full.T.astype(np.float64).dot(q_full.astype(np.float64)) - np.eye(k)))
-        r, r_ref = ref.range_residual(a_full, q_full), ref.range_residual(a_full, q_ref)
-        print(f"[multi-gpu x{world}] config-4 shape f32 {m}x{n}, rank {k}: |Q^T Q - I| {orth:.2e}, residual {r:.4e} (oracle {r_ref:.4e})", flush=True)
+        print(f"[multi-gpu x{world}] config-4 shape f32 {m}x{n}, rank {k}: |Q^T Q - I| {orth:.2e}, residual {r:.6e} "
+              f"(oracle {r_ref:.6e}, oracle with the sketch rounded once from double {r_alt:.6e}: roundoff floor {floor:.2e}); "
+              f"deviation {abs(r - r_ref) / r_ref:.2e}", flush=True)
         assert orth < 5e-5
-        assert abs(r - r_ref) <= 2e-2 * r_ref + 1e-6, (r, r_ref)
+        assert abs(r - r_ref) <= max(1e-4, 3.0 * floor) * r_ref, (r, r_ref, floor)
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_OK", flush=True)

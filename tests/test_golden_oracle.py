@@ -19,7 +19,7 @@ def test_oracle_reproduces_golden_case(name):
         stream = ref.OmegaStream(a.dtype, blocks=[blocks[:, i * s:(i + 1) * s] for i in range(nb)])
         return ref.sample_range_adaptive(a, tol, s, stream)
 
-    gc.run_case(ref, name, g, make_stream, adaptive)
+    gc.run_case(ref, name, g, make_stream, adaptive, oracle_side=True)
 
 
 def test_oracle_config2_toy():

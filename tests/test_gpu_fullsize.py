@@ -48,3 +48,125 @@ def test_config2_full_size_parity_and_properties():
     print(f"config 2 full size: max rel singular-value error {err_s:.2e}; residual {res_dev:.12e} vs {res_ref:.12e}")
     assert err_s < 1e-10
     assert abs(res_dev - res_ref) <= 1e-10 * res_ref
+
+
+def blocked_rel_err(a, approx_rows, block=2048):
+    """|| A - approx ||_F / || A ||_F in double precision, row block by row block (the full-size matrices are 4 GiB:
+    the checker never holds a widened copy of A).  approx_rows(r0, r1) returns rows [r0, r1) of the approximation."""
+    wide = np.complex128 if np.iscomplexobj(a) else np.float64
+    num = den = 0.0
+    for r0 in range(0, a.shape[0], block):
+        r1 = min(a.shape[0], r0 + block)
+        blk = a[r0:r1].astype(wide)
+        num += np.linalg.norm(blk - approx_rows(r0, r1).astype(wide)) ** 2
+        den += np.linalg.norm(blk) ** 2
+    return float(np.sqrt(num / den))
+
+
+def blocked_range_residual(a, q, block=2048):
+    """|| A - Q Q^H A ||_F / || A ||_F (oracle.reference_path.range_residual) without widened copies of A."""
+    wide = np.complex128 if np.iscomplexobj(a) else np.float64
+    q = q.astype(wide)
+    qha = np.zeros((q.shape[1], a.shape[1]), dtype=wide)
+    for r0 in range(0, a.shape[0], block):
+        r1 = min(a.shape[0], r0 + block)
+        qha += np.conj(q[r0:r1].T).dot(a[r0:r1].astype(wide))
+    return blocked_rel_err(a, lambda r0, r1: q[r0:r1].dot(qha), block)
+
+
+@pytest.mark.timeout(1800)
+def test_config3_full_size_parity():
+    """configs[2]: column ID via pivoted QR on the sketch, f32, 32768 x 32768, rank to tol 1e-4, sample_size 64:
+    sample_range_adaptive(1e-4, 64) -> QR::compute_from_range_estimate -> compress(ADAPTIVE(1e-4)) -> column_id()
+    (src/random_sampling.rs:223-274, src/qr.rs:311-323, 187-200, 270-309) against the oracle on the same A and the
+    same stream of Omega blocks: rank history exact, skeleton columns = the double-precision ?geqp3 choice on the
+    device's own factor b wherever the gap exceeds 1e-6, range residual and ID error within 1e-4 relative."""
+    from golden_common import adjudicate
+    from rusty_compression_b200 import api
+    n, s, tol = 32768, 64, 1e-4
+    ctx = api.default_context()
+    a_dev = api.decaying_spectrum_matrix((n, n), np.float32, 1235, r0=1024, decade_every=64.0)
+    ctx.reset_counters()
+    q_dev, hist_dev = api.sample_range_adaptive(a_dev, tol, s, seed=42, device=True)
+    qr_dev = api.QR.compute_from_range_estimate(q_dev, a_dev)
+    assert ctx.counter("range_b_reused") == 1          # B = Q^H A of the sampler is reused (one pass over A saved)
+    qrc_dev = qr_dev.compress(api.ADAPTIVE(tol))
+    cid_dev = qrc_dev.column_id()
+    assert ctx.counter("kernel_launches") > 100
+    k_dev = qrc_dev.rank()
+    b_dev = ref.conj_t(a_dev.conj_matmat(q_dev).to_numpy())        # the factor the device pivoted, from its own product
+    a = a_dev.to_numpy()
+    q = q_dev.to_numpy()
+    # --- the oracle on the same A and the same Philox stream of Omega blocks
+    q_ref, hist_ref = ref.sample_range_adaptive(a, tol, s, ref.OmegaStream(np.float32, seed=42))
+    assert [r for r, _ in hist_dev] == [r for r, _ in hist_ref], (hist_dev, hist_ref)
+    for (_, e_dev), (_, e_ref) in zip(hist_dev, hist_ref):
+        # the estimates are f32 differences of O(1) quantities: a value of size rho carries eps_f32 / rho relative roundoff
+        assert abs(e_dev - e_ref) <= 1e-4 * e_ref + 3e-7, (hist_dev, hist_ref)
+    res_dev, res_ref = blocked_range_residual(a, q), blocked_range_residual(a, q_ref)
+    qr_ref = ref.QR.compute_from_range_estimate(q_ref, a)
+    order = adjudicate(b_dev, qr_dev.ind, qr_ref.ind, upto=k_dev, label="config 3 col_ind")
+    if order is not None:
+        qr_ref = ref.QR.compute_from_range_estimate(q_ref, a, order=order)
+    qrc_ref = qr_ref.compress(ref.ADAPTIVE(tol))
+    assert k_dev == qrc_ref.rank(), (k_dev, qrc_ref.rank())
+    cid_ref = qrc_ref.column_id()
+    c_d, z_d = cid_dev.c, cid_dev.z
+    err_dev = blocked_rel_err(a, lambda r0, r1: c_d[r0:r1].astype(np.float64).dot(z_d.astype(np.float64)))
+    err_ref = blocked_rel_err(a, lambda r0, r1: cid_ref.c[r0:r1].astype(np.float64).dot(cid_ref.z.astype(np.float64)))
+    print(f"config 3 full size: rank history {[r for r, _ in hist_dev]}, rank {k_dev}; range residual {res_dev:.8e} vs "
+          f"{res_ref:.8e}; column-ID error {err_dev:.8e} vs {err_ref:.8e}")
+    assert abs(res_dev - res_ref) <= 1e-4 * res_ref, (res_dev, res_ref)
+    assert abs(err_dev - err_ref) <= 1e-4 * err_ref, (err_dev, err_ref)
+    # size-independent properties
+    assert np.max(np.abs(q.T.astype(np.float64).dot(q.astype(np.float64)) - np.eye(q.shape[1]))) < 2e-5
+    assert sorted(cid_dev.col_ind.tolist()) == list(range(n))
+    sk = cid_dev.col_ind[:k_dev]
+    assert np.max(np.abs(z_d[:, sk] - np.eye(k_dev))) < 1e-5          # Z restricted to the skeleton columns is I
+    assert np.linalg.norm(c_d - a[:, sk]) <= 10 * tol * np.linalg.norm(a[:, sk])   # C ~ A[:, skeleton] (src/col_interp_decomp.rs:221-222)
+
+
+@pytest.mark.timeout(1800)
+def test_config5_full_size_parity():
+    """configs[4]: two-sided ID, c64, 16384 x 16384 low-rank kernel matrix, rank 128 (+10): sample_range_by_rank ->
+    QR::compute_from_range_estimate -> compress(RANK(128)) -> column_id -> two_sided_id (src/col_interp_decomp.rs:116-125):
+    skeleton rows and columns exact, both ID errors within 1e-10 relative of the oracle's on the same A and Omega."""
+    from golden_common import adjudicate
+    from oracle.philox import random_gaussian as philox_gaussian
+    from rusty_compression_b200 import api
+    n, k, p = 16384, 128, 10
+    a_dev = api.helmholtz_kernel_matrix((n, n), np.complex128)
+    omega = philox_gaussian((n, k + p), np.complex128, seed=42)
+    q_dev = api.sample_range_by_rank(a_dev, k, p, omega=omega, device=True)
+    qr_dev = api.QR.compute_from_range_estimate(q_dev, a_dev).compress(api.RANK(k))
+    cid_dev = qr_dev.column_id()
+    ts_dev = cid_dev.two_sided_id()
+    b_dev = ref.conj_t(a_dev.conj_matmat(q_dev).to_numpy())
+    a = a_dev.to_numpy()
+    q_ref = ref.sample_range_by_rank(a, k, p, ref.OmegaStream(np.complex128, blocks=[omega]))
+    res_dev, res_ref = blocked_range_residual(a, q_dev.to_numpy()), blocked_range_residual(a, q_ref)
+    assert abs(res_dev - res_ref) <= 1e-10 * res_ref, (res_dev, res_ref)
+    qr_ref = ref.QR.compute_from_range_estimate(q_ref, a)
+    order = adjudicate(b_dev, qr_dev.ind, qr_ref.ind, upto=k, label="config 5 col_ind")
+    if order is not None:
+        qr_ref = ref.QR.compute_from_range_estimate(q_ref, a, order=order)
+    cid_ref = qr_ref.compress(ref.RANK(k)).column_id()
+    assert np.array_equal(cid_dev.col_ind[:k], cid_ref.col_ind[:k])
+    c_d, z_d = cid_dev.c, cid_dev.z
+    e_dev = blocked_rel_err(a, lambda r0, r1: c_d[r0:r1].dot(z_d))
+    e_ref = blocked_rel_err(a, lambda r0, r1: cid_ref.c[r0:r1].dot(cid_ref.z))
+    ts_ref = cid_ref.two_sided_id()
+    order2 = adjudicate(ref.conj_t(c_d), ts_dev.row_ind, ts_ref.row_ind, upto=k, label="config 5 row_ind")
+    if order2 is not None:
+        ts_ref = cid_ref.two_sided_id(order=order2)
+    assert np.array_equal(ts_dev.row_ind[:k], ts_ref.row_ind[:k])
+    xr_d, xr_r = ts_dev.x.dot(ts_dev.r), ts_ref.x.dot(ts_ref.r)
+    tc_d = ts_dev.c
+    t_dev = blocked_rel_err(a, lambda r0, r1: tc_d[r0:r1].dot(xr_d))
+    t_ref = blocked_rel_err(a, lambda r0, r1: ts_ref.c[r0:r1].dot(xr_r))
+    print(f"config 5 full size: column-ID error {e_dev:.12e} vs {e_ref:.12e}; two-sided {t_dev:.12e} vs {t_ref:.12e}")
+    assert abs(e_dev - e_ref) <= 1e-10 * e_ref, (e_dev, e_ref)
+    assert abs(t_dev - t_ref) <= 1e-10 * t_ref, (t_dev, t_ref)
+    # skeleton property: X ~ A[row skeleton, column skeleton] (what the crate's tests check at 10 tol)
+    sk = a[np.ix_(ts_dev.row_ind[:k], ts_dev.col_ind[:k])]
+    assert ref.rel_diff_fro(ts_dev.x, sk) < 1e-3

@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+from golden_common import adjudicate
 from oracle import reference_path as ref
 from oracle.philox import random_gaussian as oracle_gaussian
 
@@ -214,12 +215,12 @@ def test_tall_pivoted_qr_matches_lapack(api, dtype, shape, qr_mode):
     k = min(shape)
     assert np.max(np.abs(np.conj(q.T).dot(q) - np.eye(k))) < (1e-5 if tol > 1e-6 else 1e-13)
     assert relerr(q.dot(r), a[:, ind]) < (1e-5 if tol > 1e-6 else 1e-13)
-    gaps = ref.pivot_gaps(a, ind0)
-    first_bad = next((j for j in range(k) if ind[j] != ind0[j]), None)
-    if first_bad is not None:
-        assert gaps[first_bad] <= (1e-3 if tol > 1e-6 else 1e-6), (first_bad, gaps[first_bad])
-    else:
-        assert np.max(np.abs(np.abs(np.diagonal(r)) - np.abs(np.diagonal(r0))) / np.abs(r0[0, 0])) < tol
+    # pivots: the double-precision ?geqp3 sequence wherever the gap exceeds 1e-6 (all four scalars); on a tie the
+    # oracle is replayed in the device's order, nothing is skipped
+    order = adjudicate(a, ind, ind0, label=f"tall {shape} {np.dtype(dtype).name}")
+    if order is not None:
+        q0, r0, ind0 = ref.pivoted_qr_with_order(a, order)
+    assert np.max(np.abs(np.abs(np.diagonal(r)) - np.abs(np.diagonal(r0))) / np.abs(r0[0, 0])) < tol
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -234,10 +235,10 @@ def test_wide_pivoted_qr_matches_lapack(api, dtype, shape):
     assert sorted(ind.tolist()) == list(range(shape[1]))
     assert np.max(np.abs(np.conj(q.T).dot(q) - np.eye(k))) < (1e-5 if single else 1e-13)
     assert relerr(q.dot(r), a[:, ind]) < (1e-5 if single else 1e-13)
-    gaps = ref.pivot_gaps(a, ind0)
-    first_bad = next((j for j in range(k) if ind[j] != ind0[j]), None)
-    if first_bad is not None:
-        assert gaps[first_bad] <= (1e-3 if single else 1e-6), (first_bad, gaps[first_bad])
+    order = adjudicate(a, ind, ind0, label=f"wide {shape} {np.dtype(dtype).name}")
+    if order is not None:
+        q0, r0, ind0 = ref.pivoted_qr_with_order(a, order)
+    assert np.max(np.abs(np.abs(np.diagonal(r)) - np.abs(np.diagonal(r0))) / np.abs(r0[0, 0])) < (2e-4 if single else 1e-9)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

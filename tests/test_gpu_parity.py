@@ -1,9 +1,13 @@
 """Parity of the full pipelines against the oracle on the same A and the same Omega
-(north_star): pivots / skeleton indices bit-exact wherever the pivot gap exceeds 1e-6, singular
-values, range residual and ID error within 1e-10 relative (f64/c64) and 1e-4 (f32/c32)."""
+(north_star): pivots / skeleton indices bit-exact wherever the pivot gap exceeds 1e-6 -- for all four scalar
+types: the device takes its pivot decisions in double, so f32 / c32 are held to the sequence ?geqp3 picks in
+double precision on the same single-precision data -- singular values, range residual and ID
+error within 1e-10 relative (f64/c64) and 1e-4 (f32/c32).  A pivot tie never skips anything: the oracle is
+replayed in the device's validated order (golden_common.adjudicate)."""
 import numpy as np
 import pytest
 
+from golden_common import adjudicate
 from oracle import reference_path as ref
 from oracle.inputs import decaying_spectrum_matrix, helmholtz_kernel_matrix
 from oracle.philox import random_gaussian
@@ -19,14 +23,6 @@ def api():
     return a
 
 
-def check_indices(a_for_gaps, got, want, min_gap):
-    got, want = np.asarray(got), np.asarray(want)
-    if np.array_equal(got, want):
-        return
-    j = int(np.nonzero(got != want)[0][0])
-    gaps = ref.pivot_gaps(a_for_gaps, want)
-    assert j < len(gaps) and gaps[j] <= min_gap, f"pivot mismatch at step {j} with gap {gaps[j]:.3e}"
-    pytest.skip(f"pivot tie at step {j} (gap {gaps[j]:.2e} <= {min_gap}): later quantities not comparable")
 
 
 @pytest.fixture(params=[0, 1], ids=["cholqr2-auto", "householder-tsqr"])
@@ -61,7 +57,7 @@ def test_rsvd_parity(api, dtype, it_count, qr_mode):
     assert abs(rec_dev - rec_ref) <= tol * rec_ref + (1e-6 if tol > 1e-6 else 0)
 
 
-@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32, np.complex64])
 def test_column_and_two_sided_id_parity(api, dtype):
     """Config-5 pipeline at oracle scale: sample_range_by_rank -> QR::compute_from_range_estimate ->
     compress(RANK) -> column_id -> two_sided_id (src/qr.rs:270-323, src/col_interp_decomp.rs:116-125)."""
@@ -69,22 +65,29 @@ def test_column_and_two_sided_id_parity(api, dtype):
     k, p = 48, 10
     a = helmholtz_kernel_matrix(m, n, dtype)
     omega = random_gaussian((n, k + p), dtype, seed=42)
-    q_ref = ref.sample_range_by_rank(a, k, p, ref.OmegaStream(dtype, blocks=[omega]))
-    qr_ref = ref.QR.compute_from_range_estimate(q_ref, a).compress(ref.RANK(k))
-    cid_ref = qr_ref.column_id()
-    ts_ref = cid_ref.two_sided_id()
+    tol = RTOL[dtype]
     op = api.DeviceMatrix.from_numpy(a)
     q_dev = api.sample_range_by_rank(op, k, p, omega=omega)
     qr_dev = api.QR.compute_from_range_estimate(q_dev, op).compress(api.RANK(k))
     cid_dev = qr_dev.column_id()
     ts_dev = cid_dev.two_sided_id()
-    tol = RTOL[dtype]
-    gap = 1e-6 if tol < 1e-6 else 1e-3
-    b_ref = ref.conj_t(ref.DenseOperator(a).conj_matmat(q_ref))
-    check_indices(b_ref, cid_dev.col_ind[:k], cid_ref.col_ind[:k], gap)
+    q_ref = ref.sample_range_by_rank(a, k, p, ref.OmegaStream(dtype, blocks=[omega]))
+    res_ref, res_dev = ref.range_residual(a, q_ref), ref.range_residual(a, q_dev)
+    assert abs(res_dev - res_ref) <= tol * res_ref, (res_dev, res_ref)
+    # the factor the device pivoted is b = (A^H Q_dev)^H from its own product; its skeleton columns must be the
+    # double-precision ?geqp3 choice on that b wherever the gap exceeds 1e-6
+    b_dev = ref.conj_t(op.conj_matmat(q_dev).to_numpy())
+    qr_ref = ref.QR.compute_from_range_estimate(q_ref, a)
+    order = adjudicate(b_dev, cid_dev.col_ind, qr_ref.ind, upto=k, label=f"{np.dtype(dtype).name} col_ind")
+    if order is not None:
+        qr_ref = ref.QR.compute_from_range_estimate(q_ref, a, order=order)
+    cid_ref = qr_ref.compress(ref.RANK(k)).column_id()
     err_ref, err_dev = ref.rel_diff_fro(cid_ref.to_mat(), a), ref.rel_diff_fro(cid_dev.to_mat(), a)
     assert abs(err_dev - err_ref) <= tol * err_ref, (err_dev, err_ref)
-    check_indices(ref.conj_t(cid_ref.c), ts_dev.row_ind[:k], ts_ref.row_ind[:k], gap)
+    ts_ref = cid_ref.two_sided_id()
+    order2 = adjudicate(ref.conj_t(cid_dev.c), ts_dev.row_ind, ts_ref.row_ind, upto=k, label=f"{np.dtype(dtype).name} row_ind")
+    if order2 is not None:
+        ts_ref = cid_ref.two_sided_id(order=order2)
     e2_ref, e2_dev = ref.rel_diff_fro(ts_ref.to_mat(), a), ref.rel_diff_fro(ts_dev.to_mat(), a)
     assert abs(e2_dev - e2_ref) <= 10 * tol * e2_ref, (e2_dev, e2_ref)
     # skeleton property: X[i, j] ~ A[row_ind[i], col_ind[j]]
@@ -94,6 +97,69 @@ def test_column_and_two_sided_id_parity(api, dtype):
     x = random_gaussian((n, 3), dtype, seed=9)
     assert ref.rel_diff_fro(cid_dev.dot(x), cid_ref.to_mat().dot(x)) < (1e-3 if tol > 1e-6 else 1e-9)
     assert ref.rel_diff_fro(ts_dev.dot(x[:, 0]), ts_ref.to_mat().dot(x[:, 0])) < (1e-3 if tol > 1e-6 else 1e-8)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32, np.complex64])
+def test_row_id_route_and_apply_parity(api, dtype):
+    """The row route: LQ::compute_from -> compress(RANK) -> row_id -> two_sided_id, and Apply for RowID
+    (src/qr.rs:354-403, src/row_interp_decomp.rs:120-154): row skeleton, both errors, `dot` on a matrix and a vector."""
+    m, n, k = 700, 500, 40
+    a = helmholtz_kernel_matrix(m, n, dtype)
+    tol = RTOL[dtype]
+    name = np.dtype(dtype).name
+    lq_dev, lq_ref = api.LQ.compute_from(a), ref.LQ.compute_from(a)
+    order = adjudicate(ref.conj_t(a), lq_dev.ind, lq_ref.ind, upto=k, label=f"{name} LQ ind")
+    if order is not None:
+        lq_ref = ref.LQ.compute_from(a, order=order)
+    rid_dev, rid_ref = lq_dev.compress(api.RANK(k)).row_id(), lq_ref.compress(ref.RANK(k)).row_id()
+    assert rid_dev.x.shape == (m, k) and rid_dev.r.shape == (k, n) and len(rid_dev.row_ind) == m
+    e_ref, e_dev = ref.rel_diff_fro(rid_ref.to_mat(), a), ref.rel_diff_fro(rid_dev.to_mat(), a)
+    assert abs(e_dev - e_ref) <= tol * e_ref, (e_dev, e_ref)
+    # X restricted to the skeleton rows is the identity (src/qr.rs:375-402)
+    assert np.max(np.abs(rid_dev.x[rid_dev.row_ind[:k]] - np.eye(k))) < (1e-5 if tol > 1e-6 else 1e-12)
+    # Apply: RowID . matrix and RowID . vector (rc_row_id_apply), against the oracle's x (r rhs)
+    rhs = random_gaussian((n, 4), dtype, seed=5)
+    want = rid_ref.dot(rhs)
+    assert ref.rel_diff_fro(rid_dev.dot(rhs), want) < (2e-4 if tol > 1e-6 else 1e-9)
+    assert ref.rel_diff_fro(rid_dev.dot(rhs[:, 1]), want[:, 1]) < (2e-4 if tol > 1e-6 else 1e-9)
+    assert ref.rel_diff_fro(rid_dev.dot(rhs), rid_dev.to_mat().dot(rhs)) < (2e-5 if tol > 1e-6 else 1e-12)
+    ts_dev, ts_ref = rid_dev.two_sided_id(), rid_ref.two_sided_id()
+    order2 = adjudicate(rid_dev.r, ts_dev.col_ind, ts_ref.col_ind, upto=k, label=f"{name} RowID::two_sided_id col_ind")
+    if order2 is not None:
+        ts_ref = rid_ref.two_sided_id(order=order2)
+    t_ref, t_dev = ref.rel_diff_fro(ts_ref.to_mat(), a), ref.rel_diff_fro(ts_dev.to_mat(), a)
+    assert abs(t_dev - t_ref) <= 10 * tol * t_ref, (t_dev, t_ref)
+    assert np.array_equal(ts_dev.row_ind, rid_dev.row_ind)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32, np.complex64])
+def test_containers_from_parts(api, dtype):
+    """QR / LQ / SVD assembled from parts (pub fields: src/qr.rs:31-51, src/svd.rs:13-20) behave like the
+    factorisations they were taken from: rc_qr_new / rc_lq_new / rc_svd_new."""
+    a = helmholtz_kernel_matrix(120, 90, dtype)
+    tol = 1e-5 if RTOL[dtype] > 1e-6 else 1e-12
+    qr = api.QR.compute_from(a)
+    qr2 = api.QR.new(qr.q, qr.r, qr.ind)
+    assert ref.rel_diff_fro(qr2.to_mat(), qr.to_mat()) < tol and np.array_equal(qr2.ind, qr.ind)
+    c1, c2 = qr.compress(api.RANK(20)).column_id(), qr2.compress(api.RANK(20)).column_id()
+    assert ref.rel_diff_fro(c2.to_mat(), c1.to_mat()) < tol and np.array_equal(c1.col_ind, c2.col_ind)
+    # a QR the caller computed elsewhere (here: the oracle's) is accepted as is
+    qo = ref.QR.compute_from(a)
+    cid = api.QR.new(qo.q, qo.r, qo.ind).compress(api.RANK(20)).column_id()
+    assert abs(ref.rel_diff_fro(cid.to_mat(), a) - ref.rel_diff_fro(qo.compress(ref.RANK(20)).column_id().to_mat(), a)) < 1e3 * tol
+    lq = api.LQ.compute_from(a)
+    lq2 = api.LQ.new(lq.l, lq.q, lq.ind)
+    assert ref.rel_diff_fro(lq2.to_mat(), lq.to_mat()) < tol
+    assert ref.rel_diff_fro(lq2.compress(api.RANK(20)).row_id().to_mat(), lq.compress(api.RANK(20)).row_id().to_mat()) < tol
+    svd = api.SVD.compute_from(a)
+    svd2 = api.SVD.new(svd.u, svd.s, svd.vt)
+    assert ref.rel_diff_fro(svd2.to_mat(), svd.to_mat()) < tol and svd2.rank() == svd.rank()
+    assert svd2.compress(api.ADAPTIVE(1e-2)).rank() == svd.compress(api.ADAPTIVE(1e-2)).rank()
+    assert ref.rel_diff_fro(svd2.to_qr().to_mat(), svd.to_mat()) < 10 * tol
+    with pytest.raises(AssertionError):
+        api.QR.new(qr.q, qr.r[:-1], qr.ind)              # q.cols != r.rows
+    with pytest.raises(AssertionError):
+        api.SVD.new(svd.u, svd.s[:-1], svd.vt)
 
 
 def test_adaptive_example_parity(api):
