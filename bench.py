@@ -12,6 +12,13 @@ row-sharded; TSQR R-factors all-gathered, A^H Q partials all-reduced over NCCL).
 
 Prints ONE JSON line on rank 0.  `value` = algorithmic GFLOP/s with A resident in HBM;
 `e2e` = the same through the C ABI with host buffers (H2D of A and D2H of U, s, Vt timed).
+
+BASELINE's metric is "rSVD/ID ... at 1/2/4/8 B200", so the same line carries the ID half and the sharded configs as
+sub-records (each timed like `value`: CUDA events on the launching stream, max over ranks; not part of `value`):
+  id_config3      N = 1: configs[2], column ID via pivoted QR on the sketch, f32 32768^2, tol 1e-4 (+ its own cpu_baseline)
+  id_config5      every N: configs[4], two-sided ID, c64 16384^2, rank 128, rows sharded over the N GPUs (strong scaling)
+  config4_strong  N >= 2: configs[3], row-sharded tall-skinny range finder, f32 2^23 x 8192, rank 256 (strong scaling)
+  sharded_parity  N >= 2: the row-sharded result against the unsharded CUDA result on the same (small) matrix
 """
 import argparse
 import json
@@ -179,7 +186,9 @@ def reference_arm(args, result_out):
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([s for _, s in vals])) * 1e3
     sample = (f"{m_sample} of {c['m']} rows (same n, k, p, it, spectrum); one GEMM per product (best-case CPU); "
-              f"oracle = scipy LAPACK ?geqp3/?orgqr/?gesdd on OpenBLAS")
+              f"oracle = scipy LAPACK ?geqp3/?orgqr/?gesdd on OpenBLAS"
+              + (f"; at --gpus {args.gpus} this arm still times ONE {m_sample}-row shard on the host cores (a rate, not the "
+                 f"{args.gpus}-shard job)" if args.gpus > 1 else ""))
     line = {"impl": "reference", "metric": "rsvd_f64_algorithmic_gflops", "value": value, "unit": "GFLOP/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -228,6 +237,171 @@ def pin_to_gpu_numa_node(index):
         return None, None
 
 
+# ----------------------------------------------------------------------------------- sub-records
+CFG3 = dict(n=32768, s=64, tol=1e-4, r0=1024, decade_every=64.0, seed=1235, omega_seed=42)
+CFG5 = dict(n=16384, k=128, p=10, seed=7, kappa=20.0, shift=1.5, omega_seed=42)
+CFG4 = dict(log2m=23, n=8192, k=256, p=10, r0=512, decade_every=64.0, seed=9, omega_seed=42)
+
+
+def config3_work(n, r_final, s, rank_id):
+    """SURVEY 8(d) config 3 as EXECUTED here: A Omega on r + s columns and A^H q on r columns (B = Q^H A of the sampler
+    is reused by compute_from_range_estimate, so the reference's third product with A is not executed and not
+    counted), re-projections, pivoted QR of the r x n factor, the triangular solves of the column ID."""
+    m = n
+    gemm = 2.0 * m * n * (2 * r_final + s)
+    other = 2.0 * m * r_final ** 2 + n * r_final ** 2 + 2.0 * n * r_final ** 2 + n * rank_id ** 2
+    passes = 2 * (r_final // s) + 1
+    return gemm + other, passes * m * n * 4.0, passes, gemm
+
+
+def bench_config3(api, ctx, timed, peaks, hbm_peak, cpu):
+    import numpy as np
+    c = CFG3
+    n, s, tol = c["n"], c["s"], c["tol"]
+    a = api.decaying_spectrum_matrix((n, n), np.float32, c["seed"], r0=c["r0"], decade_every=c["decade_every"], ctx=ctx)
+    out = {}
+
+    def step():
+        q, hist = api.sample_range_adaptive(a, tol, s, seed=c["omega_seed"], ctx=ctx, device=True)
+        qrc = api.QR.compute_from_range_estimate(q, a).compress(api.ADAPTIVE(tol))
+        cid = qrc.column_id()
+        out["hist"], out["rank"] = hist, qrc.rank()
+        return cid
+
+    ms = timed(step, 5, 3)
+    r_final, rank_id = out["hist"][-1][0], out["rank"]
+    flops, bytes_, passes, gemm_flops = config3_work(n, r_final, s, rank_id)
+    tf32_peak = peaks.get("tf32_umma_tflops") or 845.0
+    rec = {"workload": f"configs[2]: column ID via pivoted QR on the sketch, f32, {n}x{n}, sigma_j = 10^(-j/{c['decade_every']:g}), "
+                       f"sample_range_adaptive({tol:g}, {s}) -> QR::compute_from_range_estimate -> compress(ADAPTIVE({tol:g})) -> column_id()",
+           "ms": ms, "adaptive_rank": int(r_final), "id_rank": int(rank_id), "passes_over_A": passes,
+           "gflops": flops / ms / 1e6, "hbm_gbs": bytes_ / ms / 1e6,
+           "frac_hbm": bytes_ / ms / 1e6 / hbm_peak,
+           "frac_tf32": 3.0 * gemm_flops / ms / 1e9 / tf32_peak,
+           "frac_note": "frac_hbm: algorithmic bytes (one 4 GiB read of A per executed product) / time / measured HBM peak; "
+                        "frac_tf32: 3 x algorithmic GEMM flops (the TF32 split executes three products) / time / own-measured "
+                        "tcgen05 kind::tf32 issue-rate peak; the binding roof is HBM (each 64-column pass is HBM-bound)",
+           "tf32_peak_tflops_own_measured": tf32_peak, "dtype": "f32"}
+    if cpu:
+        from oracle import reference_path as ref
+        a_host = a.to_numpy()
+        t0 = time.perf_counter()
+        q_ref, hist_ref = ref.sample_range_adaptive(a_host, tol, s, ref.OmegaStream(np.float32, seed=c["omega_seed"]))
+        qr_ref = ref.QR.compute_from_range_estimate(q_ref, a_host).compress(ref.ADAPTIVE(tol))
+        qr_ref.column_id()
+        sec = time.perf_counter() - t0
+        # the reference recomputes B = Q^H A in compute_from_range_estimate: its executed work has the third product
+        flops_ref = flops + 2.0 * n * n * r_final
+        rec["cpu_baseline"] = {"value": flops_ref / sec / 1e9, "unit": "GFLOP/s", "ms": sec * 1e3, "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"oracle pipeline on the full {n}x{n} f32 matrix (same A, same Philox Omega stream), one GEMM per "
+                                         f"product (best-case CPU), one pass; rank history {[int(r) for r, _ in hist_ref]}"}
+        del a_host
+    a.free()
+    return rec
+
+
+def bench_config5(api, ctx, timed, peaks, world, rank, cpu):
+    import numpy as np
+    c = CFG5
+    n, k, p = c["n"], c["k"], c["p"]
+    rows = n // world
+    a = api.helmholtz_kernel_matrix((rows, n), np.complex128, seed=c["seed"], kappa=c["kappa"], shift=c["shift"],
+                                    row_offset=rank * rows, ctx=ctx)
+    if world > 1:
+        a.set_shard(n, rank * rows)
+
+    def step():
+        q = api.sample_range_by_rank(a, k, p, seed=c["omega_seed"], ctx=ctx, device=True)
+        cid = api.QR.compute_from_range_estimate(q, a).compress(api.RANK(k)).column_id()
+        return cid.two_sided_id()
+
+    ms = timed(step, 5, 3)
+    l = k + p
+    gemm = 8.0 * n * n * (l + k)
+    flops = gemm + 4.0 * 2.0 * (2.0 * n * l * l) + 2.0 * 4.0 * 2.0 * n * k * k + 4.0 * 2.0 * n * k * k      # + tall QR, two wide pivoted QRs, TRSMs
+    bytes_ = 2.0 * n * n * 16.0
+    fp64_peak = peaks.get("dmma_tflops") or 37.0
+    rec = {"workload": f"configs[4]: two-sided ID, c64, {n}x{n} Helmholtz kernel matrix (kappa {c['kappa']:g}, box gap 0.5), rank {k} (+{p}): "
+                       "sample_range_by_rank -> QR::compute_from_range_estimate -> compress(RANK) -> column_id -> two_sided_id",
+           "ms": ms, "n_gpus": world, "rows_per_gpu": rows, "scaling": "strong", "gflops": flops / ms / 1e6, "hbm_gbs": bytes_ / ms / 1e6,
+           "frac_fp64": flops / ms / 1e9 / (fp64_peak * world), "fp64_peak_tflops_own_measured": fp64_peak,
+           "frac_note": "algorithmic flops (8 m n (l + k) for the two products with A + QRs + solves) / time / (own-measured DMMA peak x N); "
+                        "FP64-pipe bound (arithmetic intensity 66 flop/B)", "dtype": "c64"}
+    if cpu and world == 1:
+        from oracle import reference_path as ref
+        from oracle.philox import random_gaussian
+        a_host = a.to_numpy()
+        omega = random_gaussian((n, l), np.complex128, c["omega_seed"])
+        t0 = time.perf_counter()
+        q_ref = ref.sample_range_by_rank(a_host, k, p, ref.OmegaStream(np.complex128, blocks=[omega]))
+        ref.QR.compute_from_range_estimate(q_ref, a_host).compress(ref.RANK(k)).column_id().two_sided_id()
+        sec = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": flops / sec / 1e9, "unit": "GFLOP/s", "ms": sec * 1e3, "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"oracle pipeline on the full {n}x{n} c64 matrix (same A, same Omega), one GEMM per product, one pass"}
+        del a_host
+    a.free()
+    return rec
+
+
+def bench_config4(api, ctx, timed, peaks, hbm_peak, world, rank):
+    import numpy as np
+    c = CFG4
+    m, n, k, p = 1 << c["log2m"], c["n"], c["k"], c["p"]
+    l = k + p
+    rows = m // world
+    a = api.tall_shard_matrix(rank * rows, rows, n, np.float32, c["seed"], m, r0=c["r0"], decade_every=c["decade_every"], ctx=ctx)
+    a.set_shard(m, rank * rows)
+    ms = timed(lambda: api.sample_range_by_rank(a, k, p, seed=c["omega_seed"], ctx=ctx, device=True), 3, 2)
+    flops = 2.0 * m * n * l + 2.0 * (2.0 * m * l * l - 2.0 / 3.0 * l ** 3)
+    bytes_ = m * n * 4.0 + 3.0 * m * l * 4.0
+    tf32_peak = peaks.get("tf32_umma_tflops") or 845.0
+    a.free()
+    return {"workload": f"configs[3]: row-sharded tall-skinny range finder + TSQR, f32, 2^{c['log2m']} x {n} (256 GiB, generated per shard on "
+                        f"device), rank {k} (+{p}): sample_range_by_rank on the sharded operator",
+            "ms": ms, "n_gpus": world, "rows_per_gpu": rows, "scaling": "strong", "tflops": flops / ms / 1e9,
+            "hbm_gbs": bytes_ / ms / 1e6, "frac_hbm": bytes_ / ms / 1e6 / (hbm_peak * world),
+            "frac_tf32": 3.0 * flops / ms / 1e9 / (tf32_peak * world), "tf32_peak_tflops_own_measured": tf32_peak,
+            "frac_note": "algorithmic flops (GEMM 2 m n l + tall QR) x 3 (TF32 split) / time / (own-measured tcgen05 kind::tf32 peak x N); "
+                         "strong-scaling efficiency = ms(N = 2) x 2 / (ms(N) x N) across the N = 2, 4, 8 lines", "dtype": "f32"}
+
+
+def sharded_parity(api, ctx, world, rank, local):
+    """N >= 2: the row-sharded pipelines against the UNSHARDED CUDA path on the same matrix (gathered on rank 0), so the
+    multi-GPU results are checked on the very box the scaling numbers come from."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rows, n, k, p = 4096, 1024, 48, 10
+    m = rows * world
+    a_loc = api.decaying_spectrum_matrix((rows, n), np.float64, 77, r0=128, decade_every=10.0, row_offset=rank * rows, ctx=ctx)
+    a_loc.set_shard(m, rank * rows)
+    q = api.sample_range_power_iteration(a_loc, k, p, 2, seed=5, ctx=ctx, device=True)
+    s_sh = api.SVD.compute_from_range_estimate(q, a_loc).s_f64()
+    q2 = api.sample_range_by_rank(a_loc, k, p, seed=5, ctx=ctx, device=True)
+    cid = api.QR.compute_from_range_estimate(q2, a_loc).compress(api.RANK(k)).column_id()
+    col_sh = cid.col_ind[:k].copy()
+    row_sh = cid.two_sided_id().row_ind[:k].copy()
+    t = torch.from_numpy(a_loc.to_numpy()).cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    rec = None
+    if rank == 0:
+        ctx1 = api.Context(device=local)            # no communicator: the single-GPU path
+        a_full = api.DeviceMatrix.from_numpy(torch.cat(parts, 0).cpu().numpy(), ctx=ctx1)
+        q1 = api.sample_range_power_iteration(a_full, k, p, 2, seed=5, ctx=ctx1, device=True)
+        s_1 = api.SVD.compute_from_range_estimate(q1, a_full).s_f64()
+        q3 = api.sample_range_by_rank(a_full, k, p, seed=5, ctx=ctx1, device=True)
+        cid1 = api.QR.compute_from_range_estimate(q3, a_full).compress(api.RANK(k)).column_id()
+        rec = {"workload": f"f64 {m}x{n} row-sharded over {world} GPUs vs the unsharded CUDA path on the gathered matrix (rank {k} (+{p}))",
+               "max_rel_singular_value_deviation": float(np.max(np.abs(s_sh - s_1) / s_1)),
+               "skeleton_columns_identical": bool(np.array_equal(col_sh, cid1.col_ind[:k])),
+               "skeleton_rows_identical": bool(np.array_equal(row_sh, cid1.two_sided_id().row_ind[:k]))}
+        a_full.free()
+        ctx1.close()
+    a_loc.free()
+    return rec
+
+
 def _claim_stdout():
     """Exactly ONE line may reach stdout (the JSON result): libraries such as NCCL print banners to
     fd 1, so fd 1 is pointed at stderr for the whole run and the result goes to the saved descriptor."""
@@ -249,6 +423,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-gemv", action="store_true")
+    ap.add_argument("--skip-sub", action="store_true", help="skip the id_config3 / id_config5 / config4_strong sub-records")
     args = ap.parse_args()
     if args.m:
         CFG["m"] = args.m
@@ -359,6 +534,8 @@ def main():
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "peak_source": "own-measured DMMA microbenchmark (rc_peaks); MEASURED_PEAKS.json has no FP64 figure",
                     "own_measured_peaks": peaks, "traffic": prof.get("dram_bytes_per_launch"),
+                    "traffic_source": "ncu --set full capture of this kernel committed as profiles/dominant_kernel.json (dram__bytes_read.sum + "
+                                      "dram__bytes_write.sum per launch); not re-measured by this run",
                     "algorithmic_bytes_per_launch": m * n * 8 + (n + m) * l * 8,
                     "hbm_gbs_of_this_kernel": (m * n * 8 + (n + m) * l * 8) / (ms_nn * 1e-3) / 1e9,
                     "hbm_frac_of_measured": (m * n * 8 + (n + m) * l * 8) / (ms_nn * 1e-3) / 1e9 / hbm_peak,
@@ -396,13 +573,37 @@ def main():
                "ms_per_step": ms_e2e, "api": "rc_matrix_from_host -> rc_sample_range_power_iteration -> "
                                            "rc_svd_compute_from_range_estimate -> rc_matrix_to_host (pinned host buffers)"}
 
+    if all_cpus:
+        try:
+            os.sched_setaffinity(0, all_cpus)              # the CPU baselines use every host core
+        except Exception:
+            pass
+    # ---- sub-records: the ID half of the metric and the sharded configs (see the module docstring)
+    sub = {}
+    if not args.skip_sub:
+        try:
+            a_dev.free()
+        except Exception:
+            pass
+        peaks_all = roofline["own_measured_peaks"] if roofline else {}
+
+        def guarded(name, fn):
+            try:
+                r = fn()
+                if rank == 0 and r is not None:
+                    sub[name] = r
+            except Exception as e:            # a sub-record never takes the headline line down with it
+                if rank == 0:
+                    sub[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+        if world == 1:
+            guarded("id_config3", lambda: bench_config3(api, ctx, timed, peaks_all, hbm_peak, not args.skip_cpu))
+        guarded("id_config5", lambda: bench_config5(api, ctx, timed, peaks_all, world, rank, not args.skip_cpu))
+        if world > 1:
+            guarded("config4_strong", lambda: bench_config4(api, ctx, timed, peaks_all, hbm_peak, world, rank))
+            guarded("sharded_parity", lambda: sharded_parity(api, ctx, world, rank, local))
     if rank == 0:
         cpu = None
-        if all_cpus:
-            try:
-                os.sched_setaffinity(0, all_cpus)          # the CPU baseline uses every host core
-            except Exception:
-                pass
         if not args.skip_cpu and world == 1:       # the CPU baseline is an N = 1 figure
             m_sample = min(CPU_SAMPLE_ROWS, CFG["m"])
             gf, sec = cpu_sample(m_sample, "gemm", reps=3)
@@ -417,6 +618,11 @@ def main():
                 "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "hbm_gbs_algorithmic": hbm_gbs, "algorithmic_flops_per_step_per_gpu": flops_rank}
+        line.update(sub)
+        if world > 1:
+            line["reference_arm_note"] = ("bench.py --impl reference times ONE 65536-row shard on the host cores at every N (the CPU has "
+                                          "no second socket to scale to): the driver's ratio at N > 1 divides an N-GPU aggregate rate by a "
+                                          "one-shard CPU rate")
         result_out.write(json.dumps(line) + "\n")
         result_out.flush()
     if world > 1:
