@@ -159,6 +159,64 @@ void download_ind(rc_ctx* c, const int* dind, int64_t n, std::vector<uint64_t>& 
 }
 
 
+// Acceptance test of a Cholesky-QR2 panel from its two status words (chol.cu): round 1 without breakdown and with
+// diag(R1) spanning less than 1e6 (2e2 in single precision), round 2 without breakdown and with a Gram matrix of q1
+// within 0.25 of I.
+bool cholqr2_acceptable(const double* h, bool single) {
+    const double max_ratio = single ? 2.0e2 : 1.0e6;
+    const bool ok1 = h[0] == 0.0 && h[1] > 0.0 && h[2] / h[1] <= max_ratio;
+    const bool ok2 = h[4] == 0.0 && h[5] > 0.0 && h[7] <= 0.25;
+    return ok1 && ok2;
+}
+
+// Deferred (speculative) region: see rc_ctx::defer_depth.  finish_deferred() reads all collected status words with
+// ONE host synchronisation and says whether every speculative panel was acceptable.
+struct DeferScope {
+    rc_ctx* c;
+    explicit DeferScope(rc_ctx* ctx) : c(ctx) { c->defer_depth++; }
+    ~DeferScope() { c->defer_depth--; }
+};
+bool finish_deferred(rc_ctx* c) {
+    bool ok = true;
+    const size_t n = c->deferred.size();
+    if (n == 0) { RC_CUDA(cudaStreamSynchronize(c->stream)); return true; }
+    std::vector<double> h(8 * n);
+    for (size_t i = 0; i < n; ++i)
+        RC_CUDA(cudaMemcpyAsync(h.data() + 8 * i, c->deferred[i].status, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i) {
+        if (!cholqr2_acceptable(h.data() + 8 * i, c->deferred[i].single)) { ok = false; c->cholqr_fallbacks++; c->cholqr_used--; }
+        cudaFreeAsync(c->deferred[i].status, c->stream);
+    }
+    c->deferred.clear();
+    return ok;
+}
+void drop_deferred(rc_ctx* c) {
+    for (auto& d : c->deferred) cudaFreeAsync(d.status, c->stream);
+    c->deferred.clear();
+}
+
+// Work on an auxiliary stream (with its own tile-scheduler scratch) for the lifetime of the scope.  Everything the
+// library enqueues -- kernels, stream-ordered allocations and frees, collectives -- follows c->stream.
+struct StreamScope {
+    rc_ctx* c;
+    cudaStream_t saved_stream;
+    int* saved_counter;
+    StreamScope(rc_ctx* ctx, int idx) : c(ctx), saved_stream(ctx->stream), saved_counter(ctx->tile_counter) {
+        if (!c->aux_stream[idx]) {
+            RC_CUDA(cudaStreamCreateWithFlags(&c->aux_stream[idx], cudaStreamNonBlocking));
+            RC_CUDA(cudaMalloc((void**)&c->aux_tile_counter[idx], 256));
+        }
+        c->stream = c->aux_stream[idx];
+        c->tile_counter = c->aux_tile_counter[idx];
+    }
+    ~StreamScope() { c->stream = saved_stream; c->tile_counter = saved_counter; }
+};
+cudaEvent_t aux_event(rc_ctx* c, int i) {
+    if (!c->aux_event[i]) RC_CUDA(cudaEventCreateWithFlags(&c->aux_event[i], cudaEventDisableTiming));
+    return c->aux_event[i];
+}
+
 // Cholesky-QR2 fast path for a tall, numerically full-rank panel (Y = Q R with Q = q1 * rinv2):
 // two rounds of Gram matrix (one TN GEMM + all-reduce across row shards) -> small Cholesky -> Y R^{-1}.
 // All the work is GEMM-shaped, so it runs at tensor-pipe speed instead of the latency-bound
@@ -170,7 +228,7 @@ void download_ind(rc_ctx* c, const int* dind, int64_t n, std::vector<uint64_t>& 
 template <class T>
 bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, int dtype,
              DevBuf<T>& q1, DevBuf<T>& rinv2, DevBuf<T>& rfac, int64_t& lds) {
-    if (c->qr_mode == 1) return false;
+    if (c->qr_mode == 1 || c->force_householder) return false;
     const int64_t m_all = m;    // (local rows; the Gram matrices are summed across shards)
     if ((!sharded && m_all < 4 * w) || w > chol_max_width(c, dtype) || w < 2) return false;
     lds = rc_pad_ld(dtype, w);
@@ -178,7 +236,6 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
     DevBuf<double> status(c, 8);
     double h[8];
     const bool single = (dtype == RC_F32 || dtype == RC_C32);
-    const double max_ratio = single ? 2.0e2 : 1.0e6;
     auto gram_chol = [&](const T* x, int64_t ldx, T* rr, T* ri, double* st) -> bool {
         if (sharded && lds != w) RC_CUDA(cudaMemsetAsync(g.p, 0, sizeof(T) * w * lds, c->stream));   // padding is summed too
         gemm<T>(c, RC_OP_H, RC_OP_N, w, w, m, x, ldx, x, ldx, g.p, lds, rc_one<T>(), rc_zero<T>());
@@ -196,11 +253,16 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
     if (!gram_chol(q1.p, lds, r2.p, rinv2.p, status.p + 4)) return false;
     rfac.alloc(c, (size_t)w * lds);
     gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, r2.p, lds, r1.p, lds, rfac.p, lds, rc_one<T>(), rc_zero<T>());
+    if (c->defer_depth > 0) {
+        // speculative: carry on as if both rounds were accepted; the status words are checked at the end of the
+        // deferred region (finish_deferred), which re-runs it on the Householder path when a panel was not acceptable
+        c->deferred.push_back({status.take(), single});
+        c->cholqr_used++;
+        return true;
+    }
     RC_CUDA(cudaMemcpyAsync(h, status.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     RC_CUDA(cudaStreamSynchronize(c->stream));
-    const bool ok1 = h[0] == 0.0 && h[1] > 0.0 && h[2] / h[1] <= max_ratio;      // round 1: no breakdown, diag(R1) ratio
-    const bool ok2 = h[4] == 0.0 && h[5] > 0.0 && h[7] <= 0.25;                  // round 2: Gram matrix of q1 close to I
-    if (!(ok1 && ok2)) { c->cholqr_fallbacks++; return false; }
+    if (!cholqr2_acceptable(h, single)) { c->cholqr_fallbacks++; return false; }
     rc_trace(c, "  cholqr2: 2 x (gram + chol), q1 = Y rinv1");
     c->cholqr_used++;
     return true;
@@ -298,7 +360,7 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
         gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, qfull.p, ldq, q1p.p, ldq1, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
         rc_trace(c, "pqr_tall: form Q1, Q = Qfull Q1");
     }
-    download_ind(c, dind.p, w, out.ind);
+    if (out.want_ind) download_ind(c, dind.p, w, out.ind);
     out.q.reset(q.release());
     out.r.reset(r.release());
 }
@@ -329,6 +391,7 @@ void pivoted_qr_impl(rc_ctx* c, const rc_matrix* arr, bool input_is_conj_transpo
             MatPtr wide(mat_new(c, dtype | 1, arr->rows, arr->cols));
             k_cast<W, T>(c, P<W>(wide.get()), wide->ld, P<T>(arr), arr->ld, arr->rows, arr->cols);
             QrParts ow;
+            ow.want_ind = out.want_ind;
             pivoted_qr_impl<W>(c, wide.get(), input_is_conj_transposed, ncq, true, ow);
             MatPtr q(mat_new(c, dtype, ow.q->rows, ow.q->cols)), r(mat_new(c, dtype, ow.r->rows, ow.r->cols));
             k_cast<T, W>(c, P<T>(q.get()), q->ld, P<W>(ow.q.get()), ow.q->ld, q->rows, q->cols);
@@ -377,7 +440,7 @@ void pivoted_qr_impl(rc_ctx* c, const rc_matrix* arr, bool input_is_conj_transpo
     MatPtr q(mat_new(c, dtype, p, ncq));
     pivqr_form_q<T>(c, vbuf.p, tau.p, p, kk, ncq, P<T>(q.get()), q->ld);
     rc_trace(c, "  pivoted_qr: form Q");
-    download_ind(c, dind.p, n, out.ind);
+    if (out.want_ind) download_ind(c, dind.p, n, out.ind);
     out.q.reset(q.release());
     out.r.reset(r.release());
 }
@@ -538,6 +601,62 @@ rc_matrix* sample_by_rank_impl(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t
 // restarts from Y0 = A Omega and the result equals the it_count = 1 result; every trip is
 // executed as the reference executes it.  Option "true_power_iteration" advances Y instead.
 template <class T>
+rc_matrix* sample_power_once(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p, int64_t it_count,
+                             const rc_matrix* omega) {
+    const int64_t l = k + p;
+    MatPtr y0(matmat_impl<T>(c, a, omega));                      // :140-141
+    MatPtr res;                                                  // :142 (res = y0 unless a trip replaces it)
+    if (c->true_power_iteration || it_count < 2 || !c->overlap) {
+        MatPtr cur;                                              // only for true_power_iteration
+        for (int64_t index = 0; index < it_count; ++index) {
+            const rc_matrix* start = (c->true_power_iteration && cur.get()) ? cur.get() : y0.get();
+            QrParts q1; q1.want_ind = false;
+            pivoted_qr_impl<T>(c, start, false, -1, false, q1);      // :145-146 (all columns of Q)
+            MatPtr z(conj_matmat_impl<T>(c, a, q1.q.get()));          // :148
+            QrParts q2; q2.want_ind = false;
+            pivoted_qr_impl<T>(c, z.get(), false, -1, true, q2);     // :148-149
+            MatPtr ynew(matmat_impl<T>(c, a, q2.q.get()));            // :150
+            if (c->true_power_iteration) { cur.reset(ynew.release()); if (index == it_count - 1) res.reset(cur.release()); }
+            else if (index == it_count - 1) res.reset(ynew.release());   // :151-153
+        }
+    } else {
+        // Reference semantics (quirk Q1): every trip starts from the same Y0 and none reads another's result, so the
+        // trips are independent.  They are executed -- all of them, as the reference executes them -- on two auxiliary
+        // streams, issued stage by stage in lockstep (the order of the collectives is then the same on every rank of a
+        // sharded run): while one trip sits in the latency-bound one-CTA kernels of its pivoted QR (Cholesky, pivoting,
+        // forming Q), the other trip's kernels fill the rest of the machine.
+        struct Trip { QrParts q1, q2; MatPtr z, ynew; };
+        std::vector<Trip> trips((size_t)it_count);
+        cudaEvent_t ev_y0 = aux_event(c, 0);
+        RC_CUDA(cudaEventRecord(ev_y0, c->stream));
+        for (int stage = 0; stage < 4; ++stage) {
+            for (int64_t t = 0; t < it_count; ++t) {
+                Trip& tr = trips[(size_t)t];
+                StreamScope on_aux(c, (int)(t & 1));
+                if (stage == 0 && t < 2) RC_CUDA(cudaStreamWaitEvent(c->stream, ev_y0, 0));
+                switch (stage) {
+                    case 0: tr.q1.want_ind = false; pivoted_qr_impl<T>(c, y0.get(), false, -1, false, tr.q1); break;   // :145-146
+                    case 1: tr.z.reset(conj_matmat_impl<T>(c, a, tr.q1.q.get())); break;                              // :148
+                    case 2: tr.q2.want_ind = false; pivoted_qr_impl<T>(c, tr.z.get(), false, -1, true, tr.q2); break; // :148-149
+                    default: tr.ynew.reset(matmat_impl<T>(c, a, tr.q2.q.get())); break;                               // :150
+                }
+            }
+        }
+        for (int s = 0; s < 2; ++s) {                            // join: everything below (and every free) follows both
+            cudaEvent_t ev = aux_event(c, 1 + s);
+            RC_CUDA(cudaEventRecord(ev, c->aux_stream[s]));
+            RC_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
+        }
+        res.reset(trips[(size_t)it_count - 1].ynew.release());   // :151-153 (the last trip's product)
+    }
+    const rc_matrix* fin = res.get() ? res.get() : y0.get();
+    QrParts qr; qr.want_ind = false;
+    int64_t kk = std::min<int64_t>(mat_sharded(a) ? a->global_rows : a->rows, l);
+    pivoted_qr_impl<T>(c, fin, false, std::min(k, kk), true, qr);   // :156-159
+    return qr.q.release();
+}
+
+template <class T>
 rc_matrix* sample_power_impl(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p, int64_t it_count,
                              const rc_matrix* omega, uint64_t seed) {
     const int64_t n = a->cols, l = k + p;
@@ -545,25 +664,28 @@ rc_matrix* sample_power_impl(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p
     MatPtr gen;
     if (!omega) { gen.reset(gaussian_new<T>(c, a->dtype, n, l, seed, 0, 0)); omega = gen.get(); }
     RC_REQUIRE(omega->rows == n && omega->cols == l, "omega must be %lld x %lld", (long long)n, (long long)l);
-    MatPtr y0(matmat_impl<T>(c, a, omega));                      // :140-141
-    MatPtr res;                                                  // :142 (res = y0 unless a trip replaces it)
-    MatPtr cur;                                                  // only for true_power_iteration
-    for (int64_t index = 0; index < it_count; ++index) {
-        const rc_matrix* start = (c->true_power_iteration && cur.get()) ? cur.get() : y0.get();
-        QrParts q1;
-        pivoted_qr_impl<T>(c, start, false, -1, false, q1);      // :145-146 (all columns of Q)
-        MatPtr z(conj_matmat_impl<T>(c, a, q1.q.get()));          // :148
-        QrParts q2;
-        pivoted_qr_impl<T>(c, z.get(), false, -1, true, q2);     // :148-149
-        MatPtr ynew(matmat_impl<T>(c, a, q2.q.get()));            // :150
-        if (c->true_power_iteration) { cur.reset(ynew.release()); if (index == it_count - 1) res.reset(cur.release()); }
-        else if (index == it_count - 1) res.reset(ynew.release());   // :151-153
+    if (!c->speculate || c->qr_mode == 1 || c->defer_depth > 0) return sample_power_once<T>(c, a, k, p, it_count, omega);
+    // Speculative pass: no host synchronisation inside the pipeline (the Cholesky-QR2 panels are assumed acceptable,
+    // pivot vectors are not downloaded); one synchronisation at the end checks every panel's status word, and a
+    // rejected panel re-runs the sampler on the unconditionally stable Householder TSQR.
+    MatPtr q;
+    bool ok = false;
+    try {
+        DeferScope defer(c);
+        q.reset(sample_power_once<T>(c, a, k, p, it_count, omega));
+        ok = true;
+    } catch (...) {
+        drop_deferred(c);
+        throw;
     }
-    const rc_matrix* fin = res.get() ? res.get() : y0.get();
-    QrParts qr;
-    int64_t kk = std::min<int64_t>(mat_sharded(a) ? a->global_rows : a->rows, l);
-    pivoted_qr_impl<T>(c, fin, false, std::min(k, kk), true, qr);   // :156-159
-    return qr.q.release();
+    if (ok && finish_deferred(c)) return q.release();
+    q.reset(nullptr);
+    c->force_householder = true;
+    try {
+        q.reset(sample_power_once<T>(c, a, k, p, it_count, omega));
+    } catch (...) { c->force_householder = false; throw; }
+    c->force_householder = false;
+    return q.release();
 }
 
 // AdaptiveSampling::sample_range_adaptive (src/random_sampling.rs:223-274).  Q and B live in
@@ -880,6 +1002,11 @@ rc_status rc_ctx_destroy(rc_ctx* c) {
         cudaStreamSynchronize(c->stream);
         try { comm_destroy(c); } catch (...) {}
         if (c->tile_counter) cudaFree(c->tile_counter);
+        for (int i = 0; i < 2; ++i) {
+            if (c->aux_stream[i]) { cudaStreamSynchronize(c->aux_stream[i]); cudaStreamDestroy(c->aux_stream[i]); }
+            if (c->aux_tile_counter[i]) cudaFree(c->aux_tile_counter[i]);
+        }
+        for (int i = 0; i < 4; ++i) if (c->aux_event[i]) cudaEventDestroy(c->aux_event[i]);
         if (c->own_stream) cudaStreamDestroy(c->stream);
     }
     delete c;
@@ -909,6 +1036,8 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
         else if (!strcmp(key, "true_power_iteration")) c->true_power_iteration = (int)v;
         else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;
         else if (!strcmp(key, "pivot_precision")) c->pivot_f64 = (v != 0);
+        else if (!strcmp(key, "speculate")) c->speculate = (int)v;
+        else if (!strcmp(key, "overlap")) c->overlap = (int)v;
         else if (!strcmp(key, "reuse_range_b")) c->reuse_range_b = (int)v;
         else if (!strcmp(key, "trace")) c->trace = (int)v;
         else RC_THROW(RC_INVALID_ARGUMENT, "unknown option '%s'", key);

@@ -126,6 +126,8 @@ rc_matrix* mat_mul(rc_ctx* c, RcOp opa, const rc_matrix* a, RcOp opb, const rc_m
 struct QrParts {
     MatPtr q, r;
     std::vector<uint64_t> ind;
+    bool want_ind = true;     // false: the caller only needs q / r (the samplers); skips the device-to-host copy of the
+                              // pivot vector and its host synchronisation
 };
 struct SvdParts {
     MatPtr u, vt;

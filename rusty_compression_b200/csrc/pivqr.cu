@@ -184,9 +184,11 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int cap, int 
             }
         }
         __syncthreads();
-        const int pv = s_win.phys;          // physical pivot column
-        const int pv_lpos = s_win.lpos;     // where it sat logically
         const int dc = s_windisp;           // physical column sitting at logical position i
+        // (no winner = every candidate norm is NaN, possible only in a speculative run on garbage, rc_ctx::defer_depth:
+        // keep the column at position i so that all indices stay in range)
+        const int pv = s_win.phys >= 0 ? s_win.phys : dc;          // physical pivot column
+        const int pv_lpos = s_win.phys >= 0 ? s_win.lpos : i;      // where it sat logically
         // (d) logical swap, done by the owners
         if (tid == 0) {
             if (dc >= 0 && dc != pv && (dc % G) == b) lpos[dc / G] = pv_lpos;
@@ -392,7 +394,10 @@ pivqr_small_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, int* 
             best = warp_best(best);
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, m));
-            const int pv = best.phys;
+            // (all candidate norms NaN -- a speculative run on the output of a Cholesky that broke down, rc_ctx::defer_depth
+            // -- leaves no winner: take the column already sitting at position i, so every index stays in range)
+            const int pv = best.phys >= 0 ? best.phys : disp;
+            if (best.phys < 0) best.lpos = i;
             if (lane == 0) {
                 if (disp >= 0 && disp != pv) lpos[disp] = best.lpos;
                 lpos[pv] = i;

@@ -54,6 +54,20 @@ struct rc_ctx {
     int pivot_f64 = 1;            // 1: pivot decisions on f32 / c32 inputs are taken in double (pivqr.cu, pivoted_qr_impl)
     int qr_mode = 0;              // 0 auto (Cholesky-QR2 fast path with Householder-TSQR fallback), 1 TSQR only
     int64_t cholqr_used = 0, cholqr_fallbacks = 0, range_b_reused = 0;
+    // Speculative execution (host_api.cu, DeferScope): inside a deferred region the Cholesky-QR2 panels do not read
+    // their status words back (no host synchronisation in the middle of a pipeline); the words are collected here and
+    // checked once at the end, and a failed check re-runs the region with the Householder TSQR forced.
+    int speculate = 1;            // option "speculate"
+    int overlap = 1;              // option "overlap": independent stages on auxiliary streams
+    int defer_depth = 0;
+    bool force_householder = false;
+    struct DeferredCheck { double* status; bool single; };
+    std::vector<DeferredCheck> deferred;
+    // auxiliary streams for independent stages (the two power-iteration trips of the reference are independent of
+    // each other, quirk Q1), each with its own scratch for the dynamic GEMM tile scheduler
+    cudaStream_t aux_stream[2] = {nullptr, nullptr};
+    int* aux_tile_counter[2] = {nullptr, nullptr};
+    cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
     // counters
     int64_t launches = 0, gemm_flops = 0, h2d_bytes = 0, d2h_bytes = 0;
     int* tile_counter = nullptr;   // device scratch for the dynamic GEMM tile scheduler
