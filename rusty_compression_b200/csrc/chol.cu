@@ -9,112 +9,152 @@ namespace {
 
 constexpr int CT = 1024;
 
+constexpr int NB = 16;        // block size of the factorisation and of the triangular inverse
+
+// Blocked right-looking Cholesky G = L L^H (L = R^H lower triangular) and blocked triangular inverse X = L^{-1}.
+// The unblocked kernel this replaces paid one block barrier and one dependent scalar chain per COLUMN (74 of each for
+// the 74 x 74 Gram matrix of the config-2 sketch: ~90 us, on the critical path of every tall QR); here the serial part
+// is one 16 x 16 diagonal block per 16 columns, factored and inverted by one warp, and everything else is
+// GEMM-shaped work for the whole block:
+//   per block column:  diagonal block (warp 0: Cholesky, then its inverse)            | barrier
+//                      panel   L21 = A21 L11^{-H}   (one output per thread)           | 2 barriers (in place)
+//                      update  A22 -= L21 L21^H                                       | barrier
+//   inverse:           level d = 1 .. nblk-1 (block sub-diagonal d, all blocks of a level at once):
+//                      T = sum_k L_ik X_kj ; X_ij = -X_ii T                           | 2 barriers per level
 template <class T>
 __global__ void __launch_bounds__(CT)
 chol_inv_kernel(const T* __restrict__ g, int64_t ldg, int w, T* __restrict__ r, T* __restrict__ rinv, int64_t ldo, double* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* S = reinterpret_cast<T*>(smem_raw);          // w x w row-major working copy (upper part used)
-    T* X = S + (size_t)w * w;                        // inverse
+    const int ld = w | 1;                            // odd pitch: a column of L / X touches every bank once
+    T* L = reinterpret_cast<T*>(smem_raw);           // lower triangle: the factor
+    T* X = L + (size_t)w * ld;                       // lower triangle: its inverse; the upper triangle is scratch
     __shared__ double s_red[CT / 32];
-    __shared__ double s_piv[257];                    // pivots d_j = R_jj^2 (w <= 256 is guaranteed by the smem limit)
+    __shared__ double s_dinv[256];                   // 1 / L_jj (w <= 256 is guaranteed by the shared-memory limit)
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    using R = RealOf<T>;
     double defect = 0.0;
     for (int e = tid; e < w * w; e += CT) {
         int i = e / w, j = e - i * w;
         T v = g[(int64_t)i * ldg + j];
-        S[e] = v;
+        if (j <= i) L[i * ld + j] = v;
         T d = (i == j) ? v - rc_one<T>() : v;
         defect = fmax(defect, rc_abs(d));
     }
     if (tid == 0) s_bad = 0;
-    // block max of the defect
     for (int m = 16; m > 0; m >>= 1) defect = fmax(defect, __shfl_xor_sync(0xffffffffu, defect, m));
     if (lane == 0) s_red[warp] = defect;
     __syncthreads();
     if (tid == 0) { double d = 0.0; for (int i = 0; i < CT / 32; ++i) d = fmax(d, s_red[i]); status[3] = d; }
-    // Right-looking (outer-product) Cholesky with ONE barrier per step: step j updates the trailing upper
-    // triangle with the UNSCALED row j, S[r][c] -= conj(S[j][r]) S[j][c] / d_j, so no thread has to wait for the
-    // scaled pivot row; the rows are scaled by 1 / sqrt(d_j) once at the end.
-    // The reciprocal of the NEXT pivot is computed by the thread that finishes S[j+1][j+1] (its first element
-    // of the step), so the ~200-cycle double division overlaps that thread's remaining updates instead of
-    // sitting at the head of every step for everybody.
-    __shared__ double s_invd[2];
-    if (tid == 0) {
-        const double d0 = (double)rc_real(S[0]);
-        s_piv[0] = d0; if (!(d0 > 0.0)) s_bad = 1;
-        s_invd[0] = 1.0 / ((d0 > 0.0) ? d0 : 1.0);
-    }
-    __syncthreads();
-    {
-        const int tx = lane, ty = warp;              // 32 x 32 thread tile (measured: a 16 x 16 tile with a
-        for (int j = 0; j < w; ++j) {                // 256-thread named barrier is 30 % slower at w = 74)
-            const RealOf<T> id = (RealOf<T>)s_invd[j & 1];
-            for (int rr = j + 1 + ty; rr < w; rr += 32) {
-                const T f = rc_conj(S[j * w + rr]) * id;
-                for (int cc = j + 1 + tx; cc < w; cc += 32)
-                    if (cc >= rr) {
-                        const T v = S[rr * w + cc] - f * S[j * w + cc];
-                        S[rr * w + cc] = v;
-                        if (rr == j + 1 && cc == j + 1) {        // thread 0, first element: the next pivot
-                            const double d = (double)rc_real(v);
-                            s_piv[j + 1] = d; if (!(d > 0.0)) s_bad = 1;
-                            s_invd[(j + 1) & 1] = 1.0 / ((d > 0.0) ? d : 1.0);
-                        }
+
+    const int nblk = (w + NB - 1) / NB;
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int j0 = kb * NB, jb = min(NB, w - j0);
+        // ---- diagonal block: unblocked Cholesky (lane = row), then the inverse of the block (lane = column)
+        if (warp == 0) {
+            for (int c = 0; c < jb; ++c) {
+                double d = (double)rc_real(L[(j0 + c) * ld + j0 + c]);
+                if (!(d > 0.0)) { if (lane == 0) s_bad = 1; d = 1.0; }
+                const double rd = rsqrt(d);
+                if (lane >= c && lane < jb) {
+                    T* e = &L[(j0 + lane) * ld + j0 + c];
+                    *e = (lane == c) ? rc_make<T>(d * rd, 0.0) : *e * (R)rd;
+                }
+                if (lane == 0) s_dinv[j0 + c] = rd;
+                __syncwarp();
+                if (lane > c && lane < jb) {
+                    const T lrc = L[(j0 + lane) * ld + j0 + c];
+                    for (int c2 = c + 1; c2 <= lane; ++c2) {
+                        T* e = &L[(j0 + lane) * ld + j0 + c2];
+                        *e = *e - lrc * rc_conj(L[(j0 + c2) * ld + j0 + c]);
                     }
+                }
+                __syncwarp();
+            }
+            if (lane < jb) {
+                const int c = lane;
+                X[(j0 + c) * ld + j0 + c] = rc_make<T>(s_dinv[j0 + c], 0.0);
+                for (int rr = c + 1; rr < jb; ++rr) {
+                    T acc = rc_zero<T>();
+                    for (int k = c; k < rr; ++k) acc = rc_fma(L[(j0 + rr) * ld + j0 + k], X[(j0 + k) * ld + j0 + c], acc);
+                    X[(j0 + rr) * ld + j0 + c] = -(acc * (R)s_dinv[j0 + rr]);
+                }
+            }
+        }
+        __syncthreads();
+        const int i0 = j0 + jb, nrow = w - i0;
+        if (nrow <= 0) break;
+        // ---- panel: L21 = A21 X11^H, out[i][c] = sum_{c' <= c} A[i][c'] conj(X11[c][c']); one output per thread, held in
+        //      a register across the barrier because the panel is overwritten in place
+        {
+            T outv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = tid + u * CT;
+                outv[u] = rc_zero<T>();
+                if (e < nrow * jb) {
+                    const int i = i0 + e / jb, c = e % jb;
+                    T acc = rc_zero<T>();
+                    for (int c1 = 0; c1 <= c; ++c1) acc = rc_fma(L[i * ld + j0 + c1], rc_conj(X[(j0 + c) * ld + j0 + c1]), acc);
+                    outv[u] = acc;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = tid + u * CT;
+                if (e < nrow * jb) L[(i0 + e / jb) * ld + j0 + e % jb] = outv[u];
             }
             __syncthreads();
         }
-    }
-    // scale the rows: R[j][c] = S[j][c] / sqrt(d_j); diagonal real positive
-    for (int e = tid; e < w * w; e += CT) {
-        int i = e / w, j = e - i * w;
-        if (j >= i) {
-            const double d = s_piv[i];
-            const double piv = sqrt((d > 0.0) ? d : 1.0);
-            S[e] = (i == j) ? rc_make<T>(piv, 0.0) : S[e] * (RealOf<T>)(1.0 / piv);
-        }
+        // ---- trailing update (lower triangle): A22[i][j] -= sum_c L21[i][c] conj(L21[j][c])
+        for (int i = i0 + warp; i < w; i += CT / 32)
+            for (int j = i0 + lane; j <= i; j += 32) {
+                T acc = L[i * ld + j];
+                for (int c = 0; c < jb; ++c) acc = acc - L[i * ld + j0 + c] * rc_conj(L[j * ld + j0 + c]);
+                L[i * ld + j] = acc;
+            }
+        __syncthreads();
     }
     __syncthreads();
+    // ---- X = L^{-1}: the diagonal blocks are in place; block sub-diagonal d needs only the sub-diagonals < d
+    for (int d = 1; d < nblk; ++d) {
+        const int nb_lvl = nblk - d;                                 // blocks (i = j + d, j), j = 0 .. nblk-1-d
+        // T = sum_k L_ik X_kj, stored transposed in the (unused) upper triangle of X
+        for (int e = tid; e < nb_lvl * NB * NB; e += CT) {
+            const int j = e / (NB * NB), rr = (e / NB) % NB, c = e % NB;
+            const int row = (j + d) * NB + rr, col = j * NB + c;
+            if (row < w) {
+                T acc = rc_zero<T>();
+                for (int kk = col; kk < (j + d) * NB; ++kk) acc = rc_fma(L[row * ld + kk], X[kk * ld + col], acc);
+                X[col * ld + row] = acc;
+            }
+        }
+        __syncthreads();
+        // X_ij = -X_ii T
+        for (int e = tid; e < nb_lvl * NB * NB; e += CT) {
+            const int j = e / (NB * NB), rr = (e / NB) % NB, c = e % NB;
+            const int ib = (j + d) * NB, row = ib + rr, col = j * NB + c;
+            if (row < w) {
+                T acc = rc_zero<T>();
+                for (int r1 = 0; r1 <= rr; ++r1) acc = rc_fma(X[row * ld + ib + r1], X[col * ld + ib + r1], acc);
+                X[row * ld + col] = -acc;
+            }
+        }
+        __syncthreads();
+    }
     if (warp == 0) {
         double dmin = 1e300, dmax = 0.0;
-        for (int j = lane; j < w; j += 32) { double pv = (double)rc_real(S[j * w + j]); dmin = fmin(dmin, pv); dmax = fmax(dmax, pv); }
+        for (int j = lane; j < w; j += 32) { double pv = (double)rc_real(L[j * ld + j]); dmin = fmin(dmin, pv); dmax = fmax(dmax, pv); }
         for (int m = 16; m > 0; m >>= 1) { dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, m)); dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, m)); }
         if (lane == 0) { status[0] = (double)s_bad; status[1] = dmin; status[2] = dmax; }
     }
-    // R out (upper triangular, zeros below)
+    // R = L^H (upper triangular, zeros below), R^{-1} = X^H
     for (int e = tid; e < w * w; e += CT) {
         int i = e / w, j = e - i * w;
-        r[(int64_t)i * ldo + j] = (j >= i) ? S[e] : rc_zero<T>();
+        r[(int64_t)i * ldo + j] = (j >= i) ? rc_conj(L[j * ld + i]) : rc_zero<T>();
+        rinv[(int64_t)i * ldo + j] = (j >= i) ? rc_conj(X[j * ld + i]) : rc_zero<T>();
     }
-    // X = R^{-1}: columns are independent (no block barriers); four lanes share a column and split each
-    // inner product, so the dependent chain of a column is c steps of (c - i) / 4 FMAs + two shuffles.  The
-    // eight columns of a warp run a common trip count (the shuffles need the whole warp).
-    {
-        const int sub = lane & 3;
-        for (int cbase = warp * 8; cbase < w; cbase += (CT / 32) * 8) {
-            const int c = cbase + (lane >> 2);
-            const bool active = c < w;
-            const int cmax = min(cbase + 7, w - 1);
-            if (active) {
-                for (int i = w - 1 - sub; i > c; i -= 4) X[i * w + c] = rc_zero<T>();
-                if (sub == 0) X[c * w + c] = rc_one<T>() / S[c * w + c];
-            }
-            __syncwarp();
-            for (int i = cmax - 1; i >= 0; --i) {
-                const bool work = active && i < c;
-                T acc = rc_zero<T>();
-                if (work)
-                    for (int l = i + 1 + sub; l <= c; l += 4) acc = rc_fma(S[i * w + l], X[l * w + c], acc);
-                acc = acc + rc_shfl_xor(acc, 1);
-                acc = acc + rc_shfl_xor(acc, 2);
-                if (work && sub == 0) X[i * w + c] = -(acc / S[i * w + i]);
-                __syncwarp();
-            }
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < w * w; e += CT) { int i = e / w, j = e - i * w; rinv[(int64_t)i * ldo + j] = X[e]; }
 }
 
 }  // namespace
@@ -122,7 +162,7 @@ chol_inv_kernel(const T* __restrict__ g, int64_t ldg, int w, T* __restrict__ r, 
 // r, rinv: w x w row-major (ld = ldo).  Returns false if w does not fit in shared memory.
 template <class T>
 bool chol_inv(rc_ctx* c, const T* g, int64_t ldg, int64_t w, T* r, T* rinv, int64_t ldo, double* status_dev) {
-    size_t smem = 2 * (size_t)w * w * sizeof(T);
+    size_t smem = 2 * (size_t)w * (size_t)(w | 1) * sizeof(T);
     size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
     if (smem + 8192 > lim || w > 256) return false;
     RC_CUDA(cudaFuncSetAttribute(chol_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -13,19 +13,24 @@ namespace {
 constexpr int JT = 1024;
 constexpr int JW = JT / 32;
 
-template <class T, bool SMEM>
+// LPP lanes share a column pair, so a warp rotates 32 / LPP pairs at once.  A round is ISSUE-bound, not latency-bound:
+// with one pair per warp every one of the 32 lanes executed the ~150-instruction scalar chain of its pair redundantly
+// and the 32 warps of a round cost ~2 400 issue cycles on the four schedulers (measured 3 300 cycles per round at
+// n = 64); with 8 lanes per pair the same round is 8 warps of about the same length.
+template <class T, bool SMEM, int LPP>
 __global__ void __launch_bounds__(JT)
-jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int max_sweeps, double tol,
+jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int ldg, int max_sweeps, double tol,
               T* __restrict__ u, int64_t ldu, double* __restrict__ s_out, T* __restrict__ w, int64_t ldw,
               double* __restrict__ sig_scratch, int* __restrict__ info) {
     __shared__ int s_rot;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // SMEM: G (rows x n) and V (n x n) are resident in shared memory for the whole iteration
+    // SMEM: G (rows x n, column stride ldg) and V (n x n) are resident in shared memory for the whole iteration
     T* G = SMEM ? reinterpret_cast<T*>(smem_raw) : Gg;
-    T* V = SMEM ? G + (size_t)rows * n : Vg;
+    T* V = SMEM ? G + (size_t)ldg * n : Vg;
+    const int ldgg = SMEM ? ldg : rows;             // the global copy is dense
     if (SMEM) {
-        for (int e = tid; e < rows * n; e += JT) G[e] = Gg[e];
+        for (int e = tid; e < rows * n; e += JT) { int c = e / rows, r = e - c * rows; G[(size_t)c * ldg + r] = Gg[e]; }
     }
     const int npad = n + (n & 1);
     const int half = npad / 2;
@@ -35,54 +40,72 @@ jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int max_s
         V[e] = (r == c) ? rc_one<T>() : rc_zero<T>();
     }
     __syncthreads();
+    constexpr int PPW = 32 / LPP;                   // pairs per warp
+    const int sl = lane % LPP, sg = lane / LPP;
+    const double tol2 = tol * tol;
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         if (tid == 0) s_rot = 0;
         __syncthreads();
         for (int round = 0; round < npad - 1; ++round) {
-            for (int k = warp; k < half; k += JW) {
-                int a, b;
-                if (k == 0) { a = npad - 1; b = round; }
-                else { a = (round + k) % (npad - 1); b = (round - k + (npad - 1)) % (npad - 1); }
-                int p = min(a, b), q = max(a, b);
-                if (q >= n) continue;                      // padding column
-                T* gp = G + (int64_t)p * rows;
-                T* gq = G + (int64_t)q * rows;
+            for (int k0 = warp * PPW; k0 < half; k0 += JW * PPW) {          // warp-uniform trip count (shuffles below)
+                const int k = k0 + sg;
+                int a = npad - 1, b = round;
+                if (k > 0) {
+                    a = round + k; if (a >= npad - 1) a -= npad - 1;
+                    b = round - k; if (b < 0) b += npad - 1;
+                }
+                const int p = min(a, b), q = max(a, b);
+                const bool valid = (k < half) && (q < n);                   // q == n: padding column of an odd n
+                T* gp = G + (int64_t)(valid ? p : 0) * ldgg;
+                T* gq = G + (int64_t)(valid ? q : 0) * ldgg;
                 double alpha = 0.0, beta = 0.0, gre = 0.0, gim = 0.0;
-                for (int r = lane; r < rows; r += 32) {
-                    T x = gp[r], y = gq[r];
-                    alpha += rc_abs2(x);
-                    beta += rc_abs2(y);
-                    // gamma = conj(x) * y
-                    double xr = (double)rc_real(x), xi = (double)rc_imag(x);
-                    double yr = (double)rc_real(y), yi = (double)rc_imag(y);
-                    gre += xr * yr + xi * yi;
-                    gim += xr * yi - xi * yr;
+                if (valid)
+                    for (int r = sl; r < rows; r += LPP) {
+                        T x = gp[r], y = gq[r];
+                        alpha += rc_abs2(x);
+                        beta += rc_abs2(y);
+                        // gamma = conj(x) * y
+                        double xr = (double)rc_real(x), xi = (double)rc_imag(x);
+                        double yr = (double)rc_real(y), yi = (double)rc_imag(y);
+                        gre += xr * yr + xi * yi;
+                        gim += xr * yi - xi * yr;
+                    }
+#pragma unroll
+                for (int m = LPP / 2; m > 0; m >>= 1) {
+                    alpha += __shfl_xor_sync(0xffffffffu, alpha, m);
+                    beta += __shfl_xor_sync(0xffffffffu, beta, m);
+                    gre += __shfl_xor_sync(0xffffffffu, gre, m);
+                    if (ScalarTraits<T>::is_complex) gim += __shfl_xor_sync(0xffffffffu, gim, m);
                 }
-                alpha = rc_warp_sum(alpha); beta = rc_warp_sum(beta);
-                gre = rc_warp_sum(gre); gim = rc_warp_sum(gim);
-                // real scalars: gamma is real, no hypot (a ~200-cycle call at the head of the rotation chain)
-                const double gabs = ScalarTraits<T>::is_complex ? hypot(gre, gim) : fabs(gre);
-                if (gabs == 0.0 || gabs <= tol * sqrt(alpha * beta)) continue;
-                if (lane == 0) s_rot = 1;
-                double zeta = (beta - alpha) / (2.0 * gabs);
-                double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double cs = rsqrt(1.0 + t * t), sn = cs * t;
-                // e^{-i theta} = conj(gamma)/|gamma|
-                double er = gre / gabs, ei = -gim / gabs;
-                T ph = rc_make<T>(er, ei);
-                T csT = rc_make<T>(cs, 0.0), snT = rc_make<T>(sn, 0.0);
-                for (int r = lane; r < rows; r += 32) {
-                    T x = gp[r], y = ph * gq[r];
-                    gp[r] = csT * x - snT * y;
-                    gq[r] = snT * x + csT * y;
-                }
-                T* vp = V + (int64_t)p * n;
-                T* vq = V + (int64_t)q * n;
-                for (int r = lane; r < n; r += 32) {
-                    T x = vp[r], y = ph * vq[r];
-                    vp[r] = csT * x - snT * y;
-                    vq[r] = snT * x + csT * y;
+                // The scalar chain at the head of every rotation is kept to reciprocal square roots and one
+                // reciprocal: no hypot, no divisions, no square root of alpha * beta (the threshold is compared in
+                // squares).  The angle only steers convergence; the rotation is orthogonal because cs and sn are
+                // derived from the same t.
+                const double g2 = gre * gre + gim * gim;
+                if (valid && g2 != 0.0 && g2 > tol2 * alpha * beta) {
+                    if (sl == 0) s_rot = 1;
+                    const double rg = rsqrt(g2);                        // 1 / |gamma|
+                    const double zeta = (beta - alpha) * 0.5 * rg;
+                    const double w1 = 1.0 + zeta * zeta;
+                    const double t = copysign(1.0, zeta) * __drcp_rn(fabs(zeta) + w1 * rsqrt(w1));
+                    const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+                    // e^{-i theta} = conj(gamma)/|gamma|
+                    const double er = gre * rg, ei = -gim * rg;
+                    T ph = rc_make<T>(er, ei);
+                    T csT = rc_make<T>(cs, 0.0), snT = rc_make<T>(sn, 0.0);
+                    for (int r = sl; r < rows; r += LPP) {
+                        T x = gp[r], y = ph * gq[r];
+                        gp[r] = csT * x - snT * y;
+                        gq[r] = snT * x + csT * y;
+                    }
+                    T* vp = V + (int64_t)p * n;
+                    T* vq = V + (int64_t)q * n;
+                    for (int r = sl; r < n; r += LPP) {
+                        T x = vp[r], y = ph * vq[r];
+                        vp[r] = csT * x - snT * y;
+                        vq[r] = snT * x + csT * y;
+                    }
                 }
             }
             __syncthreads();
@@ -90,10 +113,10 @@ jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int max_s
         if (s_rot == 0) break;
         __syncthreads();
     }
-    if (tid == 0) info[0] = (sweep >= max_sweeps) ? 1 : 0;
+    if (tid == 0) { info[0] = (sweep >= max_sweeps) ? 1 : 0; info[1] = sweep; }
     // singular values
     for (int c = warp; c < n; c += JW) {
-        const T* gc = G + (int64_t)c * rows;
+        const T* gc = G + (int64_t)c * ldgg;
         double a = 0.0;
         for (int r = lane; r < rows; r += 32) a += rc_abs2(gc[r]);
         a = rc_warp_sum(a);
@@ -110,7 +133,7 @@ jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int max_s
         }
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, m);
-        const T* gc = G + (int64_t)c * rows;
+        const T* gc = G + (int64_t)c * ldgg;
         const T* vc = V + (int64_t)c * n;
         double inv = (sc > 0.0) ? 1.0 / sc : 0.0;
         T invT = rc_make<T>(inv, 0.0);
@@ -127,20 +150,34 @@ void jacobi_svd(rc_ctx* c, const T* g, int64_t ldg, int64_t rows, int64_t n, T* 
     RC_REQUIRE(n > 0 && n <= 8192 && rows >= n, "jacobi_svd: unsupported size %lld x %lld", (long long)rows, (long long)n);
     DevBuf<T> G(c, (size_t)rows * n), V(c, (size_t)n * n);
     DevBuf<double> sig(c, (size_t)n);
-    DevBuf<int> info(c, 1);
+    DevBuf<int> info(c, 2);
     // column-major copy of g == transpose of the row-major matrix
     k_transpose<T>(c, G.p, rows, g, ldg, rows, n, false);
     double eps = (sizeof(RealOf<T>) == 4) ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
     double tol = eps * sqrt((double)rows);
-    size_t smem = ((size_t)rows * n + (size_t)n * n) * sizeof(T);
+    // column stride of the shared-memory copy: an odd multiple of 64 bytes when the rows would otherwise put every
+    // column on the same banks (the lane groups of a warp work on different columns)
+    const int ldc = (int)((rows * sizeof(T)) % 128 == 0 ? rows + (int64_t)(64 / sizeof(T)) : rows);
+    size_t smem = ((size_t)ldc * n + (size_t)n * n) * sizeof(T);
     size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
-    if (smem + 4096 <= lim) {
-        RC_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        jacobi_kernel<T, true><<<1, JT, smem, c->stream>>>(G.p, V.p, (int)rows, (int)n, 60, tol, u, ldu, s, w, ldw, sig.p, info.p);
-    } else {
-        jacobi_kernel<T, false><<<1, JT, 0, c->stream>>>(G.p, V.p, (int)rows, (int)n, 60, tol, u, ldu, s, w, ldw, sig.p, info.p);
-    }
+    const bool fits = smem + 4096 <= lim;
+    // lanes per column pair: enough pairs per round to keep the 32 warps' worth of lanes busy, but no more lanes than rows
+    const int lpp = (n >= 128 || rows > 256) ? 32 : (n >= 96 ? 16 : 8);
+#define RC_JACOBI(SM, L)                                                                                              \
+    do {                                                                                                              \
+        if (SM) RC_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, SM, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        jacobi_kernel<T, SM, L><<<1, JT, SM ? smem : 0, c->stream>>>(G.p, V.p, (int)rows, (int)n, ldc, 60, tol, u, ldu, s, w, ldw, sig.p, info.p); \
+    } while (0)
+    if (fits) { if (lpp == 8) RC_JACOBI(true, 8); else if (lpp == 16) RC_JACOBI(true, 16); else RC_JACOBI(true, 32); }
+    else { if (lpp == 8) RC_JACOBI(false, 8); else if (lpp == 16) RC_JACOBI(false, 16); else RC_JACOBI(false, 32); }
+#undef RC_JACOBI
     RC_CHECK_LAUNCH(c);
+    if (c->trace) {
+        int h[2] = {0, 0};
+        RC_CUDA(cudaMemcpyAsync(h, info.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        RC_CUDA(cudaStreamSynchronize(c->stream));
+        fprintf(stderr, "[rc trace]     jacobi %lld x %lld: %d sweeps%s\n", (long long)rows, (long long)n, h[1], h[0] ? " (NOT converged)" : "");
+    }
 }
 
 template void jacobi_svd<float>(rc_ctx*, const float*, int64_t, int64_t, int64_t, float*, int64_t, double*, float*, int64_t);
