@@ -52,34 +52,50 @@ chol_inv_kernel(const T* __restrict__ g, int64_t ldg, int w, T* __restrict__ r, 
         const int j0 = kb * NB, jb = min(NB, w - j0);
         // ---- diagonal block: unblocked Cholesky (lane = row), then the inverse of the block (lane = column)
         if (warp == 0) {
-            for (int c = 0; c < jb; ++c) {
-                double d = (double)rc_real(L[(j0 + c) * ld + j0 + c]);
-                if (!(d > 0.0)) { if (lane == 0) s_bad = 1; d = 1.0; }
-                const double rd = rsqrt(d);
-                if (lane >= c && lane < jb) {
-                    T* e = &L[(j0 + lane) * ld + j0 + c];
-                    *e = (lane == c) ? rc_make<T>(d * rd, 0.0) : *e * (R)rd;
-                }
-                if (lane == 0) s_dinv[j0 + c] = rd;
-                __syncwarp();
-                if (lane > c && lane < jb) {
-                    const T lrc = L[(j0 + lane) * ld + j0 + c];
-                    for (int c2 = c + 1; c2 <= lane; ++c2) {
-                        T* e = &L[(j0 + lane) * ld + j0 + c2];
-                        *e = *e - lrc * rc_conj(L[(j0 + c2) * ld + j0 + c]);
+            // The block lives in REGISTERS (lane = row, a[c] = L[row][c]) and rows talk through shuffles: a
+            // read-modify-write loop over shared memory serialises on every store (the compiler must assume that the
+            // next load aliases it), which made this 16-step chain the most expensive part of the kernel.
+            T a[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) a[c] = (lane < jb && c <= lane) ? L[(j0 + lane) * ld + j0 + c] : rc_zero<T>();
+            double dinv_mine = 1.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c < jb) {                                       // warp-uniform
+                    double d = __shfl_sync(0xffffffffu, (double)rc_real(a[c]), c);
+                    const bool bad = !(d > 0.0);
+                    if (bad) d = 1.0;
+                    const double rd = rsqrt(d);
+                    if (lane == c) { a[c] = rc_make<T>(d * rd, 0.0); dinv_mine = rd; if (bad) s_bad = 1; }
+                    else if (lane > c) a[c] = a[c] * (R)rd;
+#pragma unroll
+                    for (int c2 = c + 1; c2 < NB; ++c2) {
+                        if (c2 < jb) {
+                            const T l2c = rc_shfl(a[c], c2);        // L[c2][c]
+                            if (lane >= c2) a[c2] = a[c2] - a[c] * rc_conj(l2c);
+                        }
                     }
                 }
-                __syncwarp();
             }
-            if (lane < jb) {
-                const int c = lane;
-                X[(j0 + c) * ld + j0 + c] = rc_make<T>(s_dinv[j0 + c], 0.0);
-                for (int rr = c + 1; rr < jb; ++rr) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) if (lane < jb && c <= lane) L[(j0 + lane) * ld + j0 + c] = a[c];
+            if (lane < jb) s_dinv[j0 + lane] = dinv_mine;
+            __syncwarp();
+            // inverse of the block, lane = column: x[rr] = -(1 / L_rr) sum_{k < rr} L[rr][k] x[k]  (x[k] = 0 for k < lane)
+            T x[NB];
+#pragma unroll
+            for (int rr = 0; rr < NB; ++rr) {
+                x[rr] = rc_zero<T>();
+                if (rr < jb) {
                     T acc = rc_zero<T>();
-                    for (int k = c; k < rr; ++k) acc = rc_fma(L[(j0 + rr) * ld + j0 + k], X[(j0 + k) * ld + j0 + c], acc);
-                    X[(j0 + rr) * ld + j0 + c] = -(acc * (R)s_dinv[j0 + rr]);
+#pragma unroll
+                    for (int k = 0; k < rr; ++k) acc = rc_fma(L[(j0 + rr) * ld + j0 + k], x[k], acc);
+                    const R dr = (R)s_dinv[j0 + rr];
+                    x[rr] = (rr == lane) ? rc_make<T>((double)dr, 0.0) : ((rr > lane) ? -(acc * dr) : rc_zero<T>());
                 }
             }
+#pragma unroll
+            for (int rr = 0; rr < NB; ++rr) if (lane < jb && rr >= lane && rr < jb) X[(j0 + rr) * ld + j0 + lane] = x[rr];
         }
         __syncthreads();
         const int i0 = j0 + jb, nrow = w - i0;

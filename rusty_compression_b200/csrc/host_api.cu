@@ -268,6 +268,18 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
     return true;
 }
 
+// Pivoted QR of the small w x w factor of a tall panel (row-major `rf`): R (into r), pivots (dind) and the first ncq
+// columns of its orthogonal factor (q1, row-major).  One fused kernel when the factor fits it (pivqr.cu), else
+// transpose -> cooperative / one-CTA factorisation -> form Q.
+template <class T>
+void small_pivqr(rc_ctx* c, const T* rf, int64_t ldrf, int64_t w, int64_t ncq, rc_matrix* r, int* dind, T* q1, int64_t ldq1,
+                 DevBuf<T>& wc, DevBuf<T>& vbuf, DevBuf<T>& tau) {
+    if (pivqr_fused<T>(c, rf, ldrf, 0, w, w, ncq, P<T>(r), r->ld, dind, q1, ldq1)) return;
+    k_transpose<T>(c, wc.p, w, rf, ldrf, w, w, false);          // column-major copy = transpose of the row-major factor
+    pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r), r->ld, dind, vbuf.p, tau.p);
+    pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1, ldq1);
+}
+
 // Tall-skinny route: Y = Q0 R0 by (distributed) Householder TSQR, pivoting on R0, Q = Q0 Q1.
 // Panels wider than the shared-memory limit are orthogonalised block by block against the
 // previous panels (two projection passes) before their own TSQR.
@@ -287,9 +299,7 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
     if (cholqr2<T>(c, y, ldy, m, w, sharded, dtype, cq1, crinv2, crfac, lds)) {
         rc_trace(c, "pqr_tall: cholqr2");
         // pivot on R = R2 R1, then Q = q1 (R2^{-1} Q1piv)
-        k_transpose<T>(c, wc.p, w, crfac.p, lds, w, w, false);
-        pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
-        pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1.p, ncq);
+        small_pivqr<T>(c, crfac.p, lds, w, ncq, r.get(), dind.p, q1.p, ncq, wc, vbuf, tau);
         DevBuf<T> tq(c, (size_t)w * rc_pad_ld(dtype, ncq));
         const int64_t ldtq = rc_pad_ld(dtype, ncq);
         gemm<T>(c, RC_OP_N, RC_OP_N, w, ncq, w, crinv2.p, lds, q1.p, ncq, tq.p, ldtq, rc_one<T>(), rc_zero<T>());
@@ -297,10 +307,7 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
     } else if (w <= wmax) {
         DistTsqr<T> ts;
         ts.factor(c, y, ldy, m, w, sharded);
-        // column-major copy of R0 = transpose of the row-major factor
-        k_transpose<T>(c, wc.p, w, ts.r(), w, w, w, false);
-        pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
-        pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1.p, ncq);
+        small_pivqr<T>(c, ts.r(), w, w, ncq, r.get(), dind.p, q1.p, ncq, wc, vbuf, tau);
         ts.apply(q1.p, ncq, ncq, P<T>(q.get()), q->ld);
     } else {
         // Panels of at most min(wmax, Cholesky width) columns.  Each panel is orthogonalised against the
@@ -351,12 +358,10 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
                 ts.apply(eye.p, cw, cw, qfull.p + c0, ldq);
             }
         }
-        k_transpose<T>(c, wc.p, w, r0.p, w, w, w, false);
-        pivqr_factor<T>(c, wc.p, w, w, w, P<T>(r.get()), r->ld, dind.p, vbuf.p, tau.p);
-        rc_trace(c, "pqr_tall: pivoted QR of R");
         const int64_t ldq1 = rc_pad_ld(dtype, ncq);
         DevBuf<T> q1p(c, (size_t)w * ldq1);
-        pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1p.p, ldq1);
+        small_pivqr<T>(c, r0.p, w, w, ncq, r.get(), dind.p, q1p.p, ldq1, wc, vbuf, tau);
+        rc_trace(c, "pqr_tall: pivoted QR of R");
         gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, qfull.p, ldq, q1p.p, ldq1, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
         rc_trace(c, "pqr_tall: form Q1, Q = Qfull Q1");
     }
@@ -422,6 +427,18 @@ void pivoted_qr_impl(rc_ctx* c, const rc_matrix* arr, bool input_is_conj_transpo
         return;
     }
     RC_REQUIRE(!sharded, "pivoted_qr: a row-sharded matrix must be tall (rows >= cols)");
+    // ---- small general matrices: the fused one-CTA kernel reads the input as it is (row-major or conj-transposed)
+    if (p * n <= 65536) {
+        MatPtr r(mat_new(c, dtype, kk, n)), q(mat_new(c, dtype, p, ncq));
+        DevBuf<int> dind(c, (size_t)n);
+        if (pivqr_fused<T>(c, P<T>(arr), arr->ld, input_is_conj_transposed ? 2 : 0, p, n, ncq, P<T>(r.get()), r->ld, dind.p,
+                           P<T>(q.get()), q->ld)) {
+            if (out.want_ind) download_ind(c, dind.p, n, out.ind);
+            out.q.reset(q.release());
+            out.r.reset(r.release());
+            return;
+        }
+    }
     // ---- general / short-wide: cooperative pivoted Householder on a column-major copy
     DevBuf<T> wc(c, (size_t)p * n);
     if (input_is_conj_transposed) {
@@ -1037,6 +1054,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
         else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;
         else if (!strcmp(key, "pivot_precision")) c->pivot_f64 = (v != 0);
         else if (!strcmp(key, "speculate")) c->speculate = (int)v;
+        else if (!strcmp(key, "fused_small_qr")) c->fused_small_qr = (int)v;
         else if (!strcmp(key, "overlap")) c->overlap = (int)v;
         else if (!strcmp(key, "reuse_range_b")) c->reuse_range_b = (int)v;
         else if (!strcmp(key, "trace")) c->trace = (int)v;

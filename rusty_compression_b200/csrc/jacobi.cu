@@ -10,8 +10,7 @@
 
 namespace {
 
-constexpr int JT = 1024;
-constexpr int JW = JT / 32;
+constexpr int JT = 512;            // at most 16 warps (128 registers per thread: the register tiles of a pair)
 
 // LPP lanes share a column pair, so a warp rotates 32 / LPP pairs at once.  A round is ISSUE-bound, not latency-bound:
 // with one pair per warp every one of the 32 lanes executed the ~150-instruction scalar chain of its pair redundantly
@@ -25,17 +24,18 @@ jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int ldg, 
     __shared__ int s_rot;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = blockDim.x, JW = NT >> 5;
     // SMEM: G (rows x n, column stride ldg) and V (n x n) are resident in shared memory for the whole iteration
     T* G = SMEM ? reinterpret_cast<T*>(smem_raw) : Gg;
     T* V = SMEM ? G + (size_t)ldg * n : Vg;
     const int ldgg = SMEM ? ldg : rows;             // the global copy is dense
     if (SMEM) {
-        for (int e = tid; e < rows * n; e += JT) { int c = e / rows, r = e - c * rows; G[(size_t)c * ldg + r] = Gg[e]; }
+        for (int e = tid; e < rows * n; e += NT) { int c = e / rows, r = e - c * rows; G[(size_t)c * ldg + r] = Gg[e]; }
     }
     const int npad = n + (n & 1);
     const int half = npad / 2;
     // V = I
-    for (int e = tid; e < n * n; e += JT) {
+    for (int e = tid; e < n * n; e += NT) {
         int c = e / n, r = e - c * n;
         V[e] = (r == c) ? rc_one<T>() : rc_zero<T>();
     }
@@ -59,8 +59,35 @@ jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int ldg, 
                 const bool valid = (k < half) && (q < n);                   // q == n: padding column of an odd n
                 T* gp = G + (int64_t)(valid ? p : 0) * ldgg;
                 T* gq = G + (int64_t)(valid ? q : 0) * ldgg;
+                T* vp = V + (int64_t)(valid ? p : 0) * n;
+                T* vq = V + (int64_t)(valid ? q : 0) * n;
                 double alpha = 0.0, beta = 0.0, gre = 0.0, gim = 0.0;
-                if (valid)
+                // Register tile: each lane's share of the two columns (of G and of V) is loaded ONCE, up front, and
+                // stored once at the end.  A load-rotate-store loop over shared memory serialises on its own stores
+                // (the next iteration's loads may alias them), which tripled the length of a round.
+                constexpr int RPL = ScalarTraits<T>::is_complex ? 4 : 8;
+                const bool tiled = (rows <= RPL * LPP) && (n <= RPL * LPP);
+                T xg[RPL], yg[RPL], xv[RPL], yv[RPL];
+                if (tiled) {
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u) {
+                        const int r = sl + u * LPP;
+                        const bool in = valid && r < rows, inv = valid && r < n;
+                        xg[u] = in ? gp[r] : rc_zero<T>();
+                        yg[u] = in ? gq[r] : rc_zero<T>();
+                        xv[u] = inv ? vp[r] : rc_zero<T>();
+                        yv[u] = inv ? vq[r] : rc_zero<T>();
+                    }
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u) {
+                        alpha += rc_abs2(xg[u]);
+                        beta += rc_abs2(yg[u]);
+                        const double xr = (double)rc_real(xg[u]), xi = (double)rc_imag(xg[u]);
+                        const double yr = (double)rc_real(yg[u]), yi = (double)rc_imag(yg[u]);
+                        gre += xr * yr + xi * yi;
+                        gim += xr * yi - xi * yr;
+                    }
+                } else if (valid) {
                     for (int r = sl; r < rows; r += LPP) {
                         T x = gp[r], y = gq[r];
                         alpha += rc_abs2(x);
@@ -71,6 +98,7 @@ jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int ldg, 
                         gre += xr * yr + xi * yi;
                         gim += xr * yi - xi * yr;
                     }
+                }
 #pragma unroll
                 for (int m = LPP / 2; m > 0; m >>= 1) {
                     alpha += __shfl_xor_sync(0xffffffffu, alpha, m);
@@ -94,17 +122,32 @@ jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int ldg, 
                     const double er = gre * rg, ei = -gim * rg;
                     T ph = rc_make<T>(er, ei);
                     T csT = rc_make<T>(cs, 0.0), snT = rc_make<T>(sn, 0.0);
-                    for (int r = sl; r < rows; r += LPP) {
-                        T x = gp[r], y = ph * gq[r];
-                        gp[r] = csT * x - snT * y;
-                        gq[r] = snT * x + csT * y;
-                    }
-                    T* vp = V + (int64_t)p * n;
-                    T* vq = V + (int64_t)q * n;
-                    for (int r = sl; r < n; r += LPP) {
-                        T x = vp[r], y = ph * vq[r];
-                        vp[r] = csT * x - snT * y;
-                        vq[r] = snT * x + csT * y;
+                    if (tiled) {
+#pragma unroll
+                        for (int u = 0; u < RPL; ++u) {
+                            const int r = sl + u * LPP;
+                            if (r < rows) {
+                                const T y = ph * yg[u];
+                                gp[r] = csT * xg[u] - snT * y;
+                                gq[r] = snT * xg[u] + csT * y;
+                            }
+                            if (r < n) {
+                                const T y = ph * yv[u];
+                                vp[r] = csT * xv[u] - snT * y;
+                                vq[r] = snT * xv[u] + csT * y;
+                            }
+                        }
+                    } else {
+                        for (int r = sl; r < rows; r += LPP) {
+                            T x = gp[r], y = ph * gq[r];
+                            gp[r] = csT * x - snT * y;
+                            gq[r] = snT * x + csT * y;
+                        }
+                        for (int r = sl; r < n; r += LPP) {
+                            T x = vp[r], y = ph * vq[r];
+                            vp[r] = csT * x - snT * y;
+                            vq[r] = snT * x + csT * y;
+                        }
                     }
                 }
             }
@@ -161,12 +204,16 @@ void jacobi_svd(rc_ctx* c, const T* g, int64_t ldg, int64_t rows, int64_t n, T* 
     size_t smem = ((size_t)ldc * n + (size_t)n * n) * sizeof(T);
     size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
     const bool fits = smem + 4096 <= lim;
-    // lanes per column pair: enough pairs per round to keep the 32 warps' worth of lanes busy, but no more lanes than rows
-    const int lpp = (n >= 128 || rows > 256) ? 32 : (n >= 96 ? 16 : 8);
+    // lanes per column pair: the fewest that still hold a pair's share of G and V in the register tile of the kernel
+    // (8 rows per lane, 4 for complex scalars); a warp rotates 32 / lpp pairs at once
+    const int rpl = ScalarTraits<T>::is_complex ? 4 : 8;
+    const int lpp = (rows <= 8 * rpl) ? 8 : ((rows <= 16 * rpl) ? 16 : 32);
+    const int half = (int)((n + 1) / 2);
+    const int nthreads = std::min(JT, std::max(64, 32 * ((half + 32 / lpp - 1) / (32 / lpp))));
 #define RC_JACOBI(SM, L)                                                                                              \
     do {                                                                                                              \
         if (SM) RC_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, SM, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        jacobi_kernel<T, SM, L><<<1, JT, SM ? smem : 0, c->stream>>>(G.p, V.p, (int)rows, (int)n, ldc, 60, tol, u, ldu, s, w, ldw, sig.p, info.p); \
+        jacobi_kernel<T, SM, L><<<1, nthreads, SM ? smem : 0, c->stream>>>(G.p, V.p, (int)rows, (int)n, ldc, 60, tol, u, ldu, s, w, ldw, sig.p, info.p); \
     } while (0)
     if (fits) { if (lpp == 8) RC_JACOBI(true, 8); else if (lpp == 16) RC_JACOBI(true, 16); else RC_JACOBI(true, 32); }
     else { if (lpp == 8) RC_JACOBI(false, 8); else if (lpp == 16) RC_JACOBI(false, 16); else RC_JACOBI(false, 32); }

@@ -457,6 +457,232 @@ pivqr_small_kernel(T* __restrict__ Wg, int64_t ldwg, int p, int n, int kk, int* 
     for (int e = tid; e < p * n; e += NT) { int c = e / p, r = e - c * p; Wg[(int64_t)c * ldwg + r] = W[e]; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small factors, fused: pivoted QR + R + Q in ONE kernel (one CTA), for the l x l triangles of the tall sketches --
+// the chain that sits on the critical path of every tall pivoted QR (it used to be transpose -> pivqr_small_kernel ->
+// gather_r_kernel -> form_q_kernel -> transpose: ~285 us for 74 x 74 f64).  What changed against pivqr_small_kernel:
+//   * ONE block barrier per step.  Every warp reduces the per-warp candidates itself and derives the reflector
+//     scalars redundantly (the candidate carries the trailing norm of its column AND the norm below the diagonal, so
+//     ?larfg needs no pass over the pivot column); there is no serial warp-0 phase and no second barrier.
+//   * the logical position of a column is kept by the lane group that owns the column (registers), so the swap
+//     bookkeeping of ?geqp3 needs no cross-thread traffic; tie-breaks are unchanged (first maximum in swap order).
+//   * a lane's share of its column is loaded into registers once per step, updated there and stored once: a
+//     read-modify-write loop over shared memory serialises on its own stores (possible aliasing), which is what made
+//     the old update phase latency-bound.
+//   * reflectors stay in shared memory; Q = H_0 ... H_{kk-1} I[:, :ncq] is formed by the same lane groups without a
+//     single barrier (columns are independent), R and Q leave the kernel row-major in the caller's precision.
+// Tin: storage type at the boundary; T: arithmetic type (double / c64 for f32 / c32 inputs when pivot decisions are
+// taken in double, rc_ctx::pivot_f64).  LPC lanes per column; RPL rows per lane (p <= LPC * RPL).
+struct __align__(16) CandF {
+    double val;    // norm of rows i .. p-1 of the column (the pivot criterion)
+    double xn2;    // squared norm of rows i+1 .. p-1 (?larfg's xnorm^2)
+    int lpos, phys;
+    int pad0, pad1;
+};
+__device__ __forceinline__ bool betterF(const CandF& a, const CandF& b) {
+    if (a.phys < 0) return false;
+    if (b.phys < 0) return true;
+    if (a.val != b.val) return a.val > b.val;
+    return a.lpos < b.lpos;
+}
+__device__ __forceinline__ CandF shflF(const CandF& c, int m) {
+    CandF o;
+    o.val = __shfl_xor_sync(0xffffffffu, c.val, m);
+    o.xn2 = __shfl_xor_sync(0xffffffffu, c.xn2, m);
+    o.lpos = __shfl_xor_sync(0xffffffffu, c.lpos, m);
+    o.phys = __shfl_xor_sync(0xffffffffu, c.phys, m);
+    return o;
+}
+// ?larfg without divisions or square roots on the critical path: one rsqrt and one reciprocal
+template <class T>
+__device__ __forceinline__ void larfg_fast(T alpha, double xnorm2, T& tau, T& scale, T& beta) {
+    const double ar = (double)rc_real(alpha), ai = (double)rc_imag(alpha);
+    if (xnorm2 == 0.0 && ai == 0.0) { tau = rc_zero<T>(); scale = rc_zero<T>(); beta = alpha; return; }
+    const double s2 = ar * ar + ai * ai + xnorm2;
+    const double rs = rsqrt(s2);
+    const double b = -copysign(s2 * rs, ar), ib = -copysign(rs, ar);           // beta and 1 / beta
+    const double dr = ar - b, di = ai;
+    const double inv = __drcp_rn(dr * dr + di * di);
+    tau = rc_make<T>((b - ar) * ib, -ai * ib);
+    scale = rc_make<T>(dr * inv, -di * inv);
+    beta = rc_make<T>(b, 0.0);
+}
+template <class D, class S> __device__ __forceinline__ D cast_scalar(S v) { return rc_make<D>((double)rc_real(v), (double)rc_imag(v)); }
+
+constexpr int FQ_NT = 512;          // 128 registers per thread for the column tiles
+constexpr int FQ_MAXP = 2;          // columns per lane group
+
+template <class Tin, class T, int LPC, int RPL>
+__global__ void __launch_bounds__(FQ_NT)
+pivqr_fused_kernel(const Tin* __restrict__ in, int64_t ldin, int mode, int p, int n, int kk, int ncq,
+                   int* __restrict__ ind, Tin* __restrict__ rout, int64_t ldr, Tin* __restrict__ qout, int64_t ldq) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* W = reinterpret_cast<T*>(smem_raw);                 // p x n column-major (later: Q, p x ncq)
+    T* V = W + (size_t)p * n;                              // p x kk reflectors, column-major
+    T* s_tau = V + (size_t)p * kk;                         // kk
+    T* s_diag = s_tau + kk;                                // kk
+    int* s_pos2col = reinterpret_cast<int*>(s_diag + kk);  // n
+    __shared__ CandF s_cand[2][FQ_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = blockDim.x, NW = NT >> 5, NG = NT / LPC;
+    const int g = tid / LPC, sl = tid % LPC;
+    // ---- load: mode 0 = `in` is p x n row-major, 1 = p x n column-major, 2 = `in` holds S (n x p row-major), M = S^H
+    for (int e = tid; e < p * n; e += NT) {
+        int rr, cc;
+        T v;
+        if (mode == 0) { rr = e / n; cc = e - rr * n; v = cast_scalar<T>(in[(int64_t)rr * ldin + cc]); }
+        else if (mode == 1) { cc = e / p; rr = e - cc * p; v = cast_scalar<T>(in[(int64_t)cc * ldin + rr]); }
+        else { cc = e / p; rr = e - cc * p; v = rc_conj(cast_scalar<T>(in[(int64_t)cc * ldin + rr])); }
+        W[rr + (size_t)cc * p] = v;
+    }
+    __syncthreads();
+    // ---- per-column state of this lane group: logical position (swap order of ?geqp3), pivoted flag, norms
+    int lp[FQ_MAXP];
+    bool alive[FQ_MAXP];
+    double vn[FQ_MAXP], xn2[FQ_MAXP];
+#pragma unroll
+    for (int ps = 0; ps < FQ_MAXP; ++ps) {
+        const int c = g + ps * NG;
+        lp[ps] = c; alive[ps] = c < n; vn[ps] = 0.0; xn2[ps] = 0.0;
+        double rest = 0.0, first = 0.0;
+        if (c < n)
+            for (int r = sl; r < p; r += LPC) { const double a2 = rc_abs2(W[r + (size_t)c * p]); if (r == 0) first = a2; else rest += a2; }
+#pragma unroll
+        for (int m = LPC / 2; m > 0; m >>= 1) { rest += __shfl_xor_sync(0xffffffffu, rest, m); first += __shfl_xor_sync(0xffffffffu, first, m); }
+        vn[ps] = sqrt(rest + first); xn2[ps] = rest;
+    }
+    auto publish = [&](int buf) {
+        CandF best; best.val = -1.0; best.xn2 = 0.0; best.lpos = 0x7fffffff; best.phys = -1; best.pad0 = best.pad1 = 0;
+#pragma unroll
+        for (int ps = 0; ps < FQ_MAXP; ++ps)
+            if (alive[ps]) {
+                CandF cd; cd.val = vn[ps]; cd.xn2 = xn2[ps]; cd.lpos = lp[ps]; cd.phys = g + ps * NG; cd.pad0 = cd.pad1 = 0;
+                if (betterF(cd, best)) best = cd;
+            }
+#pragma unroll
+        for (int m = LPC; m < 32; m <<= 1) { CandF o = shflF(best, m); if (betterF(o, best)) best = o; }
+        if (lane == 0) s_cand[buf][warp] = best;
+    };
+    publish(0);
+    __syncthreads();
+    for (int i = 0; i < kk; ++i) {
+        // ---- winner (every warp, redundantly)
+        CandF win; win.val = -1.0; win.xn2 = 0.0; win.lpos = 0x7fffffff; win.phys = -1; win.pad0 = win.pad1 = 0;
+        if (lane < NW) win = s_cand[i & 1][lane];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) { CandF o = shflF(win, m); if (betterF(o, win)) win = o; }
+        const int pv = win.phys;          // < 0: every candidate norm is NaN (speculative run on garbage): no reflector
+        T tau = rc_zero<T>(), scale = rc_zero<T>(), beta = rc_zero<T>();
+        const T* pcol = W + (size_t)(pv >= 0 ? pv : 0) * p;
+        if (pv >= 0) larfg_fast<T>(pcol[i], (i == p - 1) ? 0.0 : win.xn2, tau, scale, beta);
+        if (warp == 0) {
+            for (int r = lane; r < p; r += 32) V[r + (size_t)i * p] = (r < i) ? rc_zero<T>() : (r == i ? rc_one<T>() : pcol[r] * scale);
+            if (lane == 0) { s_tau[i] = tau; s_diag[i] = beta; }
+        }
+        const T ctau = rc_conj(tau);
+        // ---- own columns: bookkeeping of the swap, trailing update in registers, new norms
+#pragma unroll
+        for (int ps = 0; ps < FQ_MAXP; ++ps) {
+            const int c = g + ps * NG;
+            if (c < n) {
+                if (pv < 0) { if (lp[ps] == i) alive[ps] = false; }
+                else if (c == pv) { lp[ps] = i; alive[ps] = false; }
+                else if (lp[ps] == i) lp[ps] = win.lpos;
+            }
+            const bool act = alive[ps] && pv >= 0;
+            T* col = W + (size_t)(c < n ? c : 0) * p;
+            // rows i+1 .. p-1 in strides of LPC: only the first `nu` tile slots are live at this step (warp-uniform)
+            const int nu = (p - i - 1 + LPC - 1) / LPC;
+            T tile[RPL], vt[RPL];
+            T part = rc_zero<T>();
+#pragma unroll
+            for (int u = 0; u < RPL; ++u) {
+                if (u < nu) {
+                    const int r = i + 1 + sl + u * LPC;
+                    const bool in = act && r < p;
+                    tile[u] = in ? col[r] : rc_zero<T>();
+                    vt[u] = in ? pcol[r] * scale : rc_zero<T>();
+                    part = rc_cfma(vt[u], tile[u], part);
+                }
+            }
+#pragma unroll
+            for (int m = LPC / 2; m > 0; m >>= 1) part = part + rc_shfl_xor(part, m);
+            const T ci = act ? col[i] : rc_zero<T>();
+            const T f = ctau * (ci + part);
+            double rest = 0.0, first = 0.0;
+#pragma unroll
+            for (int u = 0; u < RPL; ++u) {
+                if (u < nu) {
+                    const int r = i + 1 + sl + u * LPC;
+                    tile[u] = tile[u] - f * vt[u];
+                    const double a2 = rc_abs2(tile[u]);
+                    if (u == 0 && sl == 0) first = a2; else rest += a2;
+                    if (act && r < p) col[r] = tile[u];
+                }
+            }
+#pragma unroll
+            for (int m = LPC / 2; m > 0; m >>= 1) { rest += __shfl_xor_sync(0xffffffffu, rest, m); first += __shfl_xor_sync(0xffffffffu, first, m); }
+            if (act) {
+                if (sl == 0) col[i] = ci - f;
+                vn[ps] = sqrt(rest + first); xn2[ps] = rest;
+            }
+        }
+        publish((i + 1) & 1);
+        __syncthreads();                                   // the one barrier of the step
+    }
+    // ---- pivot vector and the position -> column map
+#pragma unroll
+    for (int ps = 0; ps < FQ_MAXP; ++ps) {
+        const int c = g + ps * NG;
+        if (c < n && sl == 0) { const int l = min(max(lp[ps], 0), n - 1); ind[l] = c; s_pos2col[l] = c; }
+    }
+    __syncthreads();
+    // ---- R (kk x n, row-major): column j of R is the column that ended at logical position j
+    for (int e = tid; e < kk * n; e += NT) {
+        const int row = e / n, j = e - row * n;
+        T v;
+        if (row > j) v = rc_zero<T>();
+        else if (row == j) v = s_diag[row];
+        else v = W[row + (size_t)s_pos2col[j] * p];
+        rout[(int64_t)row * ldr + j] = cast_scalar<Tin>(v);
+    }
+    if (ncq <= 0) return;
+    __syncthreads();
+    // ---- Q = H_0 ... H_{kk-1} I[:, :ncq], column by column in registers (no barriers: columns are independent)
+#pragma unroll
+    for (int ps = 0; ps < FQ_MAXP; ++ps) {
+        const int c = g + ps * NG;
+        const bool act = c < ncq;
+        T tile[RPL];
+#pragma unroll
+        for (int u = 0; u < RPL; ++u) { const int r = sl + u * LPC; tile[u] = (act && r == c) ? rc_one<T>() : rc_zero<T>(); }
+        // e_c is untouched by the reflectors j > c (zeros from row j on).  The trip count is the same for the whole warp
+        // (the shuffles need every lane): the largest column of the warp's lane groups decides, the others idle.
+        const int cmax = (warp * 32 + 31) / LPC + ps * NG;
+        for (int j = min(cmax, kk - 1); j >= 0; --j) {
+            const bool on = act && j <= c;
+            const T* v = V + (size_t)j * p;
+            const int u0 = j / LPC, u1 = (p + LPC - 1) / LPC;          // live tile slots: rows j .. p-1 (warp-uniform)
+            T part = rc_zero<T>(), vr[RPL];
+#pragma unroll
+            for (int u = 0; u < RPL; ++u)
+                if (u >= u0 && u < u1) {
+                    const int r = sl + u * LPC;
+                    vr[u] = (on && r >= j && r < p) ? v[r] : rc_zero<T>();
+                    part = rc_cfma(vr[u], tile[u], part);
+                }
+#pragma unroll
+            for (int m = LPC / 2; m > 0; m >>= 1) part = part + rc_shfl_xor(part, m);
+            const T f = s_tau[j] * part;
+#pragma unroll
+            for (int u = 0; u < RPL; ++u)
+                if (u >= u0 && u < u1) tile[u] = tile[u] - f * vr[u];
+        }
+#pragma unroll
+        for (int u = 0; u < RPL; ++u) { const int r = sl + u * LPC; if (act && r < p) qout[(int64_t)r * ldq + c] = cast_scalar<Tin>(tile[u]); }
+    }
+}
+
 // r (kk x n row-major) from the factored column-major W, logical order `ind`.
 template <class T>
 __global__ void gather_r_kernel(const T* __restrict__ W, int64_t ldw, int kk, int n, const int* __restrict__ ind,
@@ -587,6 +813,43 @@ void pivqr_factor(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int
     pivqr_factor_native<T>(c, wc, ldw, p, n, r, ldr, ind, vbuf, tau);
 }
 
+// Fused small-factor route (pivqr_fused_kernel): false when the shape does not fit it.
+template <class Tin, class T>
+static bool pivqr_fused_launch(rc_ctx* c, const Tin* in, int64_t ldin, int mode, int64_t p, int64_t n, int64_t ncq,
+                               Tin* r, int64_t ldr, int* ind, Tin* q, int64_t ldq) {
+    const int64_t kk = std::min(p, n);
+    constexpr int lpc = 8;
+    if (p > 8 * 20 || n > (FQ_NT / lpc) * FQ_MAXP || ncq > kk) return false;
+    size_t smem = ((size_t)p * n + (size_t)p * kk + 2 * (size_t)kk) * sizeof(T) + (size_t)n * sizeof(int) + 64;
+    size_t lim = c->smem_optin ? c->smem_optin : (size_t)227 * 1024;
+    if (smem + 4096 > lim) return false;
+    // threads: one lane group per column when that fits (multiple of a warp), else FQ_MAXP columns per group
+    int64_t groups = n <= FQ_NT / lpc ? n : (n + FQ_MAXP - 1) / FQ_MAXP;
+    int nt = (int)std::min<int64_t>(FQ_NT, (groups * lpc + 31) / 32 * 32);
+    int pi = (int)p, ni = (int)n, kki = (int)kk, ncqi = (int)ncq;
+    if (p <= 8 * 10) {
+        RC_CUDA(cudaFuncSetAttribute(pivqr_fused_kernel<Tin, T, 8, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pivqr_fused_kernel<Tin, T, 8, 10><<<1, nt, smem, c->stream>>>(in, ldin, mode, pi, ni, kki, ncqi, ind, r, ldr, q, ldq);
+    } else {
+        RC_CUDA(cudaFuncSetAttribute(pivqr_fused_kernel<Tin, T, 8, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pivqr_fused_kernel<Tin, T, 8, 20><<<1, nt, smem, c->stream>>>(in, ldin, mode, pi, ni, kki, ncqi, ind, r, ldr, q, ldq);
+    }
+    RC_CHECK_LAUNCH(c);
+    return true;
+}
+// in: mode 0 = p x n row-major (ldin), 1 = p x n column-major, 2 = S (n x p row-major) with M = S^H.
+// r: kk x n row-major; q: p x ncq row-major; ind: n.  Returns false when the shape needs the general route.
+template <class T>
+bool pivqr_fused(rc_ctx* c, const T* in, int64_t ldin, int mode, int64_t p, int64_t n, int64_t ncq,
+                 T* r, int64_t ldr, int* ind, T* q, int64_t ldq) {
+    if (c->fused_small_qr == 0) return false;        // option "fused_small_qr" = 0: the unfused kernels (A/B, tests)
+    using W = typename AccOf<T>::type;
+    if constexpr (!std::is_same<T, W>::value) {
+        if (c->pivot_f64) return pivqr_fused_launch<T, W>(c, in, ldin, mode, p, n, ncq, r, ldr, ind, q, ldq);
+    }
+    return pivqr_fused_launch<T, T>(c, in, ldin, mode, p, n, ncq, r, ldr, ind, q, ldq);
+}
+
 template <class T>
 void pivqr_form_q(rc_ctx* c, const T* vbuf, const T* tau, int64_t p, int64_t kk, int64_t nc, T* q, int64_t ldq) {
     if (nc == 0) return;
@@ -600,6 +863,7 @@ void pivqr_form_q(rc_ctx* c, const T* vbuf, const T* tau, int64_t p, int64_t kk,
 }
 
 #define INST(T)                                                                                         \
+    template bool pivqr_fused<T>(rc_ctx*, const T*, int64_t, int, int64_t, int64_t, int64_t, T*, int64_t, int*, T*, int64_t); \
     template void pivqr_factor<T>(rc_ctx*, T*, int64_t, int64_t, int64_t, T*, int64_t, int*, T*, T*);    \
     template void pivqr_form_q<T>(rc_ctx*, const T*, const T*, int64_t, int64_t, int64_t, T*, int64_t);
 INST(float)

@@ -57,6 +57,7 @@ struct rc_ctx {
     // Speculative execution (host_api.cu, DeferScope): inside a deferred region the Cholesky-QR2 panels do not read
     // their status words back (no host synchronisation in the middle of a pipeline); the words are collected here and
     // checked once at the end, and a failed check re-runs the region with the Householder TSQR forced.
+    int fused_small_qr = 1;       // option "fused_small_qr": small pivoted QRs in the fused one-CTA kernel (pivqr.cu)
     int speculate = 1;            // option "speculate"
     int overlap = 1;              // option "overlap": independent stages on auxiliary streams
     int defer_depth = 0;
@@ -240,6 +241,12 @@ int64_t tsqr_max_width(rc_ctx*, int dtype);
 template <class T>
 void pivqr_factor(rc_ctx*, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int64_t ldr, int* ind,
                   T* vbuf, T* tau);
+// Fused small-factor route: pivoted QR of M (p x n) with R (kk x n row-major) and Q[:, :ncq] (p x ncq row-major) out of
+// one kernel.  `in`: mode 0 = M row-major (ldin), 1 = M column-major, 2 = S (n x p row-major) with M = S^H.
+// Returns false when the shape does not fit (caller uses pivqr_factor + pivqr_form_q).
+template <class T>
+bool pivqr_fused(rc_ctx*, const T* in, int64_t ldin, int mode, int64_t p, int64_t n, int64_t ncq,
+                 T* r, int64_t ldr, int* ind, T* q, int64_t ldq);
 // q (p x nc row-major, ldq) = H_0 ... H_{kk-1} * I[:, :nc]
 template <class T>
 void pivqr_form_q(rc_ctx*, const T* vbuf, const T* tau, int64_t p, int64_t kk, int64_t nc, T* q, int64_t ldq);

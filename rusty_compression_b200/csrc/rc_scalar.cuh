@@ -120,6 +120,11 @@ __device__ __forceinline__ double rc_shfl_xor(double v, int m) { return __shfl_x
 template <class R> __device__ __forceinline__ Cx<R> rc_shfl_xor(Cx<R> v, int m) {
     return Cx<R>(__shfl_xor_sync(0xffffffffu, v.re, m), __shfl_xor_sync(0xffffffffu, v.im, m));
 }
+__device__ __forceinline__ float  rc_shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double rc_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <class R> __device__ __forceinline__ Cx<R> rc_shfl(Cx<R> v, int src) {
+    return Cx<R>(__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src));
+}
 template <class T> __device__ __forceinline__ T rc_warp_sum(T v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v = v + rc_shfl_xor(v, m);
