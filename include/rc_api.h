@@ -82,6 +82,8 @@ const char* rc_last_error_string(rc_ctx* ctx);
  * "true_power_iteration" (0 = reference semantics incl. quirk Q1, 1 = textbook iteration),
  * "qr_mode" (0 = Cholesky-QR2 fast path for well-conditioned tall panels with automatic
  * fallback to Householder TSQR, 1 = Householder TSQR always),
+ * "f32_precision" (0, the default = f32 / c32 contractions as a 3-product TF32 split on tcgen05, f32-accurate; 1 = the
+ * caller opts in to ONE bf16 product per contraction, tcgen05 kind::f16 with FP32 accumulation: ~3e-3 relative),
  * "pivot_precision" (1, the default = pivot decisions on f32 / c32 inputs are taken in double precision -- the sequence
  * ?geqp3 picks in double on the same single-precision data; 0 = working precision),
  * "reuse_range_b" (1 = compute_from_range_estimate reuses the B = Q^H A the adaptive sampler built),

@@ -20,6 +20,12 @@
 // X is tiny (n x l): it is transposed and split once by a prologue kernel so that both B operands
 // are K-major TMA tiles.
 //
+// PREC = 1 (context option "f32_precision" = 1, opt-in): ONE product in bf16 -- the splitter rounds the raw f32 tile to
+// bf16 pairs (cvt.rn.bf16x2.f32) on its way into tensor memory, X^T is pre-rounded to bf16 tiles (64-byte rows,
+// SWIZZLE_64B), the MMAs are tcgen05.mma kind::f16 (two K = 16 steps per k-block instead of twelve kind::tf32 ones),
+// FP32 accumulation and promotion as before.  Same rings, same pass over A: it pays where the TF32 split is
+// tensor-bound (l > ~100); relative accuracy ~3e-3 instead of ~1e-6, which is why it is never the default.
+//
 // TRANS mode (Z = A^T Y, reduction over the rows of A, split-K with a fixed-order reduction): the
 // raw tile arrives as four [32 k][32 i] boxes and the splitter transposes it through registers while
 // splitting, so the MMA still sees a K-major A (an MN-major descriptor variant produced all-zero
@@ -65,6 +71,21 @@ CUtensorMap make_map_f32(const float* base, int64_t rows, int64_t cols, int64_t 
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RC_THROW(RC_CUDA_ERROR, "cuTensorMapEncodeTiled (f32) failed (%d)", (int)r);
+    return m;
+}
+
+// Row-major [rows][cols] bf16 matrix (the pre-rounded X^T), box = 32 cols (64 B) x box_rows, SWIZZLE_64B.
+CUtensorMap make_map_bf16(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    RC_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map box rows out of range");
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RC_THROW(RC_CUDA_ERROR, "cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r);
     return m;
 }
 
@@ -131,6 +152,32 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// instruction descriptor: D = F32, A = B = BF16 (both K-major), M = 128, N = n   (kind::f16)
+__device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t n) {
+    uint32_t d = 0;
+    d |= 1u << 4;            // c_format = F32
+    d |= 1u << 7;            // a_format = BF16
+    d |= 1u << 10;           // b_format = BF16
+    d |= (n >> 3) << 17;     // n_dim
+    d |= (uint32_t)(BM >> 4) << 24;   // m_dim
+    return d;
+}
+// kind::f16, A from tensor memory (two bf16 values of consecutive k per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 consecutive TMEM columns of this thread's lane <- 16 registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
 // 32 consecutive TMEM columns of this thread's lane <- 32 registers
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -189,7 +236,7 @@ constexpr int KC = 8;
 //                               pass is HBM-bound and ~64 KB per SM must be in flight to cover the latency
 //   ahl  (MS deep, 64 TMEM cols) A_hi / A_lo in tensor memory (lane = tile row, column = k), written by the splitter
 //   bt   (BS deep)              X_hi^T / X_lo^T tiles (L2-resident), own TMA producer warp
-template <int RS, int MS, int BS, int NPADC, bool TRANS>
+template <int RS, int MS, int BS, int NPADC, bool TRANS, int PREC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, Tf32Params prm) {
@@ -207,7 +254,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     constexpr int npad = NPADC;
     constexpr uint32_t A_BYTES = BM * BK * 4;                    // 16 KB
-    constexpr uint32_t B_BYTES = (uint32_t)NPADC * BK * 4;
+    constexpr uint32_t B_BYTES = (uint32_t)NPADC * BK * (PREC == 0 ? 4 : 2);      // one X^T tile: f32 hi (and lo) / bf16
+    constexpr uint32_t B_STAGE = PREC == 0 ? 2 * B_BYTES : B_BYTES;
     const uint32_t raw_base = smem_base;
     const uint32_t bt_base = raw_base + RS * A_BYTES;
 
@@ -283,11 +331,11 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 RC_ITEM(t)
                 for (int kb = kb0_; kb < kb1_; ++kb) {
                     mbar_wait(aempty0 + 8 * bs, bph ^ 1u);           // MS == BS: one commit frees the A (TMEM) and B slot
-                    const uint32_t sb = bt_base + bs * 2 * B_BYTES;
+                    const uint32_t sb = bt_base + bs * B_STAGE;
                     const uint32_t fb = bfull0 + 8 * bs;
-                    mbar_expect_tx(fb, 2 * B_BYTES);
+                    mbar_expect_tx(fb, B_STAGE);
                     tma_load_2d(sb, &tmBhi, kb * BK, ch_ * npad, fb);                             // [npad rows][32 k]
-                    tma_load_2d(sb + B_BYTES, &tmBlo, kb * BK, ch_ * npad, fb);
+                    if (PREC == 0) tma_load_2d(sb + B_BYTES, &tmBlo, kb * BK, ch_ * npad, fb);
                     if (++bs == BS) { bs = 0; bph ^= 1u; }
                 }
             }
@@ -298,9 +346,11 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // compile to plain uniform-datapath issues); the single-thread form of this loop spent ~100 cycles
         // per MMA on elect/branch scaffolding and capped the kernel at 12 MMAs per 1380 cycles.
         {
-            const uint32_t idesc = umma_idesc_tf32((uint32_t)npad);
+            const uint32_t idesc = PREC == 0 ? umma_idesc_tf32((uint32_t)npad) : umma_idesc_bf16((uint32_t)npad);
             // UMMA shared-memory descriptor of the X^T tiles: constant high word, low word = address >> 4
-            const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+            // (f32 tiles: 128-byte rows, SWIZZLE_128B, 8-row atoms of 1024 B; bf16 tiles: 64-byte rows, SWIZZLE_64B, 512 B)
+            const uint64_t desc_hi = PREC == 0 ? (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32
+                                               : (uint64_t)((512u >> 4) | (1u << 14) | (4u << 29)) << 32;
             const uint32_t bt_lo = (bt_base & 0x3FFFFu) >> 4;
             int ms = 0; uint32_t mph = 0;
             int bs = 0; uint32_t bph = 0;
@@ -319,7 +369,13 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (elect_one()) {
                             const uint32_t a_hi = tmem_base + (uint32_t)(2 * npad + ms * A_TMEM_COLS), a_lo = a_hi + 32u;
-                            const uint32_t bh = bt_lo + (uint32_t)bs * (2 * B_BYTES >> 4), bl = bh + (B_BYTES >> 4);
+                            const uint32_t bh = bt_lo + (uint32_t)bs * (B_STAGE >> 4), bl = bh + (B_BYTES >> 4);
+                            if (PREC == 1) {
+                                // one product, bf16: K = 16 per MMA = 32 bytes along the 64-byte row = 8 TMEM columns of A
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_bf16_ts(d_tmem, a_hi + 8u * k, desc_hi | (uint64_t)(bh + 2u * k), idesc, (kb != kc0 || k != 0) ? 1u : 0u);
+                            } else
 #pragma unroll
                             for (int k = 0; k < BK / 8; ++k) {
                                 // B K-major: 8 floats (32 B) along K inside the swizzle row; A: 8 TMEM columns per K-step
@@ -376,18 +432,36 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         vals[k] = *reinterpret_cast<const float*>(rawb + k * 128 + ((((lane >> 2) ^ (k & 7)) << 4) | ((lane & 3) << 2)));
                 }
                 uint32_t hi[32], lo[32];
+                if (PREC == 0) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    uint32_t u;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[k]));
-                    hi[k] = u;
-                    lo[k] = __float_as_uint(vals[k] - __uint_as_float(u));
+                    for (int k = 0; k < 32; ++k) {
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vals[k]));
+                        hi[k] = u;
+                        lo[k] = __float_as_uint(vals[k] - __uint_as_float(u));
+                    }
+                } else {
+                    // bf16 pairs: column j of the TMEM stage holds k = 2j (low half) and k = 2j + 1 (high half)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        uint32_t u;
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(vals[2 * j + 1]), "f"(vals[2 * j]));
+                        hi[j] = u;
+                    }
+                    lo[31] = 0u;
                 }
                 mbar_wait(aempty0 + 8 * ms, mph ^ 1u);                   // MMAs that read this TMEM stage are done
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * npad + ms * A_TMEM_COLS);
-                tmem_st32(ta, hi);
-                tmem_st32(ta + 32u, lo);
+                if (PREC == 0) {
+                    tmem_st32(ta, hi);
+                    tmem_st32(ta + 32u, lo);
+                } else {
+                    uint32_t h16[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) h16[j] = hi[j];
+                    tmem_st16(ta, h16);
+                }
                 // The raw slot is released only BEHIND the tcgen05.st: they cannot issue before the LDS results
                 // are in registers.  (An arrive placed right after the loads issues behind the LDS *issue*, and
                 // when the load/store pipe is backed up by the epilogue's store burst the TMA refill of the slot
@@ -497,6 +571,38 @@ split_transpose_kernel(const float* __restrict__ x, int64_t ldx, int K, int N, i
         __syncthreads();
     }
 }
+// X (K x N row-major) -> X^T rounded to bf16 (nrows x K row-major, K contiguous), rows >= N zero.
+__global__ void __launch_bounds__(256)
+bf16_transpose_kernel(const float* __restrict__ x, int64_t ldx, int K, int N, int nrows, unsigned short* __restrict__ xT, int64_t ldt) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int j0 = blockIdx.y * 32;
+    for (int64_t kt = blockIdx.x; kt * 32 < K; kt += gridDim.x) {
+        const int64_t k0 = kt * 32;
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int64_t k = k0 + r; const int j = j0 + tx;
+            tile[r][tx] = (k < K && j < N) ? x[k * ldx + j] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int j = j0 + r; const int64_t k = k0 + tx;
+            if (k < K && j < nrows) {
+                unsigned short h;
+                asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(tile[tx][r]));
+                xT[(int64_t)j * ldt + k] = h;
+            }
+        }
+        __syncthreads();
+    }
+}
+void launch_bf16_transpose(rc_ctx* c, const float* x, int64_t ldx, int64_t K, int N, int nrows, unsigned short* xT, int64_t ldt) {
+    dim3 block(32, 8);
+    dim3 grid((unsigned)std::min<int64_t>((K + 31) / 32, 148 * 64), (unsigned)((nrows + 31) / 32));
+    bf16_transpose_kernel<<<grid, block, 0, c->stream>>>(x, ldx, (int)K, N, nrows, xT, ldt);
+    RC_CHECK_LAUNCH(c);
+}
 void launch_split_transpose(rc_ctx* c, const float* x, int64_t ldx, int64_t K, int N, int nrows, float* hiT, float* loT, int64_t ldt) {
     dim3 block(32, 8);
     dim3 grid((unsigned)std::min<int64_t>((K + 31) / 32, 148 * 64), (unsigned)((nrows + 31) / 32));
@@ -504,12 +610,12 @@ void launch_split_transpose(rc_ctx* c, const float* x, int64_t ldx, int64_t K, i
     RC_CHECK_LAUNCH(c);
 }
 
-template <int RS, int MS, int BS, int NPADC, bool TRANS>
+template <int RS, int MS, int BS, int NPADC, bool TRANS, int PREC>
 void launch_tf32(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
                  Tf32Params prm) {
     static_assert(RS <= MAX_RS && MS <= MAX_MS && BS <= MAX_BS && MS == BS, "ring depth (A-TMEM and B rings share their release barrier)");
     static_assert(2 * NPADC + MS * A_TMEM_COLS <= 512, "tensor memory columns");
-    constexpr size_t smem = (size_t)RS * BM * BK * 4 + (size_t)BS * 2 * NPADC * BK * 4 + 1024;
+    constexpr size_t smem = (size_t)RS * BM * BK * 4 + (size_t)BS * (PREC == 0 ? 2 * NPADC * BK * 4 : NPADC * BK * 2) + 1024;
     static_assert(smem <= 226 * 1024, "ring configuration exceeds shared memory");
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * NPADC + MS * A_TMEM_COLS)) cols <<= 1;
@@ -517,18 +623,26 @@ void launch_tf32(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmBhi, co
     prm.agroup = 1;     // measured: 1 is best on B200 (2, 4, 8 are 0-4 % slower at 32768^2 x 64)
     prm.zero = 0;
     prm.vec_store = ((reinterpret_cast<uintptr_t>(prm.y) & 15) == 0 && (prm.ldy & 3) == 0 && (prm.part_stride & 3) == 0) ? 1 : 0;
-    RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<RS, MS, BS, NPADC, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RC_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<RS, MS, BS, NPADC, TRANS, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(prm.m_tiles * prm.splits * prm.nchunks, c->sm_count);
-    tf32x3_gemm_kernel<RS, MS, BS, NPADC, TRANS><<<grid, NTHREADS, smem, c->stream>>>(tmA, tmBhi, tmBlo, prm);
+    tf32x3_gemm_kernel<RS, MS, BS, NPADC, TRANS, PREC><<<grid, NTHREADS, smem, c->stream>>>(tmA, tmBhi, tmBlo, prm);
     RC_CHECK_LAUNCH(c);
 }
 template <bool TRANS>
 void dispatch_tf32(rc_ctx* c, int npad, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
-                   const Tf32Params& prm) {
+                   const Tf32Params& prm, int prec) {
+    if (prec == 1) {
+        switch (npad) {  // bf16: the X^T ring is a quarter of the size, the raw ring stays as deep as it can be
+            case 32: launch_tf32<8, 4, 4, 32, TRANS, 1>(c, tmA, tmBhi, tmBlo, prm); break;
+            case 64: launch_tf32<8, 4, 4, 64, TRANS, 1>(c, tmA, tmBhi, tmBlo, prm); break;
+            default: launch_tf32<8, 4, 4, 96, TRANS, 1>(c, tmA, tmBhi, tmBlo, prm); break;
+        }
+        return;
+    }
     switch (npad) {      //      raw (smem)  A hi/lo (TMEM)  X^T (smem)
-        case 32: launch_tf32<8, 4, 4, 32, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 32 KB
-        case 64: launch_tf32<8, 4, 4, 64, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 64 KB
-        default: launch_tf32<7, 4, 4, 96, TRANS>(c, tmA, tmBhi, tmBlo, prm); break;     // 112 + 96 KB
+        case 32: launch_tf32<8, 4, 4, 32, TRANS, 0>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 32 KB
+        case 64: launch_tf32<8, 4, 4, 64, TRANS, 0>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 64 KB
+        default: launch_tf32<7, 4, 4, 96, TRANS, 0>(c, tmA, tmBhi, tmBlo, prm); break;     // 112 + 96 KB
     }
 }
 
@@ -545,13 +659,24 @@ bool gemm_tf32x3_f32(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float* A,
     // the registers of one epilogue thread); all chunks run in ONE launch, chunk-fastest (Tf32Params)
     const int nchunks = (int)((N + MAX_CHUNK - 1) / MAX_CHUNK);
     const int npad = (int)(((N + nchunks - 1) / nchunks + 31) / 32 * 32);          // 32, 64 or 96
-    const int64_t ldt = (K + 3) / 4 * 4;
+    const int prec = c->f32_precision == 1 ? 1 : 0;
+    const int64_t ldt = (K + 7) / 8 * 8;
     const int nrows = nchunks * npad;                   // stacked X^T: column j of X is row j
-    DevBuf<float> hiT(c, (size_t)nrows * ldt), loT(c, (size_t)nrows * ldt);
-    launch_split_transpose(c, X, ldx, K, (int)N, nrows, hiT.p, loT.p, ldt);
+    DevBuf<float> hiT, loT;
+    DevBuf<unsigned short> bfT;
     CUtensorMap tmA = make_map_f32(A, M, K, lda, BM);
-    CUtensorMap tmBhi = make_map_f32(hiT.p, nrows, K, ldt, npad);
-    CUtensorMap tmBlo = make_map_f32(loT.p, nrows, K, ldt, npad);
+    CUtensorMap tmBhi, tmBlo;
+    if (prec == 1) {
+        bfT.alloc(c, (size_t)nrows * ldt);
+        launch_bf16_transpose(c, X, ldx, K, (int)N, nrows, bfT.p, ldt);
+        tmBhi = make_map_bf16(bfT.p, nrows, K, ldt, npad);
+        tmBlo = tmBhi;
+    } else {
+        hiT.alloc(c, (size_t)nrows * ldt); loT.alloc(c, (size_t)nrows * ldt);
+        launch_split_transpose(c, X, ldx, K, (int)N, nrows, hiT.p, loT.p, ldt);
+        tmBhi = make_map_f32(hiT.p, nrows, K, ldt, npad);
+        tmBlo = make_map_f32(loT.p, nrows, K, ldt, npad);
+    }
     Tf32Params prm;
     prm.y = Y; prm.ldy = ldy; prm.M = (int)M; prm.N = (int)N; prm.K = (int)K; prm.npad = npad;
     prm.m_tiles = (int)((M + BM - 1) / BM);
@@ -560,7 +685,7 @@ bool gemm_tf32x3_f32(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float* A,
     while (cols < (uint32_t)(2 * npad)) cols <<= 1;
     prm.tmem_cols = cols;
     prm.splits = 1; prm.kb_per_split = (int)((K + BK - 1) / BK); prm.part_stride = 0;
-    dispatch_tf32<false>(c, npad, tmA, tmBhi, tmBlo, prm);
+    dispatch_tf32<false>(c, npad, tmA, tmBhi, tmBlo, prm, prec);
     c->gemm_flops += 2 * M * N * K;
     return true;
 }
@@ -578,12 +703,23 @@ bool gemm_tf32x3_f32_tn(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float*
     const int nrows = nchunks * npad;
     const int64_t kblocks = (K + BK - 1) / BK;
     // B operand K-major: Y^T split into hi / lo once (Y is the small m x l matrix), chunks stacked
-    const int64_t ldt = (K + 3) / 4 * 4;
-    DevBuf<float> hi(c, (size_t)nrows * ldt), lo(c, (size_t)nrows * ldt);
-    launch_split_transpose(c, Y, ldy, K, (int)N, nrows, hi.p, lo.p, ldt);
+    const int prec = c->f32_precision == 1 ? 1 : 0;
+    const int64_t ldt = (K + 7) / 8 * 8;
+    DevBuf<float> hi, lo;
+    DevBuf<unsigned short> bfT;
     CUtensorMap tmA = make_map_f32(A, K, M, lda, 32);           // boxes [32 k rows][32 cols]
-    CUtensorMap tmBhi = make_map_f32(hi.p, nrows, K, ldt, npad);
-    CUtensorMap tmBlo = make_map_f32(lo.p, nrows, K, ldt, npad);
+    CUtensorMap tmBhi, tmBlo;
+    if (prec == 1) {
+        bfT.alloc(c, (size_t)nrows * ldt);
+        launch_bf16_transpose(c, Y, ldy, K, (int)N, nrows, bfT.p, ldt);
+        tmBhi = make_map_bf16(bfT.p, nrows, K, ldt, npad);
+        tmBlo = tmBhi;
+    } else {
+        hi.alloc(c, (size_t)nrows * ldt); lo.alloc(c, (size_t)nrows * ldt);
+        launch_split_transpose(c, Y, ldy, K, (int)N, nrows, hi.p, lo.p, ldt);
+        tmBhi = make_map_f32(hi.p, nrows, K, ldt, npad);
+        tmBlo = make_map_f32(lo.p, nrows, K, ldt, npad);
+    }
     Tf32Params prm;
     prm.M = (int)M; prm.N = (int)N; prm.K = (int)K; prm.npad = npad;
     prm.m_tiles = (int)((M + BM - 1) / BM);
@@ -605,7 +741,7 @@ bool gemm_tf32x3_f32_tn(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float*
         part.alloc(c, (size_t)splits * M * nrows);
         prm.y = part.p; prm.ldy = nrows; prm.part_stride = M * (int64_t)nrows;
     }
-    dispatch_tf32<true>(c, npad, tmA, tmBhi, tmBlo, prm);
+    dispatch_tf32<true>(c, npad, tmA, tmBhi, tmBlo, prm, prec);
     if (splits > 1) rc_splitk::reduce<float>(c, M, N, splits, part.p, nrows, prm.part_stride, Z, ldz);
     c->gemm_flops += 2 * M * N * K;
     return true;

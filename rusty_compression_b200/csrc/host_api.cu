@@ -1050,6 +1050,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
     return guard(c, [&] {
         if (!strcmp(key, "gemm_impl")) c->gemm_impl = (int)v;
         else if (!strcmp(key, "dmma_tail")) c->dmma_tail = (int)v;
+        else if (!strcmp(key, "f32_precision")) { RC_REQUIRE(v == 0 || v == 1, "f32_precision: 0 (3xTF32) or 1 (bf16)"); c->f32_precision = (int)v; }
         else if (!strcmp(key, "true_power_iteration")) c->true_power_iteration = (int)v;
         else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;
         else if (!strcmp(key, "pivot_precision")) c->pivot_f64 = (v != 0);

@@ -46,6 +46,7 @@ struct rc_ctx {
     size_t smem_optin = 0;
     // options
     int gemm_impl = 0;            // 0 auto, 1 generic only
+    int f32_precision = 0;        // option "f32_precision": 0 = 3xTF32 split (f32-accurate, default), 1 = bf16 single product (opt-in)
     int dmma_tail = 1;            // 1: ragged last column group of the DMMA GEMM on the DFMA tail path (gemm_dmma.cu)
     int true_power_iteration = 0;
     int trace = 0;                // option "trace": print wall time between rc_trace() marks (stream-synchronising)

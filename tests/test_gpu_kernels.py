@@ -268,3 +268,50 @@ def test_device_helmholtz_generator_matches_host_mirror(api, dtype):
     assert relerr(got, want) < tol
     shard = api.helmholtz_kernel_matrix((100, 200), dtype, seed=7, row_offset=150).to_numpy()
     assert relerr(shard, want[150:250]) < tol
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64])
+@pytest.mark.parametrize("shape", [(4096, 1024, 74), (4096, 2048, 266), (2048, 512, 64), (1000, 333, 130)])
+def test_bf16_opt_in_contraction(api, dtype, shape):
+    """north_star (2): "tcgen05 ... for bf16 where the caller opts in" -- context option f32_precision = 1 runs the f32 / c32
+    contractions (MatMat / ConjMatMat, src/types.rs:58-101) as ONE bf16 product (tcgen05 kind::f16, FP32 accumulation)
+    instead of the 3-product TF32 split.  Tolerance: bf16 keeps 8 significant bits (unit roundoff 2^-9 = 2e-3) and both
+    operands are rounded, so the product differs from the f64 reference by ~2^-9 relative in the Frobenius norm:
+    accepted below 1e-2, and required to be ABOVE 1e-4 -- the default path is at ~1e-6, so a result that accurate would
+    mean the option was ignored."""
+    m, k, n = shape
+    ctx = api.default_context()
+    a, x, w = rnd((m, k), dtype, 1), rnd((k, n), dtype, 2), rnd((m, n), dtype, 3)
+    ad = api.DeviceMatrix.from_numpy(a)
+    wide = np.complex128 if np.dtype(dtype).kind == "c" else np.float64
+    y_ref, z_ref = a.astype(wide).dot(x.astype(wide)), np.conj(a.T).astype(wide).dot(w.astype(wide))
+    ctx.set_option("f32_precision", 1)
+    try:
+        y16, z16 = ad.matmat(x).to_numpy(), ad.conj_matmat(w).to_numpy()
+    finally:
+        ctx.set_option("f32_precision", 0)
+    y32, z32 = ad.matmat(x).to_numpy(), ad.conj_matmat(w).to_numpy()
+    for got16, got32, want, what in ((y16, y32, y_ref, "A X"), (z16, z32, z_ref, "A^H W")):
+        e16, e32 = relerr(got16, want), relerr(got32, want)
+        assert e32 < 1e-5, (what, e32)
+        assert 1e-4 < e16 < 1e-2, (what, e16)
+    with pytest.raises(AssertionError):
+        ctx.set_option("f32_precision", 7)
+
+
+def test_bf16_opt_in_range_finder(api):
+    """The opt-in through a pipeline: fixed-rank range finder on an f32 operator with bf16 contractions still captures
+    the range to the accuracy the format allows (residual within 3e-2 of the f32 path's, here ~1e-2 absolute)."""
+    from oracle.inputs import decaying_spectrum_matrix
+    a, _ = decaying_spectrum_matrix(4096, 1024, np.float32, seed=4, r0=128, decade_every=16.0)
+    ctx = api.default_context()
+    op = api.DeviceMatrix.from_numpy(a)
+    q32 = api.sample_range_by_rank(op, 32, 8, seed=1)
+    ctx.set_option("f32_precision", 1)
+    try:
+        q16 = api.sample_range_by_rank(op, 32, 8, seed=1)
+    finally:
+        ctx.set_option("f32_precision", 0)
+    r32, r16 = ref.range_residual(a, q32), ref.range_residual(a, q16)
+    assert np.max(np.abs(q16.T.astype(np.float64).dot(q16.astype(np.float64)) - np.eye(32))) < 1e-4
+    assert r16 < r32 + 3e-2 and r16 < 5e-2, (r16, r32)
