@@ -188,9 +188,11 @@ __device__ __forceinline__ void dmma_consumer(const DmmaParams& prm, const uint3
         mbar_wait(full0 + 8 * stage, phase);             // first stage of the next tile (or the sentinel)
         const int t = tile_ring[seq & 7];
         if (t < 0) break;
-        const int mt = t % prm.m_tiles;
-        const int rest = t / prm.m_tiles;
-        const int nc = rest % prm.n_chunks, sp = rest / prm.n_chunks;
+        // work-item order: n-chunk fastest, so the CTAs that share a tile of A run side by side and A comes from HBM
+        // once and from L2 for the other chunks (m-tile fastest streamed the whole of A once per chunk)
+        const int nc = t % prm.n_chunks;
+        const int rest = t / prm.n_chunks;
+        const int mt = rest % prm.m_tiles, sp = rest / prm.m_tiles;
         const int m0 = mt * BM, n0 = nc * BN;
         const int kbeg = sp * prm.k_chunk;
         const int kend = min(prm.K, kbeg + prm.k_chunk);
@@ -342,9 +344,9 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_arrive(full0 + 8 * stage);            // wake the consumers with the sentinel
                     break;
                 }
-                const int mt = t % prm.m_tiles;
-                const int rest = t / prm.m_tiles;
-                const int nc = rest % prm.n_chunks, sp = rest / prm.n_chunks;
+                const int nc = t % prm.n_chunks;
+                const int rest = t / prm.n_chunks;
+                const int mt = rest % prm.m_tiles, sp = rest / prm.m_tiles;
                 const int m0 = mt * BM, n0 = nc * BN;
                 const int kbeg = sp * prm.k_chunk;
                 const int kend = min(prm.K, kbeg + prm.k_chunk);
@@ -429,30 +431,55 @@ bool gemm_dmma_f64(rc_ctx* c, bool a_transposed, int64_t M, int64_t N, int64_t K
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
     if ((lda & 1) || (ldb & 1)) return false;                 // TMA: 16-byte row pitch
     if (M > (1LL << 30) || N > (1LL << 30) || K > (1LL << 30)) return false;
-    // n-chunking: fewest chunks of at most 96 columns, each a multiple of 16
-    int n_chunks = (int)((N + 95) / 96);
-    int bn = (int)(((N + n_chunks - 1) / n_chunks + 15) / 16 * 16);
-    if (bn > 96) bn = 96;
-    n_chunks = (int)((N + bn - 1) / bn);
     DmmaParams prm;
     prm.M = (int)M; prm.N = (int)N; prm.K = (int)K;
     prm.m_tiles = (int)((M + BM - 1) / BM);
-    prm.n_chunks = n_chunks;
-    int64_t tiles = (int64_t)prm.m_tiles * n_chunks;
-    int splits = 1;
     const int64_t grid_cap = 2LL * c->sm_count;
-    if (tiles < 2 * grid_cap) {
-        // enough work items for ~4 rounds of the persistent grid, picked so the last round is full
-        int64_t want = (3 * grid_cap + tiles - 1) / tiles;
-        int64_t maxs = std::max<int64_t>(1, K / (BK * 16));
-        double best_eff = -1.0;
-        for (int64_t s = std::max<int64_t>(1, want); s <= std::min<int64_t>(maxs, 2 * want + 2); ++s) {
-            int64_t tot = tiles * s, rounds = (tot + grid_cap - 1) / grid_cap;
-            double eff = (double)tot / (double)(rounds * grid_cap);
-            if (eff > best_eff + 0.02) { best_eff = eff; splits = (int)s; }
+    int bn = 96, n_chunks = 1, splits = 1;
+    if (N <= 96) {
+        // one chunk: the narrowest multiple of 16 that holds N
+        bn = (int)((N + 15) / 16 * 16);
+        const int64_t tiles = prm.m_tiles;
+        if (tiles < 2 * grid_cap) {
+            // enough work items for ~4 rounds of the persistent grid, picked so the last round is full
+            int64_t want = (3 * grid_cap + tiles - 1) / tiles;
+            int64_t maxs = std::max<int64_t>(1, K / (BK * 16));
+            double best_eff = -1.0;
+            for (int64_t s = std::max<int64_t>(1, want); s <= std::min<int64_t>(maxs, 2 * want + 2); ++s) {
+                int64_t tot = tiles * s, rounds = (tot + grid_cap - 1) / grid_cap;
+                double eff = (double)tot / (double)(rounds * grid_cap);
+                if (eff > best_eff + 0.02) { best_eff = eff; splits = (int)s; }
+            }
+            if (best_eff < 0) splits = (int)std::max<int64_t>(1, std::min<int64_t>(want, maxs));
         }
-        if (best_eff < 0) splits = (int)std::max<int64_t>(1, std::min<int64_t>(want, maxs));
+    } else {
+        // Several column chunks (the real expansion of the c64 products, wide f64 operands): tile width and split-K
+        // factor by a cost model -- time ~ padded work / (pipe efficiency of the tile shape x how evenly the work
+        // items fill the SMs).  The two CTAs of an SM share one FP64 pipe, so the quantisation that matters is items
+        // per SM.  Narrower tiles can waste fewer padded columns (N = 256 real columns: 4 x 64 instead of 3 x 96 with
+        // 12 % padding), and a split-K of 2-4 fills the last round even when there are plenty of tiles (config 5,
+        // Y = A Omega: 768 items on 148 SMs leave the last of 6 rounds 19 % full; 3 splits fill 15.6 of 16 rounds and
+        // the partial sums cost ~1 % of the GEMM).
+        double best = -1.0;
+        const int64_t maxs_k = std::max<int64_t>(1, K / (BK * 16));
+        for (int cand = 96; cand >= 48; cand -= 16) {
+            const int64_t nch = (N + cand - 1) / cand;
+            const double pad_eff = (double)N / (double)(nch * cand);
+            const double tile_eff = cand >= 80 ? 1.0 : (cand == 64 ? 0.97 : 0.93);
+            const int64_t tiles = (int64_t)prm.m_tiles * nch;
+            const int64_t smax = std::min<int64_t>(maxs_k, tiles < 2 * grid_cap ? 4 * grid_cap / std::max<int64_t>(1, tiles) + 2 : 4);
+            for (int64_t sp = 1; sp <= std::max<int64_t>(1, smax); ++sp) {
+                const int64_t items = tiles * sp;
+                const int64_t rounds = (items + c->sm_count - 1) / c->sm_count;
+                const double fill = (double)items / (double)(rounds * c->sm_count);
+                const double occ = items >= grid_cap ? 1.0 : 0.5 + 0.5 * (double)items / (double)grid_cap;
+                const double red = sp > 1 ? 1.0 / (1.0 + 0.004 * (double)sp * 16384.0 / (double)std::max<int64_t>(K, 1)) : 1.0;
+                const double score = pad_eff * tile_eff * fill * occ * red;
+                if (score > best + 1e-3) { best = score; bn = cand; n_chunks = (int)nch; splits = (int)sp; }
+            }
+        }
     }
+    prm.n_chunks = n_chunks;
     int64_t k_chunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
     splits = (int)((K + k_chunk - 1) / k_chunk);
     prm.splits = splits;

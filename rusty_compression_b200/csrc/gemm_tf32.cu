@@ -40,7 +40,7 @@ namespace {
 constexpr int BM = 128;           // UMMA M (cta_group::1)
 constexpr int BK = 32;            // floats per stage = one 128-byte swizzle row
 constexpr int NTHREADS = 480;     // 15 warps: A-TMA, MMA, 4 splitters, 4 epilogue, B-TMA, 4 more splitters
-constexpr int MAX_RS = 8, MAX_MS = 4, MAX_BS = 4;   // ring depths: raw A tiles (smem), split A (TMEM), B tiles (smem)
+constexpr int MAX_RS = 8, MAX_MS = 6, MAX_BS = 6;   // ring depths: raw A tiles (smem), split A (TMEM), B tiles (smem)
 constexpr int MAX_CHUNK = 96;     // columns per work item: the promoted FP32 accumulator row lives in one epilogue thread's registers
 constexpr int A_TMEM_COLS = 64;   // one split stage in TMEM: A_hi (32 columns = 32 k) + A_lo (32 columns)
 
@@ -636,6 +636,16 @@ void dispatch_tf32(rc_ctx* c, int npad, const CUtensorMap& tmA, const CUtensorMa
             case 32: launch_tf32<8, 4, 4, 32, TRANS, 1>(c, tmA, tmBhi, tmBlo, prm); break;
             case 64: launch_tf32<8, 4, 4, 64, TRANS, 1>(c, tmA, tmBhi, tmBlo, prm); break;
             default: launch_tf32<8, 4, 4, 96, TRANS, 1>(c, tmA, tmBhi, tmBlo, prm); break;
+        }
+        return;
+    }
+    if (c->tf32_ring == 1) {
+        // deeper split ring (option "tf32_ring" = 1): the splitters spend ~30 % of their samples waiting for the MMAs of
+        // the stage four k-blocks back to retire (ncu, round 1) -- six TMEM stages of A_hi / A_lo next to the two accumulators
+        switch (npad) {
+            case 32: launch_tf32<8, 6, 6, 32, TRANS, 0>(c, tmA, tmBhi, tmBlo, prm); break;     // 128 + 48 KB, 64 + 384 TMEM columns
+            case 64: launch_tf32<7, 6, 6, 64, TRANS, 0>(c, tmA, tmBhi, tmBlo, prm); break;     // 112 + 96 KB, 128 + 384
+            default: launch_tf32<6, 5, 5, 96, TRANS, 0>(c, tmA, tmBhi, tmBlo, prm); break;     //  96 + 120 KB, 192 + 320
         }
         return;
     }

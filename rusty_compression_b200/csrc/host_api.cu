@@ -115,6 +115,10 @@ void gemm(rc_ctx* c, RcOp opa, RcOp opb, int64_t M, int64_t N, int64_t K, const 
     gemm_generic<T>(c, opa, opb, M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
     c->gemm_flops += (ScalarTraits<T>::is_complex ? 8 : 2) * M * N * K;
 }
+template void gemm<float>(rc_ctx*, RcOp, RcOp, int64_t, int64_t, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float, float);
+template void gemm<double>(rc_ctx*, RcOp, RcOp, int64_t, int64_t, int64_t, const double*, int64_t, const double*, int64_t, double*, int64_t, double, double);
+template void gemm<c32>(rc_ctx*, RcOp, RcOp, int64_t, int64_t, int64_t, const c32*, int64_t, const c32*, int64_t, c32*, int64_t, c32, c32);
+template void gemm<c64>(rc_ctx*, RcOp, RcOp, int64_t, int64_t, int64_t, const c64*, int64_t, const c64*, int64_t, c64*, int64_t, c64, c64);
 
 // ============================================================================ pivoted QR
 namespace {
@@ -280,13 +284,68 @@ void small_pivqr(rc_ctx* c, const T* rf, int64_t ldrf, int64_t w, int64_t ncq, r
     pivqr_form_q<T>(c, vbuf.p, tau.p, w, w, ncq, q1, ldq1);
 }
 
+// Unpivoted QR of a tall panel that is wider than one shared-memory block: Y = Qfull R0 by column panels.
+// Panels of at most min(wmax, Cholesky width) columns; each is orthogonalised against the previous ones (block
+// classical Gram-Schmidt, twice) and then factored on its own: Cholesky-QR2 when it is well conditioned (all
+// GEMM-shaped, tensor pipe), Householder TSQR otherwise.  qfull: m x w (ld = ldq), r0: w x w row-major (ld = w).
+template <class T>
+void panel_qr(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, int dtype,
+              DevBuf<T>& qfull, int64_t& ldq, DevBuf<T>& r0) {
+    const int64_t wmax = tsqr_max_width(c, dtype);
+    int64_t wpan = std::min(wmax, c->qr_mode == 1 ? wmax : chol_max_width(c, dtype));
+    const bool single = (dtype == RC_F32 || dtype == RC_C32);
+    (void)single;
+    int64_t npan = (w + wpan - 1) / wpan;
+    int64_t wp = (w + npan - 1) / npan;
+    {   // panel starts on 16-byte boundaries (TMA operand alignment), as long as the panel still fits
+        const int64_t e = std::max<int64_t>(1, (int64_t)(16 / rc_dtype_size(dtype)));
+        const int64_t up = (wp + e - 1) / e * e;
+        if (up <= wpan) wp = up;
+    }
+    ldq = rc_pad_ld(dtype, w);                        // 16-byte row pitch: the tensor-pipe GEMMs can take it
+    qfull.alloc(c, (size_t)m * ldq);
+    r0.alloc(c, (size_t)w * w);
+    k_fill<T>(c, r0.p, w, w, w, rc_zero<T>());
+    for (int64_t c0 = 0; c0 < w; c0 += wp) {
+        int64_t cw = std::min(wp, w - c0);
+        T* yp = y + c0;
+        if (c0 > 0) {
+            const int64_t ldt = rc_pad_ld(dtype, cw);
+            DevBuf<T> t(c, (size_t)c0 * ldt), proj(c, (size_t)m * ldt);
+            for (int pass = 0; pass < 2; ++pass) {
+                if (sharded && ldt != cw) RC_CUDA(cudaMemsetAsync(t.p, 0, sizeof(T) * c0 * ldt, c->stream));
+                gemm<T>(c, RC_OP_H, RC_OP_N, c0, cw, m, qfull.p, ldq, yp, ldy, t.p, ldt, rc_one<T>(), rc_zero<T>());
+                if (sharded) comm_allreduce_sum(c, t.p, (size_t)c0 * ldt, dtype);
+                gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, c0, qfull.p, ldq, t.p, ldt, proj.p, ldt, rc_one<T>(), rc_zero<T>());
+                k_sub<T>(c, yp, ldy, yp, ldy, proj.p, ldt, m, cw);                    // Y_p -= Q (Q^H Y_p)
+                k_add<T>(c, r0.p + c0, w, r0.p + c0, w, t.p, ldt, c0, cw);             // R0[0:c0, c0:c0+cw] += t
+            }
+            rc_trace(c, "pqr_tall: panel projection x2");
+        }
+        DevBuf<T> pq1, prinv2, prfac;
+        int64_t lds = 0;
+        if (cholqr2<T>(c, yp, ldy, m, cw, sharded, dtype, pq1, prinv2, prfac, lds)) {
+            rc_trace(c, "pqr_tall: panel cholqr2");
+            gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, cw, pq1.p, lds, prinv2.p, lds, qfull.p + c0, ldq, rc_one<T>(), rc_zero<T>());
+            k_copy<T>(c, r0.p + c0 * w + c0, w, prfac.p, lds, cw, cw);
+            rc_trace(c, "pqr_tall: panel Q = q1 rinv2");
+        } else {
+            DistTsqr<T> ts;
+            ts.factor(c, yp, ldy, m, cw, sharded);
+            k_copy<T>(c, r0.p + c0 * w + c0, w, ts.r(), cw, cw, cw);
+            DevBuf<T> eye(c, (size_t)cw * cw);
+            k_eye<T>(c, eye.p, cw, cw, cw);
+            ts.apply(eye.p, cw, cw, qfull.p + c0, ldq);
+        }
+    }
+}
+
 // Tall-skinny route: Y = Q0 R0 by (distributed) Householder TSQR, pivoting on R0, Q = Q0 Q1.
 // Panels wider than the shared-memory limit are orthogonalised block by block against the
 // previous panels (two projection passes) before their own TSQR.
 template <class T>
 void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, bool sharded, int dtype, QrParts& out) {
     const int64_t wmax = tsqr_max_width(c, dtype);
-    DevBuf<T> r0(c, (size_t)w * w);
     DevBuf<T> wc(c, (size_t)w * w), vbuf(c, (size_t)w * w), tau(c, (size_t)w);
     DevBuf<int> dind(c, (size_t)w);
     MatPtr r(mat_new(c, dtype, w, w));
@@ -310,57 +369,12 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
         small_pivqr<T>(c, ts.r(), w, w, ncq, r.get(), dind.p, q1.p, ncq, wc, vbuf, tau);
         ts.apply(q1.p, ncq, ncq, P<T>(q.get()), q->ld);
     } else {
-        // Panels of at most min(wmax, Cholesky width) columns.  Each panel is orthogonalised against the
-        // previous ones (block classical Gram-Schmidt, twice) and then factored on its own: Cholesky-QR2 when
-        // it is well conditioned (all GEMM-shaped, tensor pipe), Householder TSQR otherwise.
-        int64_t wpan = std::min(wmax, c->qr_mode == 1 ? wmax : chol_max_width(c, dtype));
-        const bool single = (dtype == RC_F32 || dtype == RC_C32);
-        (void)single;
-        int64_t npan = (w + wpan - 1) / wpan;
-        int64_t wp = (w + npan - 1) / npan;
-        {   // panel starts on 16-byte boundaries (TMA operand alignment), as long as the panel still fits
-            const int64_t e = std::max<int64_t>(1, (int64_t)(16 / rc_dtype_size(dtype)));
-            const int64_t up = (wp + e - 1) / e * e;
-            if (up <= wpan) wp = up;
-        }
-        const int64_t ldq = rc_pad_ld(dtype, w);          // 16-byte row pitch: the tensor-pipe GEMMs can take it
-        DevBuf<T> qfull(c, (size_t)m * ldq);
-        k_fill<T>(c, r0.p, w, w, w, rc_zero<T>());
-        for (int64_t c0 = 0; c0 < w; c0 += wp) {
-            int64_t cw = std::min(wp, w - c0);
-            T* yp = y + c0;
-            if (c0 > 0) {
-                const int64_t ldt = rc_pad_ld(dtype, cw);
-                DevBuf<T> t(c, (size_t)c0 * ldt), proj(c, (size_t)m * ldt);
-                for (int pass = 0; pass < 2; ++pass) {
-                    if (sharded && ldt != cw) RC_CUDA(cudaMemsetAsync(t.p, 0, sizeof(T) * c0 * ldt, c->stream));
-                    gemm<T>(c, RC_OP_H, RC_OP_N, c0, cw, m, qfull.p, ldq, yp, ldy, t.p, ldt, rc_one<T>(), rc_zero<T>());
-                    if (sharded) comm_allreduce_sum(c, t.p, (size_t)c0 * ldt, dtype);
-                    gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, c0, qfull.p, ldq, t.p, ldt, proj.p, ldt, rc_one<T>(), rc_zero<T>());
-                    k_sub<T>(c, yp, ldy, yp, ldy, proj.p, ldt, m, cw);                    // Y_p -= Q (Q^H Y_p)
-                    k_add<T>(c, r0.p + c0, w, r0.p + c0, w, t.p, ldt, c0, cw);             // R0[0:c0, c0:c0+cw] += t
-                }
-                rc_trace(c, "pqr_tall: panel projection x2");
-            }
-            DevBuf<T> pq1, prinv2, prfac;
-            int64_t lds = 0;
-            if (cholqr2<T>(c, yp, ldy, m, cw, sharded, dtype, pq1, prinv2, prfac, lds)) {
-                rc_trace(c, "pqr_tall: panel cholqr2");
-                gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, cw, pq1.p, lds, prinv2.p, lds, qfull.p + c0, ldq, rc_one<T>(), rc_zero<T>());
-                k_copy<T>(c, r0.p + c0 * w + c0, w, prfac.p, lds, cw, cw);
-                rc_trace(c, "pqr_tall: panel Q = q1 rinv2");
-            } else {
-                DistTsqr<T> ts;
-                ts.factor(c, yp, ldy, m, cw, sharded);
-                k_copy<T>(c, r0.p + c0 * w + c0, w, ts.r(), cw, cw, cw);
-                DevBuf<T> eye(c, (size_t)cw * cw);
-                k_eye<T>(c, eye.p, cw, cw, cw);
-                ts.apply(eye.p, cw, cw, qfull.p + c0, ldq);
-            }
-        }
+        DevBuf<T> qfull, r0p;
+        int64_t ldq = 0;
+        panel_qr<T>(c, y, ldy, m, w, sharded, dtype, qfull, ldq, r0p);
         const int64_t ldq1 = rc_pad_ld(dtype, ncq);
         DevBuf<T> q1p(c, (size_t)w * ldq1);
-        small_pivqr<T>(c, r0.p, w, w, ncq, r.get(), dind.p, q1p.p, ldq1, wc, vbuf, tau);
+        small_pivqr<T>(c, r0p.p, w, w, ncq, r.get(), dind.p, q1p.p, ldq1, wc, vbuf, tau);
         rc_trace(c, "pqr_tall: pivoted QR of R");
         gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, qfull.p, ldq, q1p.p, ldq1, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
         rc_trace(c, "pqr_tall: form Q1, Q = Qfull Q1");
@@ -392,7 +406,11 @@ void pivoted_qr_impl(rc_ctx* c, const rc_matrix* arr, bool input_is_conj_transpo
     // single-precision inputs keep the unpivoted reduction in working precision and only pivot in double (pivqr.cu).
     using W = typename AccOf<T>::type;
     if constexpr (!std::is_same<T, W>::value) {
-        if (c->pivot_f64 && !sharded && p * n <= (int64_t)1 << 20) {
+        // (general dense single-precision matrices -- both dimensions large -- also go through double as long as the
+        // widened copy stays modest: the pivots deep into the spectrum sit at 1e-4..1e-7 of the leading norm, below
+        // the roundoff an f32 reduction to R would leave in them)
+        const bool dense_general = std::min(p, n) > 512 && p * n <= ((int64_t)1 << 27);
+        if (c->pivot_f64 && !sharded && (p * n <= ((int64_t)1 << 20) || dense_general)) {
             MatPtr wide(mat_new(c, dtype | 1, arr->rows, arr->cols));
             k_cast<W, T>(c, P<W>(wide.get()), wide->ld, P<T>(arr), arr->ld, arr->rows, arr->cols);
             QrParts ow;
@@ -470,6 +488,7 @@ template <class T>
 void svd_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int dtype, bool sharded,
               MatPtr& u, std::vector<double>& s, MatPtr& wmat) {
     DevBuf<double> ds(c, (size_t)w);
+    DevBuf<int> info(c, 2);
     MatPtr um(mat_new(c, dtype, m, w)), wm(mat_new(c, dtype, w, w));
     const int64_t wmax = tsqr_max_width(c, dtype);
     DevBuf<T> cq1, crinv2, crfac;
@@ -477,22 +496,34 @@ void svd_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int dtype, boo
     if (m >= w && cholqr2<T>(c, y, ldy, m, w, sharded, dtype, cq1, crinv2, crfac, lds)) {
         const int64_t ldu = rc_pad_ld(dtype, w);
         DevBuf<T> ur(c, (size_t)w * ldu), tq(c, (size_t)w * ldu);
-        jacobi_svd<T>(c, crfac.p, lds, w, w, ur.p, ldu, ds.p, P<T>(wm.get()), wm->ld);
+        jacobi_svd<T>(c, crfac.p, lds, w, w, ur.p, ldu, ds.p, P<T>(wm.get()), wm->ld, info.p);
         gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, crinv2.p, lds, ur.p, ldu, tq.p, ldu, rc_one<T>(), rc_zero<T>());
         gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, cq1.p, lds, tq.p, ldu, P<T>(um.get()), um->ld, rc_one<T>(), rc_zero<T>());
     } else if (w <= wmax && m >= w) {
         DistTsqr<T> ts;
         ts.factor(c, y, ldy, m, w, sharded);
         DevBuf<T> ur(c, (size_t)w * w);
-        jacobi_svd<T>(c, ts.r(), w, w, w, ur.p, w, ds.p, P<T>(wm.get()), wm->ld);
+        jacobi_svd<T>(c, ts.r(), w, w, w, ur.p, w, ds.p, P<T>(wm.get()), wm->ld, info.p);
         ts.apply(ur.p, w, w, P<T>(um.get()), um->ld);
     } else {
-        RC_REQUIRE(!sharded, "svd: row-sharded input must be tall-skinny");
-        jacobi_svd<T>(c, y, ldy, m, w, P<T>(um.get()), um->ld, ds.p, P<T>(wm.get()), wm->ld);
+        // Wide panels (a general dense matrix, SVD::compute_from of src/svd.rs:165-169): unpivoted QR by column
+        // panels (all GEMM-shaped), Jacobi on the w x w triangle -- one CTA if it fits shared memory, else the
+        // cooperative whole-GPU kernel -- and U = Qfull Ur.
+        DevBuf<T> qfull, r0;
+        int64_t ldq = 0;
+        panel_qr<T>(c, y, ldy, m, w, sharded, dtype, qfull, ldq, r0);
+        const int64_t ldu = rc_pad_ld(dtype, w);
+        DevBuf<T> ur(c, (size_t)w * ldu);
+        jacobi_svd<T>(c, r0.p, w, w, w, ur.p, ldu, ds.p, P<T>(wm.get()), wm->ld, info.p);
+        gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, qfull.p, ldq, ur.p, ldu, P<T>(um.get()), um->ld, rc_one<T>(), rc_zero<T>());
     }
     s.resize((size_t)w);
+    int hinfo[2] = {0, 0};
     RC_CUDA(cudaMemcpyAsync(s.data(), ds.p, sizeof(double) * w, cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaMemcpyAsync(hinfo, info.p, sizeof(hinfo), cudaMemcpyDeviceToHost, c->stream));
     RC_CUDA(cudaStreamSynchronize(c->stream));
+    // ?gesdd reports non-convergence as info > 0, which the crate surfaces as LinalgError (src/compute_svd.rs:19-27)
+    if (hinfo[0] != 0 && c->defer_depth == 0) RC_THROW(RC_LINALG_ERROR, "svd: the Jacobi iteration did not converge in %d sweeps", hinfo[1]);
     u.reset(um.release());
     wmat.reset(wm.release());
 }
@@ -1050,6 +1081,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
     return guard(c, [&] {
         if (!strcmp(key, "gemm_impl")) c->gemm_impl = (int)v;
         else if (!strcmp(key, "dmma_tail")) c->dmma_tail = (int)v;
+        else if (!strcmp(key, "tf32_ring")) c->tf32_ring = (int)v;
         else if (!strcmp(key, "f32_precision")) { RC_REQUIRE(v == 0 || v == 1, "f32_precision: 0 (3xTF32) or 1 (bf16)"); c->f32_precision = (int)v; }
         else if (!strcmp(key, "true_power_iteration")) c->true_power_iteration = (int)v;
         else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;

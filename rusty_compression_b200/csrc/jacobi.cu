@@ -6,7 +6,10 @@
 // G J = U diag(s), J accumulated in V.  One warp per column pair, round-robin ordering, all pairs
 // of a round in parallel; Gram entries accumulated in double.  Singular values come out with
 // high relative accuracy, sorted descending like ?gesdd's.
+#include <cooperative_groups.h>
 #include "rc_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -186,18 +189,180 @@ jacobi_kernel(T* __restrict__ Gg, T* __restrict__ Vg, int rows, int n, int ldg, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Large factors (the w x w triangle of a dense matrix that does not fit one CTA's shared memory: SVD::compute_from on
+// a general matrix, src/svd.rs:165-169): the same one-sided Jacobi iteration as a persistent COOPERATIVE kernel over
+// the whole GPU.  G and V stay in global memory (L2-resident up to n ~ 2 800 in f64), one warp per column pair, all
+// pairs of a round-robin round in parallel across the grid, one grid-wide sync per round.  Columns move between SMs
+// from round to round, so every load bypasses L1 (ld.global.cg).
+__device__ __forceinline__ float  jld(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ double jld(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ c32 jld(const c32* p) { float2 v = __ldcg(reinterpret_cast<const float2*>(p)); return c32(v.x, v.y); }
+__device__ __forceinline__ c64 jld(const c64* p) { double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return c64(v.x, v.y); }
+
+constexpr int JG_NT = 256;
+constexpr int JG_RPT = 8;         // rows of a column pair a thread keeps in registers between the Gram pass and the rotation
+
+// One CTA per column pair: 256 threads share the two columns (a warp per pair left the round latency-bound: 1 024 warps
+// with one L2 round trip per 32 rows each -- 190 us per round at n = 2 048), the pair's Gram entries are reduced
+// through shared memory, and a thread's rows stay in registers between the Gram pass and the rotation.
+template <class T>
+__global__ void __launch_bounds__(JG_NT)
+jacobi_grid_kernel(T* __restrict__ G, T* __restrict__ V, int rows, int n, int max_sweeps, double tol, int* __restrict__ flags,
+                   T* __restrict__ u, int64_t ldu, double* __restrict__ s_out, T* __restrict__ w, int64_t ldw,
+                   double* __restrict__ sig, int* __restrict__ info) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double s_part[JG_NT / 32][4];
+    __shared__ double s_tot[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+    const int gw = (int)(gtid >> 5), nwarps = (int)(gthreads >> 5);
+    const int npad = n + (n & 1), half = npad / 2;
+    for (int64_t e = gtid; e < (int64_t)n * n; e += gthreads) V[e] = (e / n == e % n) ? rc_one<T>() : rc_zero<T>();
+    grid.sync();
+    const double tol2 = tol * tol;
+    const bool cached = rows <= JG_NT * JG_RPT;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        bool rotated = false;
+        for (int round = 0; round < npad - 1; ++round) {
+            for (int k = blockIdx.x; k < half; k += gridDim.x) {
+                int a = npad - 1, b = round;
+                if (k > 0) {
+                    a = round + k; if (a >= npad - 1) a -= npad - 1;
+                    b = round - k; if (b < 0) b += npad - 1;
+                }
+                const int p = min(a, b), q = max(a, b);
+                if (q >= n) continue;                                   // padding column of an odd n (block-uniform)
+                T* gp = G + (int64_t)p * rows;
+                T* gq = G + (int64_t)q * rows;
+                double alpha = 0.0, beta = 0.0, gre = 0.0, gim = 0.0;
+                T xr_[JG_RPT], yr_[JG_RPT];
+                if (cached) {
+#pragma unroll
+                    for (int t = 0; t < JG_RPT; ++t) {
+                        const int r = tid + t * JG_NT;
+                        xr_[t] = (r < rows) ? jld(gp + r) : rc_zero<T>();
+                        yr_[t] = (r < rows) ? jld(gq + r) : rc_zero<T>();
+                    }
+#pragma unroll
+                    for (int t = 0; t < JG_RPT; ++t) {
+                        alpha += rc_abs2(xr_[t]);
+                        beta += rc_abs2(yr_[t]);
+                        const double xr = (double)rc_real(xr_[t]), xi = (double)rc_imag(xr_[t]);
+                        const double yr = (double)rc_real(yr_[t]), yi = (double)rc_imag(yr_[t]);
+                        gre += xr * yr + xi * yi;
+                        gim += xr * yi - xi * yr;
+                    }
+                } else {
+                    for (int r = tid; r < rows; r += JG_NT) {
+                        const T x = jld(gp + r), y = jld(gq + r);
+                        alpha += rc_abs2(x);
+                        beta += rc_abs2(y);
+                        const double xr = (double)rc_real(x), xi = (double)rc_imag(x);
+                        const double yr = (double)rc_real(y), yi = (double)rc_imag(y);
+                        gre += xr * yr + xi * yi;
+                        gim += xr * yi - xi * yr;
+                    }
+                }
+                alpha = rc_warp_sum(alpha); beta = rc_warp_sum(beta); gre = rc_warp_sum(gre); gim = rc_warp_sum(gim);
+                if (lane == 0) { s_part[warp][0] = alpha; s_part[warp][1] = beta; s_part[warp][2] = gre; s_part[warp][3] = gim; }
+                __syncthreads();
+                if (tid < 4) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int ww = 0; ww < JG_NT / 32; ++ww) v += s_part[ww][tid];
+                    s_tot[tid] = v;
+                }
+                __syncthreads();
+                alpha = s_tot[0]; beta = s_tot[1]; gre = s_tot[2]; gim = s_tot[3];
+                const double g2 = gre * gre + gim * gim;
+                if (g2 != 0.0 && g2 > tol2 * alpha * beta) {
+                    rotated = true;
+                    const double rg = rsqrt(g2);
+                    const double zeta = (beta - alpha) * 0.5 * rg;
+                    const double w1 = 1.0 + zeta * zeta;
+                    const double t = copysign(1.0, zeta) * __drcp_rn(fabs(zeta) + w1 * rsqrt(w1));
+                    const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+                    const T ph = rc_make<T>(gre * rg, -gim * rg);
+                    const T csT = rc_make<T>(cs, 0.0), snT = rc_make<T>(sn, 0.0);
+                    if (cached) {
+#pragma unroll
+                        for (int t2 = 0; t2 < JG_RPT; ++t2) {
+                            const int r = tid + t2 * JG_NT;
+                            if (r < rows) {
+                                const T y = ph * yr_[t2];
+                                gp[r] = csT * xr_[t2] - snT * y;
+                                gq[r] = snT * xr_[t2] + csT * y;
+                            }
+                        }
+                    } else {
+                        for (int r = tid; r < rows; r += JG_NT) {
+                            const T x = jld(gp + r), y = ph * jld(gq + r);
+                            gp[r] = csT * x - snT * y;
+                            gq[r] = snT * x + csT * y;
+                        }
+                    }
+                    T* vp = V + (int64_t)p * n;
+                    T* vq = V + (int64_t)q * n;
+                    for (int r = tid; r < n; r += JG_NT) {
+                        const T x = jld(vp + r), y = ph * jld(vq + r);
+                        vp[r] = csT * x - snT * y;
+                        vq[r] = snT * x + csT * y;
+                    }
+                }
+                // (s_part / s_tot are rewritten by the next pair only after the two barriers above)
+            }
+            grid.sync();
+        }
+        if (rotated && tid == 0) flags[sweep] = 1;
+        grid.sync();
+        if (__ldcg(flags + sweep) == 0) break;
+    }
+    if (gtid == 0) { info[0] = (sweep >= max_sweeps) ? 1 : 0; info[1] = sweep; }
+    for (int c = gw; c < n; c += nwarps) {
+        const T* gc = G + (int64_t)c * rows;
+        double a = 0.0;
+        for (int r = lane; r < rows; r += 32) a += rc_abs2(jld(gc + r));
+        a = rc_warp_sum(a);
+        if (lane == 0) sig[c] = sqrt(a);
+    }
+    grid.sync();
+    for (int c = gw; c < n; c += nwarps) {
+        const double sc = __ldcg(sig + c);
+        int rank = 0;
+        for (int o = lane; o < n; o += 32) {
+            const double so = __ldcg(sig + o);
+            if (so > sc || (so == sc && o < c)) ++rank;
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, m);
+        const T* gc = G + (int64_t)c * rows;
+        const T* vc = V + (int64_t)c * n;
+        const T invT = rc_make<T>((sc > 0.0) ? 1.0 / sc : 0.0, 0.0);
+        for (int r = lane; r < rows; r += 32) u[(int64_t)r * ldu + rank] = jld(gc + r) * invT;
+        for (int r = lane; r < n; r += 32) w[(int64_t)r * ldw + rank] = jld(vc + r);
+        if (lane == 0) s_out[rank] = sc;
+    }
+}
+
 }  // namespace
 
 template <class T>
-void jacobi_svd(rc_ctx* c, const T* g, int64_t ldg, int64_t rows, int64_t n, T* u, int64_t ldu, double* s, T* w, int64_t ldw) {
-    RC_REQUIRE(n > 0 && n <= 8192 && rows >= n, "jacobi_svd: unsupported size %lld x %lld", (long long)rows, (long long)n);
+void jacobi_svd(rc_ctx* c, const T* g, int64_t ldg, int64_t rows, int64_t n, T* u, int64_t ldu, double* s, T* w, int64_t ldw, int* info_dev) {
+    RC_REQUIRE(n > 0 && n <= 16384 && rows >= n && rows < ((int64_t)1 << 31), "jacobi_svd: unsupported size %lld x %lld", (long long)rows, (long long)n);
     DevBuf<T> G(c, (size_t)rows * n), V(c, (size_t)n * n);
     DevBuf<double> sig(c, (size_t)n);
-    DevBuf<int> info(c, 2);
+    DevBuf<int> info_own;
+    if (!info_dev) { info_own.alloc(c, 2); info_dev = info_own.p; }
+    struct { int* p; } info{info_dev};
     // column-major copy of g == transpose of the row-major matrix
     k_transpose<T>(c, G.p, rows, g, ldg, rows, n, false);
     double eps = (sizeof(RealOf<T>) == 4) ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
-    double tol = eps * sqrt((double)rows);
+    // rotation threshold on the cosine of a column pair (?gesvj: sqrt(m) eps).  For very short columns the floor of 8 eps
+    // keeps the threshold above the rounding error of the computed Gram entries themselves (a 2 x 2 factor could rotate
+    // for ever on an eps-sized cosine and report non-convergence).
+    double tol = eps * sqrt((double)std::max<int64_t>(rows, 64));
     // column stride of the shared-memory copy: an odd multiple of 64 bytes when the rows would otherwise put every
     // column on the same banks (the lane groups of a warp work on different columns)
     const int ldc = (int)((rows * sizeof(T)) % 128 == 0 ? rows + (int64_t)(64 / sizeof(T)) : rows);
@@ -215,10 +380,26 @@ void jacobi_svd(rc_ctx* c, const T* g, int64_t ldg, int64_t rows, int64_t n, T* 
         if (SM) RC_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, SM, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         jacobi_kernel<T, SM, L><<<1, nthreads, SM ? smem : 0, c->stream>>>(G.p, V.p, (int)rows, (int)n, ldc, 60, tol, u, ldu, s, w, ldw, sig.p, info.p); \
     } while (0)
-    if (fits) { if (lpp == 8) RC_JACOBI(true, 8); else if (lpp == 16) RC_JACOBI(true, 16); else RC_JACOBI(true, 32); }
-    else { if (lpp == 8) RC_JACOBI(false, 8); else if (lpp == 16) RC_JACOBI(false, 16); else RC_JACOBI(false, 32); }
+    if (fits) {
+        if (lpp == 8) RC_JACOBI(true, 8); else if (lpp == 16) RC_JACOBI(true, 16); else RC_JACOBI(true, 32);
+        RC_CHECK_LAUNCH(c);
+    } else {
+        // does not fit one CTA: the cooperative whole-GPU kernel (one warp per column pair, one grid sync per round)
+        int per_sm = 0;
+        RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_grid_kernel<T>, JG_NT, 0));
+        const int want = half;                       // one CTA per column pair of a round
+        int grid = std::max(1, std::min(want, per_sm * c->sm_count));
+        const int max_sweeps = 60;
+        DevBuf<int> flags(c, (size_t)max_sweeps + 1);
+        RC_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int) * (max_sweeps + 1), c->stream));
+        T* Gp = G.p; T* Vp = V.p;
+        int rows_i = (int)rows, n_i = (int)n, ms = max_sweeps;
+        double* sigp = sig.p; int* flp = flags.p; int* infp = info.p;
+        void* args[] = {&Gp, &Vp, &rows_i, &n_i, &ms, &tol, &flp, &u, &ldu, &s, &w, &ldw, &sigp, &infp};
+        RC_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_grid_kernel<T>, dim3(grid), dim3(JG_NT), args, 0, c->stream));
+        RC_COUNT_LAUNCH(c);
+    }
 #undef RC_JACOBI
-    RC_CHECK_LAUNCH(c);
     if (c->trace) {
         int h[2] = {0, 0};
         RC_CUDA(cudaMemcpyAsync(h, info.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -227,7 +408,7 @@ void jacobi_svd(rc_ctx* c, const T* g, int64_t ldg, int64_t rows, int64_t n, T* 
     }
 }
 
-template void jacobi_svd<float>(rc_ctx*, const float*, int64_t, int64_t, int64_t, float*, int64_t, double*, float*, int64_t);
-template void jacobi_svd<double>(rc_ctx*, const double*, int64_t, int64_t, int64_t, double*, int64_t, double*, double*, int64_t);
-template void jacobi_svd<c32>(rc_ctx*, const c32*, int64_t, int64_t, int64_t, c32*, int64_t, double*, c32*, int64_t);
-template void jacobi_svd<c64>(rc_ctx*, const c64*, int64_t, int64_t, int64_t, c64*, int64_t, double*, c64*, int64_t);
+template void jacobi_svd<float>(rc_ctx*, const float*, int64_t, int64_t, int64_t, float*, int64_t, double*, float*, int64_t, int*);
+template void jacobi_svd<double>(rc_ctx*, const double*, int64_t, int64_t, int64_t, double*, int64_t, double*, double*, int64_t, int*);
+template void jacobi_svd<c32>(rc_ctx*, const c32*, int64_t, int64_t, int64_t, c32*, int64_t, double*, c32*, int64_t, int*);
+template void jacobi_svd<c64>(rc_ctx*, const c64*, int64_t, int64_t, int64_t, c64*, int64_t, double*, c64*, int64_t, int*);

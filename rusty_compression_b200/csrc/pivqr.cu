@@ -294,7 +294,10 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int cap, int 
             // a time with all its rows PREFETCHED INTO REGISTERS (RG per lane, loads issued back to back): the
             // column costs one L2 round trip instead of one per row iteration -- mixed into the loop above they
             // stretched the update phase from ~5 000 to 21 000 cycles per step at config 3.
-            constexpr int RG = sizeof(T) == 4 ? 10 : (sizeof(T) == 8 ? 8 : 4);
+            // (10 rows per lane for the 4- and 8-byte scalars: every step of a 320-row factor -- config 3 with the pivot
+            // decisions in double -- takes the prefetched path; with 8 the first 64 steps fell back to the row loop below,
+            // one dependent L2 round trip per 32 rows, and the update phase averaged 29 000 cycles per step)
+            constexpr int RG = sizeof(T) <= 8 ? 10 : 4;
             for (int li = cap + ((warp - cap % NW + NW) % NW); li < nl; li += NW) {
                 if (lpos[li] <= i) continue;                       // warp-uniform
                 T* col = W + (int64_t)(li * G + b) * ldw;
@@ -850,9 +853,62 @@ bool pivqr_fused(rc_ctx* c, const T* in, int64_t ldin, int mode, int64_t p, int6
     return pivqr_fused_launch<T, T>(c, in, ldin, mode, p, n, ncq, r, ldr, ind, q, ldq);
 }
 
+// Compact-WY triangle of a block of nb reflectors (?larft, forward / columnwise) from their Gram matrix
+// S = V^H V (nb x nb row-major):  T[i][i] = tau_i,  T[0:i, i] = -tau_i T[0:i, 0:i] S[0:i, i].  One CTA, thread a owns row a.
+template <class T>
+__global__ void larft_kernel(const T* __restrict__ S, int64_t lds, const T* __restrict__ tau, int nb, T* __restrict__ Tout, int64_t ldt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Ts = reinterpret_cast<T*>(smem_raw);            // nb x nb
+    const int a = threadIdx.x;
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) Ts[e] = rc_zero<T>();
+    __syncthreads();
+    for (int i = 0; i < nb; ++i) {
+        const T ti = tau[i];
+        if (a < i) {
+            T acc = rc_zero<T>();
+            for (int b = a; b < i; ++b) acc = acc + Ts[a * nb + b] * S[(int64_t)b * lds + i];
+            Ts[a * nb + i] = rc_zero<T>() - ti * acc;
+        } else if (a == i) {
+            Ts[a * nb + i] = ti;
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) Tout[(int64_t)(e / nb) * ldt + (e % nb)] = Ts[e];
+}
+
+// Large factors: Q = H_0 ... H_{kk-1} I[:, :nc] by blocks of FQ_NB reflectors in compact-WY form,
+// Q <- (I - V_b T_b V_b^H) Q from the last block to the first, all the work in GEMMs (the one-warp-per-column kernel
+// re-reads every reflector for every column: p^2 nc words of L2 traffic).  Block b = reflectors j0 .. j1-1 only touches
+// rows >= j0 and columns >= j0 of Q (e_c is invariant under the reflectors j > c), so the GEMMs shrink with j0.
+constexpr int FQ_NB = 64;
+template <class T>
+static void pivqr_form_q_blocked(rc_ctx* c, const T* vbuf, const T* tau, int64_t p, int64_t kk, int64_t nc, T* q, int64_t ldq) {
+    // reflectors as a p x kk row-major matrix (vbuf is column-major p x kk = row-major kk x p)
+    DevBuf<T> vr(c, (size_t)p * kk);
+    k_transpose<T>(c, vr.p, kk, vbuf, p, kk, p, false);
+    k_eye<T>(c, q, p, nc, ldq);
+    DevBuf<T> s(c, (size_t)FQ_NB * FQ_NB), t(c, (size_t)FQ_NB * FQ_NB), w(c, (size_t)FQ_NB * nc), tw(c, (size_t)FQ_NB * nc);
+    RC_CUDA(cudaFuncSetAttribute(larft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FQ_NB * FQ_NB * sizeof(T))));
+    const int64_t nblk = (kk + FQ_NB - 1) / FQ_NB;
+    for (int64_t b = nblk - 1; b >= 0; --b) {
+        const int64_t j0 = b * FQ_NB, nb = std::min<int64_t>(FQ_NB, kk - j0);
+        if (j0 >= nc) continue;                          // no column of I[:, :nc] is touched by this block
+        const int64_t rows = p - j0, cols = nc - j0;
+        const T* vb = vr.p + j0 * kk + j0;               // (p - j0) x nb, ld = kk
+        T* qb = q + j0 * ldq + j0;                        // (p - j0) x (nc - j0)
+        gemm<T>(c, RC_OP_H, RC_OP_N, nb, nb, rows, vb, kk, vb, kk, s.p, FQ_NB, rc_one<T>(), rc_zero<T>());
+        larft_kernel<T><<<1, FQ_NB, FQ_NB * FQ_NB * sizeof(T), c->stream>>>(s.p, FQ_NB, tau + j0, (int)nb, t.p, FQ_NB);
+        RC_CHECK_LAUNCH(c);
+        gemm<T>(c, RC_OP_H, RC_OP_N, nb, cols, rows, vb, kk, qb, ldq, w.p, cols, rc_one<T>(), rc_zero<T>());
+        gemm<T>(c, RC_OP_N, RC_OP_N, nb, cols, nb, t.p, FQ_NB, w.p, cols, tw.p, cols, rc_one<T>(), rc_zero<T>());
+        gemm<T>(c, RC_OP_N, RC_OP_N, rows, cols, nb, vb, kk, tw.p, cols, qb, ldq, rc_zero<T>() - rc_one<T>(), rc_one<T>());
+    }
+}
+
 template <class T>
 void pivqr_form_q(rc_ctx* c, const T* vbuf, const T* tau, int64_t p, int64_t kk, int64_t nc, T* q, int64_t ldq) {
     if (nc == 0) return;
+    if (p >= 512 && nc >= 128 && kk >= 128) { pivqr_form_q_blocked<T>(c, vbuf, tau, p, kk, nc, q, ldq); return; }
     DevBuf<T> qc(c, (size_t)p * nc);
     int warps = 4;
     int nb = (int)((nc + warps - 1) / warps);

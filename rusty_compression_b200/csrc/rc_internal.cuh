@@ -47,6 +47,7 @@ struct rc_ctx {
     // options
     int gemm_impl = 0;            // 0 auto, 1 generic only
     int f32_precision = 0;        // option "f32_precision": 0 = 3xTF32 split (f32-accurate, default), 1 = bf16 single product (opt-in)
+    int tf32_ring = 0;            // option "tf32_ring": 1 = deeper TMEM split ring in the tcgen05 TF32 kernel (A/B tuning)
     int dmma_tail = 1;            // 1: ragged last column group of the DMMA GEMM on the DFMA tail path (gemm_dmma.cu)
     int true_power_iteration = 0;
     int trace = 0;                // option "trace": print wall time between rc_trace() marks (stream-synchronising)
@@ -255,8 +256,10 @@ void pivqr_form_q(rc_ctx*, const T* vbuf, const T* tau, int64_t p, int64_t kk, i
 // ------------------------------------------------------------------ jacobi.cu
 // One-sided Jacobi SVD of a small rows x n matrix G (row-major, ld; rows >= n): G = U diag(s) W^H.
 // On exit u (rows x n row-major), s (n, descending, double), w (n x n row-major).
+// info_dev (optional, 2 ints on device): {1 if the sweep limit was reached without convergence, sweeps used}.
 template <class T>
-void jacobi_svd(rc_ctx*, const T* g, int64_t ldg, int64_t rows, int64_t n, T* u, int64_t ldu, double* s, T* w, int64_t ldw);
+void jacobi_svd(rc_ctx*, const T* g, int64_t ldg, int64_t rows, int64_t n, T* u, int64_t ldu, double* s, T* w, int64_t ldw,
+                int* info_dev = nullptr);
 
 // ------------------------------------------------------------------ trsm.cu
 // X (k x nrhs, ldx) = U^{-1} B (k x nrhs, ldb), U k x k upper triangular (row-major ldu);

@@ -2,7 +2,7 @@
 # Profiling recipe (B200_PROFILING.md): plain run first, then the ncu launch list, then one
 # --set full capture of the dominant kernels.  Usage: tools/gpu_profile.sh <tag>
 TAG=${1:-rX}
-CMD="python bench.py --steps 1 --warmup 1 --skip-cpu --skip-e2e"
+CMD="python bench.py --steps 1 --warmup 1 --skip-cpu --skip-e2e --skip-sub"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_list_$TAG.log | cut -c1-300
