@@ -253,15 +253,23 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t acce0 = accf0 + 16;                                                 // accumulator buffer drained (2)
 
     constexpr int npad = NPADC;
+    // PREC: 0 = 3xTF32 with A_hi and A_lo in tensor memory; 1 = bf16 single product; 2 = 3xTF32 with the HIGH part taken
+    // straight from the raw tile in shared memory (SS-form MMAs: the tensor core reads only the top 19 bits of a TF32
+    // operand, i.e. hi = a truncated, so only lo = a - trunc(a) has to be produced and stored to tensor memory -- half
+    // the splitter's tcgen05.st traffic and half the TMEM per stage; NN mode only)
+    constexpr bool TF32 = (PREC != 1);
+    constexpr bool HS = (PREC == 2);
+    static_assert(!(HS && TRANS), "the shared-memory high part needs the K-major raw tile of the NN mode");
+    constexpr int ACOLS = HS ? 32 : A_TMEM_COLS;                 // TMEM columns of one split stage
     constexpr uint32_t A_BYTES = BM * BK * 4;                    // 16 KB
-    constexpr uint32_t B_BYTES = (uint32_t)NPADC * BK * (PREC == 0 ? 4 : 2);      // one X^T tile: f32 hi (and lo) / bf16
-    constexpr uint32_t B_STAGE = PREC == 0 ? 2 * B_BYTES : B_BYTES;
+    constexpr uint32_t B_BYTES = (uint32_t)NPADC * BK * (TF32 ? 4 : 2);      // one X^T tile: f32 hi (and lo) / bf16
+    constexpr uint32_t B_STAGE = TF32 ? 2 * B_BYTES : B_BYTES;
     const uint32_t raw_base = smem_base;
     const uint32_t bt_base = raw_base + RS * A_BYTES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < RS; ++s) { mbar_init(rawfull0 + 8 * s, 1); mbar_init(rawempty0 + 8 * s, 4); }
+        for (int s = 0; s < RS; ++s) { mbar_init(rawfull0 + 8 * s, 1); mbar_init(rawempty0 + 8 * s, HS ? 5 : 4); }   // HS: + the MMAs' commit
         for (int s = 0; s < MS; ++s) { mbar_init(split0 + 8 * s, 4); mbar_init(aempty0 + 8 * s, 1); }
         for (int s = 0; s < BS; ++s) mbar_init(bfull0 + 8 * s, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4); }
@@ -335,7 +343,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t fb = bfull0 + 8 * bs;
                     mbar_expect_tx(fb, B_STAGE);
                     tma_load_2d(sb, &tmBhi, kb * BK, ch_ * npad, fb);                             // [npad rows][32 k]
-                    if (PREC == 0) tma_load_2d(sb + B_BYTES, &tmBlo, kb * BK, ch_ * npad, fb);
+                    if (TF32) tma_load_2d(sb + B_BYTES, &tmBlo, kb * BK, ch_ * npad, fb);
                     if (++bs == BS) { bs = 0; bph ^= 1u; }
                 }
             }
@@ -346,12 +354,14 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // compile to plain uniform-datapath issues); the single-thread form of this loop spent ~100 cycles
         // per MMA on elect/branch scaffolding and capped the kernel at 12 MMAs per 1380 cycles.
         {
-            const uint32_t idesc = PREC == 0 ? umma_idesc_tf32((uint32_t)npad) : umma_idesc_bf16((uint32_t)npad);
+            const uint32_t idesc = TF32 ? umma_idesc_tf32((uint32_t)npad) : umma_idesc_bf16((uint32_t)npad);
             // UMMA shared-memory descriptor of the X^T tiles: constant high word, low word = address >> 4
             // (f32 tiles: 128-byte rows, SWIZZLE_128B, 8-row atoms of 1024 B; bf16 tiles: 64-byte rows, SWIZZLE_64B, 512 B)
-            const uint64_t desc_hi = PREC == 0 ? (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32
+            const uint64_t desc_hi = TF32 ? (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32
                                                : (uint64_t)((512u >> 4) | (1u << 14) | (4u << 29)) << 32;
             const uint32_t bt_lo = (bt_base & 0x3FFFFu) >> 4;
+            const uint32_t raw_lo = (raw_base & 0x3FFFFu) >> 4;
+            int rs = 0;                                              // HS: raw slot of the current k-block
             int ms = 0; uint32_t mph = 0;
             int bs = 0; uint32_t bph = 0;
             int it = 0;                                              // counts K-chunks (TMEM buffer hand-offs)
@@ -368,13 +378,25 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         mbar_wait(split0 + 8 * ms, mph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (elect_one()) {
-                            const uint32_t a_hi = tmem_base + (uint32_t)(2 * npad + ms * A_TMEM_COLS), a_lo = a_hi + 32u;
+                            const uint32_t a_hi = tmem_base + (uint32_t)(2 * npad + ms * ACOLS), a_lo = HS ? a_hi : a_hi + 32u;
                             const uint32_t bh = bt_lo + (uint32_t)bs * (B_STAGE >> 4), bl = bh + (B_BYTES >> 4);
                             if (PREC == 1) {
                                 // one product, bf16: K = 16 per MMA = 32 bytes along the 64-byte row = 8 TMEM columns of A
 #pragma unroll
                                 for (int k = 0; k < BK / 16; ++k)
                                     umma_bf16_ts(d_tmem, a_hi + 8u * k, desc_hi | (uint64_t)(bh + 2u * k), idesc, (kb != kc0 || k != 0) ? 1u : 0u);
+                            } else if (HS) {
+                                // raw tile [128 rows][32 k] f32, SWIZZLE_128B: the same K-major layout as the X^T tiles
+                                const uint32_t ar = raw_lo + (uint32_t)rs * (A_BYTES >> 4);
+#pragma unroll
+                                for (int k = 0; k < BK / 8; ++k) {
+                                    const uint64_t dbh = desc_hi | (uint64_t)(bh + 2u * k), dbl = desc_hi | (uint64_t)(bl + 2u * k);
+                                    const uint64_t da = desc_hi | (uint64_t)(ar + 2u * k);
+                                    umma_tf32_ts(d_tmem, a_lo + 8u * k, dbh, idesc, (kb != kc0 || k != 0) ? 1u : 0u);
+                                    umma_tf32(d_tmem, da, dbl, idesc, 1u);
+                                    umma_tf32(d_tmem, da, dbh, idesc, 1u);
+                                }
+                                umma_commit(rawempty0 + 8 * rs);             // the raw slot is free when the SS MMAs have read it
                             } else
 #pragma unroll
                             for (int k = 0; k < BK / 8; ++k) {
@@ -389,6 +411,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             if (kb == kc1 - 1) umma_commit(accf0 + 8 * buf);
                         }
                         __syncwarp();
+                        if (++rs == RS) rs = 0;
                         if (++ms == MS) { ms = 0; mph ^= 1u; }
                         if (++bs == BS) { bs = 0; bph ^= 1u; }
                     }
@@ -432,7 +455,14 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         vals[k] = *reinterpret_cast<const float*>(rawb + k * 128 + ((((lane >> 2) ^ (k & 7)) << 4) | ((lane & 3) << 2)));
                 }
                 uint32_t hi[32], lo[32];
-                if (PREC == 0) {
+                if (HS) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const uint32_t u = __float_as_uint(vals[k]) & 0xFFFFE000u;      // what the tensor core reads of a
+                        hi[k] = u;
+                        lo[k] = __float_as_uint(vals[k] - __uint_as_float(u));
+                    }
+                } else if (PREC == 0) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         uint32_t u;
@@ -452,8 +482,10 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 mbar_wait(aempty0 + 8 * ms, mph ^ 1u);                   // MMAs that read this TMEM stage are done
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * npad + ms * A_TMEM_COLS);
-                if (PREC == 0) {
+                const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * npad + ms * ACOLS);
+                if (HS) {
+                    tmem_st32(ta, lo);
+                } else if (PREC == 0) {
                     tmem_st32(ta, hi);
                     tmem_st32(ta + 32u, lo);
                 } else {
@@ -614,11 +646,12 @@ template <int RS, int MS, int BS, int NPADC, bool TRANS, int PREC>
 void launch_tf32(rc_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
                  Tf32Params prm) {
     static_assert(RS <= MAX_RS && MS <= MAX_MS && BS <= MAX_BS && MS == BS, "ring depth (A-TMEM and B rings share their release barrier)");
-    static_assert(2 * NPADC + MS * A_TMEM_COLS <= 512, "tensor memory columns");
-    constexpr size_t smem = (size_t)RS * BM * BK * 4 + (size_t)BS * (PREC == 0 ? 2 * NPADC * BK * 4 : NPADC * BK * 2) + 1024;
+    constexpr int ACOLS = PREC == 2 ? 32 : A_TMEM_COLS;
+    static_assert(2 * NPADC + MS * ACOLS <= 512, "tensor memory columns");
+    constexpr size_t smem = (size_t)RS * BM * BK * 4 + (size_t)BS * (PREC != 1 ? 2 * NPADC * BK * 4 : NPADC * BK * 2) + 1024;
     static_assert(smem <= 226 * 1024, "ring configuration exceeds shared memory");
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * NPADC + MS * A_TMEM_COLS)) cols <<= 1;
+    while (cols < (uint32_t)(2 * NPADC + MS * ACOLS)) cols <<= 1;
     prm.tmem_cols = cols;
     prm.agroup = 1;     // measured: 1 is best on B200 (2, 4, 8 are 0-4 % slower at 32768^2 x 64)
     prm.zero = 0;
@@ -639,7 +672,18 @@ void dispatch_tf32(rc_ctx* c, int npad, const CUtensorMap& tmA, const CUtensorMa
         }
         return;
     }
-    if (c->tf32_ring == 1) {
+    if constexpr (!TRANS) {
+        if (c->tf32_ring == 2) {
+            // high part from shared memory (PREC = 2), six split stages of 32 TMEM columns
+            switch (npad) {
+                case 32: launch_tf32<8, 6, 6, 32, TRANS, 2>(c, tmA, tmBhi, tmBlo, prm); break;
+                case 64: launch_tf32<7, 6, 6, 64, TRANS, 2>(c, tmA, tmBhi, tmBlo, prm); break;
+                default: launch_tf32<6, 5, 5, 96, TRANS, 2>(c, tmA, tmBhi, tmBlo, prm); break;
+            }
+            return;
+        }
+    }
+    if (c->tf32_ring >= 1) {
         // deeper split ring (option "tf32_ring" = 1): the splitters spend ~30 % of their samples waiting for the MMAs of
         // the stage four k-blocks back to retire (ncu, round 1) -- six TMEM stages of A_hi / A_lo next to the two accumulators
         switch (npad) {

@@ -54,7 +54,9 @@ __device__ __forceinline__ bool pk_elect_one() {
     asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred));
     return pred != 0;
 }
-__global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, int kind, unsigned* out) {
+// n = UMMA N (multiple of 16, <= 256); ts = 1: A operand from tensor memory (the TS form the TF32-split kernel uses);
+// one_acc = 1: every MMA accumulates into the same TMEM tile (a GEMM main loop), 0: two tiles alternate
+__global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, int kind, unsigned* out, int n = 256, int ts = 0, int one_acc = 0) {
     extern __shared__ unsigned char pk_smem[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_base_s;
@@ -78,14 +80,18 @@ __global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, int kind, 
         const uint64_t hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;     // K-major, SWIZZLE_128B, SBO 1024
         const uint64_t adesc = hi | (uint64_t)((base & 0x3FFFFu) >> 4), bdesc = hi | (uint64_t)(((base + 16384u) & 0x3FFFFu) >> 4);
         const uint32_t fmt = kind == 0 ? 2u : 1u;                                         // TF32 / BF16
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (((uint32_t)n >> 3) << 17) | ((128u >> 4) << 24);
         for (int it = 0; it < iters; ++it) {
             if (pk_elect_one()) {
-                const uint32_t d = tmem + (uint32_t)((it & 1) * 256);
+                const uint32_t d = tmem + (uint32_t)((one_acc || ts) ? 0 : (it & 1) * 256);
+                const uint32_t a_tm = tmem + 256u;          // TS form: 32 columns of (zero) A at column 256
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t acc = (it > 1 || k > 0) ? 1u : 0u;
-                    if (kind == 0)
+                    if (kind == 0 && ts)
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+                                     ::"r"(d), "r"(a_tm + 8u * k), "l"(bdesc + 2u * k), "r"(idesc), "r"(acc) : "memory");
+                    else if (kind == 0)
                         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
                                      ::"r"(d), "l"(adesc + 2u * k), "l"(bdesc + 2u * k), "r"(idesc), "r"(acc) : "memory");
                     else
@@ -124,7 +130,7 @@ template <class F> float time_ms(F f, int reps) {
     return best;
 }
 
-int main() {
+int main(int argc, char** argv) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     int sms = prop.multiProcessorCount;
@@ -150,6 +156,21 @@ int main() {
         tf32 = 2.0 * 128 * 256 * 8 * 4.0 * umma_iters * sms / (t4 * 1e-3) / 1e12;
         float t5 = time_ms([&] { umma_peak_kernel<<<sms, 128, pk_bytes>>>(umma_iters, 1, nullptr); }, 5);
         bf16 = 2.0 * 128 * 256 * 16 * 4.0 * umma_iters * sms / (t5 * 1e-3) / 1e12;
+    }
+    if (argc > 1 && prop.major == 10) {
+        // rc_peaks shapes: kind::tf32 MMA time by N and operand form (what bounds the TF32-split kernel at small l)
+        const int umma_iters = 8192;
+        const size_t pk_bytes = 48 * 1024 + 1024;
+        printf("kind::tf32 M = 128, K = 8 per MMA; cycles per MMA at %.0f MHz and TFLOP/s over %d SMs\n", clk / 1000.0, sms);
+        for (int form = 0; form < 3; ++form)
+            for (int nn : {32, 64, 96, 128, 192, 256}) {
+                const int ts_ = form == 2, one = form >= 1;
+                float t = time_ms([&] { umma_peak_kernel<<<sms, 128, pk_bytes>>>(umma_iters, 0, nullptr, nn, ts_, one); }, 5);
+                const double per = (double)t * 1e-3 * (clk * 1e3) / (4.0 * umma_iters);
+                printf("  %-34s N = %3d: %6.1f cycles per MMA, %7.1f TFLOP/s\n",
+                       form == 0 ? "SS, two accumulators alternating" : (form == 1 ? "SS, one accumulator" : "TS (A from TMEM), one accumulator"),
+                       nn, per, 2.0 * 128 * nn * 8 * 4.0 * umma_iters * sms / (t * 1e-3) / 1e12);
+            }
     }
     printf("{\"dfma_tflops\": %.3f, \"dmma_tflops\": %.3f, \"tf32_umma_tflops\": %.1f, \"bf16_umma_tflops\": %.1f, \"copy_gbs\": %.1f, "
            "\"sm_count\": %d, \"clock_mhz\": %.0f}\n", dfma, dmma, tf32, bf16, copy, sms, clk / 1000.0);

@@ -91,7 +91,7 @@ def test_large_dense_svd_matches_gesdd(api, dtype, shape):
     k = min(shape)
     assert u.shape == u0.shape and vt.shape == vt0.shape and s.shape == s0.shape
     assert np.all(np.diff(s) <= 0)
-    assert np.max(np.abs(s - s0)) / s0[0] < (2e-6 if single else 1e-13)
+    assert np.max(np.abs(s - s0)) / s0[0] < (2e-5 if single else 1e-12)          # (sgesdd itself is only good to ~n eps)
     if not single:
         assert np.max(np.abs(s - s0) / s0) < 1e-8
     assert relerr((u * s).dot(vt), a) < (2e-5 if single else 1e-12)

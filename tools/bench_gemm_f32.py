@@ -13,10 +13,10 @@ if len(sys.argv) > 1:
 for (m, n, l) in shapes:
     a = api.DeviceMatrix.random_gaussian((m, n), np.float32, 1)
     x = api.DeviceMatrix.random_gaussian((n, l), np.float32, 2)
-    for impl in ((0, 3, 2) if os.environ.get('RC_SKIP_SIMT') else (0, 3, 2, 1)):
+    for impl in ((0, 3, 4, 2) if os.environ.get('RC_SKIP_SIMT') else (0, 3, 4, 2, 1)):
         ctx.set_option("gemm_impl", 1 if impl == 1 else 0)
         ctx.set_option("f32_precision", 1 if impl == 2 else 0)
-        ctx.set_option("tf32_ring", 1 if impl == 3 else 0)
+        ctx.set_option("tf32_ring", {3: 1, 4: 2}.get(impl, 0))
         for _ in range(2): y = a.matmat(x)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -33,6 +33,6 @@ for (m, n, l) in shapes:
         e1.record(stream); torch.cuda.synchronize()
         ms_t = e0.elapsed_time(e1) / reps
         print(f"   A^T Y: {ms_t:.3f} ms  {2*m*n*l/ms_t/1e9:.1f} TFLOP/s  {m*n*4/ms_t/1e6:.0f} GB/s", flush=True)
-        print(f"{m}x{n}x{l} f32 impl={ {0: 'tcgen05-tf32x3', 3: 'tcgen05-tf32x3 deep split ring', 2: 'tcgen05-bf16', 1: 'simt'}[impl] }: {ms:.3f} ms  {2*m*n*l/ms/1e9:.1f} TFLOP/s  {m*n*4/ms/1e6:.0f} GB/s", flush=True)
+        print(f"{m}x{n}x{l} f32 impl={ {0: 'tcgen05-tf32x3', 3: 'tcgen05-tf32x3 deep split ring', 4: 'tcgen05-tf32x3 hi from smem (SS) + deep ring', 2: 'tcgen05-bf16', 1: 'simt'}[impl] }: {ms:.3f} ms  {2*m*n*l/ms/1e9:.1f} TFLOP/s  {m*n*4/ms/1e6:.0f} GB/s", flush=True)
     ctx.set_option("gemm_impl", 0); ctx.set_option("f32_precision", 0); ctx.set_option("tf32_ring", 0)
     del a, x, y

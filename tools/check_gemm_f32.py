@@ -5,6 +5,8 @@ import numpy as np
 from rusty_compression_b200 import api
 
 rng = np.random.default_rng(0)
+if os.environ.get('RC_TF32_RING'):
+    api.default_context().set_option('tf32_ring', int(os.environ['RC_TF32_RING']))
 shapes = [(4096, 128, 2048), (4096, 128, 128), (4096, 64, 128), (4096, 128, 256), (4096, 256, 128), (4096, 2048, 128),
           (4096, 1024, 74), (4096, 1024, 148), (4096, 1024, 266), (8192, 4096, 320), (1000, 333, 130), (4096, 64, 1024),
           (4096, 96, 2048), (512, 128, 2048), (4096, 128, 384)]
