@@ -395,11 +395,26 @@ def sharded_parity(api, ctx, world, rank, local):
         rec = {"workload": f"f64 {m}x{n} row-sharded over {world} GPUs vs the unsharded CUDA path on the gathered matrix (rank {k} (+{p}))",
                "max_rel_singular_value_deviation": float(np.max(np.abs(s_sh - s_1) / s_1)),
                "skeleton_columns_identical": bool(np.array_equal(col_sh, cid1.col_ind[:k])),
-               "skeleton_rows_identical": bool(np.array_equal(row_sh, cid1.two_sided_id().row_ind[:k]))}
+               "skeleton_rows_identical": None}
+        row_1 = cid1.two_sided_id().row_ind[:k].copy()
+        rec["skeleton_rows_identical"] = bool(np.array_equal(row_sh, row_1))
+        # every handle of ctx1 goes before the context does
         a_full.free()
+        for h in (q1, q3, cid1):
+            h.free()
+        del q1, q3, cid1
+        import gc
+        gc.collect()
         ctx1.close()
     a_loc.free()
     return rec
+
+
+def _mark(msg):
+    """Progress marks on stderr (never stdout: exactly one JSON line goes there)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write(f"[bench] {time.strftime('%H:%M:%S')} {msg}\n")
+        sys.stderr.flush()
 
 
 def _claim_stdout():
@@ -506,7 +521,9 @@ def main():
         for _ in range(12):
             step_device()
         barrier()
+    _mark("timed region: configs[1] step")
     ms_step = timed(step_device, args.steps, args.warmup, on_start=sampler.mark)
+    _mark(f"configs[1]: {ms_step:.3f} ms per step")
     launches = (ctx.counter("kernel_launches") - launches_before) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
@@ -547,6 +564,7 @@ def main():
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D of A, D2H of U, s, Vt
     e2e = None
+    _mark("roofline leg done; e2e leg")
     if not args.skip_e2e:
         a_host = torch.empty((m, n), dtype=torch.float64, pin_memory=True)
         a_np = a_host.numpy()
@@ -588,7 +606,9 @@ def main():
         peaks_all = roofline["own_measured_peaks"] if roofline else {}
 
         def guarded(name, fn):
+            _mark(f"sub-record {name}")
             try:
+                ctx.set_option("release_workspaces", 1)      # every sub-record starts from an empty workspace cache
                 r = fn()
                 if rank == 0 and r is not None:
                     sub[name] = r
@@ -602,6 +622,7 @@ def main():
         if world > 1:
             guarded("config4_strong", lambda: bench_config4(api, ctx, timed, peaks_all, hbm_peak, world, rank))
             guarded("sharded_parity", lambda: sharded_parity(api, ctx, world, rank, local))
+    _mark("sub-records done; cpu_baseline leg")
     if rank == 0:
         cpu = None
         if not args.skip_cpu and world == 1:       # the CPU baseline is an N = 1 figure

@@ -237,7 +237,10 @@ class DeviceMatrix:
         return self.conj_matmat(np.asarray(x).reshape(-1, 1)).to_numpy()[:, 0]
 
     def free(self):
-        if self.owned and self.h:
+        # a handle that outlives its context is dropped, not freed: rc_ctx_destroy has released the context object the
+        # handle points into, so freeing through it would be a use-after-free (the device buffer is leaked instead --
+        # free the handles before Context.close())
+        if self.owned and self.h and getattr(self.ctx, "h", None):
             self.ctx.lib.rc_matrix_free(self.h)
         self.h = None
 
@@ -313,7 +316,7 @@ class _Handle:
         return _borrow(self.ctx, getter(self.h))
 
     def free(self):
-        if self.h:
+        if self.h and getattr(self.ctx, "h", None):          # (see DeviceMatrix.free)
             getattr(self.ctx.lib, self._free)(self.h)
         self.h = None
 

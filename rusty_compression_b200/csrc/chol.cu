@@ -4,6 +4,7 @@
 // status[0] = 0 ok / 1 breakdown (non-positive pivot), status[1] = min diag(R), status[2] = max diag(R),
 // status[3] = max |G - I| of the input (orthogonality defect when G is a Gram matrix of a Q factor).
 #include "rc_internal.cuh"
+#include "host_linalg.cuh"
 
 namespace {
 
@@ -186,6 +187,77 @@ bool chol_inv(rc_ctx* c, const T* g, int64_t ldg, int64_t w, T* r, T* rinv, int6
     RC_CHECK_LAUNCH(c);
     return true;
 }
+namespace {
+// status words of the 2 x 2 blocked factorisation from those of its two diagonal blocks and the full Gram matrix:
+// {breakdown in either block, min diag R, max diag R, max |G - I| over the whole w x w input}
+template <class T>
+__global__ void __launch_bounds__(256)
+chol_blocked_status_kernel(const T* __restrict__ g, int64_t ldg, int w, const double* __restrict__ sa, const double* __restrict__ sb,
+                           double* __restrict__ status) {
+    __shared__ double s_red[8];
+    double defect = 0.0;
+    for (int e = threadIdx.x; e < w * w; e += 256) {
+        const int i = e / w, j = e - i * w;
+        const T v = g[(int64_t)i * ldg + j];
+        const T d = (i == j) ? v - rc_one<T>() : v;
+        defect = fmax(defect, rc_abs(d));
+    }
+    for (int m = 16; m > 0; m >>= 1) defect = fmax(defect, __shfl_xor_sync(0xffffffffu, defect, m));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = defect;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double d = 0.0;
+        for (int i = 0; i < 8; ++i) d = fmax(d, s_red[i]);
+        status[0] = (sa[0] != 0.0 || sb[0] != 0.0) ? 1.0 : 0.0;
+        status[1] = fmin(sa[1], sb[1]);
+        status[2] = fmax(sa[2], sb[2]);
+        status[3] = d;
+    }
+}
+}  // namespace
+
+// Gram matrices wider than one CTA's shared memory (w <= 2 x chol_max_width: the 266-column f32 sketch of config 4, the
+// 138-column c64 sketch of config 5): one level of 2 x 2 blocking around the one-CTA kernel,
+//   G = [G11 G12; G12^H G22]:  R11 = chol(G11),  R12 = R11^{-H} G12,  R22 = chol(G22 - R12^H R12),
+//   R^{-1} = [R11^{-1}, -R11^{-1} R12 R22^{-1}; 0, R22^{-1}],
+// all the off-diagonal work in (small) GEMMs.  Same status words as chol_inv (breakdown of either block is a breakdown).
+template <class T>
+bool chol_inv_blocked(rc_ctx* c, const T* g, int64_t ldg, int64_t w, T* r, T* rinv, int64_t ldo, double* status_dev) {
+    if (chol_inv<T>(c, g, ldg, w, r, rinv, ldo, status_dev)) return true;
+    const int dtype = ScalarTraits<T>::code;       // rc_dtype: RC_F32 = 0, RC_F64 = 1, RC_C32 = 2, RC_C64 = 3
+    const int64_t wmax = chol_max_width(c, dtype);
+    if (w > 2 * wmax || w > 512) return false;
+    const int64_t e = std::max<int64_t>(1, (int64_t)(16 / sizeof(T)));
+    const int64_t w1 = std::min<int64_t>(wmax / e * e, ((w + 1) / 2 + e - 1) / e * e), w2 = w - w1;
+    if (w2 <= 0 || w2 > wmax) return false;
+    const int64_t l1 = rc_pad_ld(dtype, w1), l2 = rc_pad_ld(dtype, w2);
+    DevBuf<T> r11(c, (size_t)w1 * l1), ri11(c, (size_t)w1 * l1), r12(c, (size_t)w1 * l2), s22(c, (size_t)w2 * l2),
+        r22(c, (size_t)w2 * l2), ri22(c, (size_t)w2 * l2), t12(c, (size_t)w1 * l2), x12(c, (size_t)w1 * l2);
+    DevBuf<double> st(c, 8);
+    if (!chol_inv<T>(c, g, ldg, w1, r11.p, ri11.p, l1, st.p)) return false;
+    // R12 = R11^{-H} G12
+    gemm<T>(c, RC_OP_H, RC_OP_N, w1, w2, w1, ri11.p, l1, g + w1, ldg, r12.p, l2, rc_one<T>(), rc_zero<T>());
+    // S = G22 - R12^H R12
+    gemm<T>(c, RC_OP_H, RC_OP_N, w2, w2, w1, r12.p, l2, r12.p, l2, s22.p, l2, rc_one<T>(), rc_zero<T>());
+    k_sub<T>(c, s22.p, l2, g + w1 * ldg + w1, ldg, s22.p, l2, w2, w2);
+    if (!chol_inv<T>(c, s22.p, l2, w2, r22.p, ri22.p, l2, st.p + 4)) return false;
+    // X12 = -R11^{-1} R12 R22^{-1}
+    gemm<T>(c, RC_OP_N, RC_OP_N, w1, w2, w1, ri11.p, l1, r12.p, l2, t12.p, l2, rc_one<T>(), rc_zero<T>());
+    gemm<T>(c, RC_OP_N, RC_OP_N, w1, w2, w2, t12.p, l2, ri22.p, l2, x12.p, l2, rc_zero<T>() - rc_one<T>(), rc_zero<T>());
+    // assemble R and R^{-1} (upper block-triangular, zeros below)
+    k_fill<T>(c, r, w, w, ldo, rc_zero<T>());
+    k_fill<T>(c, rinv, w, w, ldo, rc_zero<T>());
+    k_copy<T>(c, r, ldo, r11.p, l1, w1, w1);
+    k_copy<T>(c, r + w1, ldo, r12.p, l2, w1, w2);
+    k_copy<T>(c, r + w1 * ldo + w1, ldo, r22.p, l2, w2, w2);
+    k_copy<T>(c, rinv, ldo, ri11.p, l1, w1, w1);
+    k_copy<T>(c, rinv + w1, ldo, x12.p, l2, w1, w2);
+    k_copy<T>(c, rinv + w1 * ldo + w1, ldo, ri22.p, l2, w2, w2);
+    chol_blocked_status_kernel<T><<<1, 256, 0, c->stream>>>(g, ldg, (int)w, st.p, st.p + 4, status_dev);
+    RC_CHECK_LAUNCH(c);
+    return true;
+}
+
 int64_t chol_max_width(rc_ctx* c, int dtype) {
     size_t lim = (c->smem_optin ? c->smem_optin : (size_t)227 * 1024) - 8192;
     int64_t w = 1;
@@ -197,3 +269,7 @@ template bool chol_inv<float>(rc_ctx*, const float*, int64_t, int64_t, float*, f
 template bool chol_inv<double>(rc_ctx*, const double*, int64_t, int64_t, double*, double*, int64_t, double*);
 template bool chol_inv<c32>(rc_ctx*, const c32*, int64_t, int64_t, c32*, c32*, int64_t, double*);
 template bool chol_inv<c64>(rc_ctx*, const c64*, int64_t, int64_t, c64*, c64*, int64_t, double*);
+template bool chol_inv_blocked<float>(rc_ctx*, const float*, int64_t, int64_t, float*, float*, int64_t, double*);
+template bool chol_inv_blocked<double>(rc_ctx*, const double*, int64_t, int64_t, double*, double*, int64_t, double*);
+template bool chol_inv_blocked<c32>(rc_ctx*, const c32*, int64_t, int64_t, c32*, c32*, int64_t, double*);
+template bool chol_inv_blocked<c64>(rc_ctx*, const c64*, int64_t, int64_t, c64*, c64*, int64_t, double*);

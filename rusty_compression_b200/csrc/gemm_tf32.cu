@@ -726,10 +726,11 @@ bool gemm_tf32x3_f32(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float* A,
         tmBhi = make_map_bf16(bfT.p, nrows, K, ldt, npad);
         tmBlo = tmBhi;
     } else {
-        hiT.alloc(c, (size_t)nrows * ldt); loT.alloc(c, (size_t)nrows * ldt);
-        launch_split_transpose(c, X, ldx, K, (int)N, nrows, hiT.p, loT.p, ldt);
-        tmBhi = make_map_f32(hiT.p, nrows, K, ldt, npad);
-        tmBlo = make_map_f32(loT.p, nrows, K, ldt, npad);
+        // only the N real rows exist: the TMA zero-fills the out-of-bounds rows of the last chunk's box
+        hiT.alloc(c, (size_t)N * ldt); loT.alloc(c, (size_t)N * ldt);
+        launch_split_transpose(c, X, ldx, K, (int)N, (int)N, hiT.p, loT.p, ldt);
+        tmBhi = make_map_f32(hiT.p, N, K, ldt, npad);
+        tmBlo = make_map_f32(loT.p, N, K, ldt, npad);
     }
     Tf32Params prm;
     prm.y = Y; prm.ldy = ldy; prm.M = (int)M; prm.N = (int)N; prm.K = (int)K; prm.npad = npad;
@@ -769,10 +770,10 @@ bool gemm_tf32x3_f32_tn(rc_ctx* c, int64_t M, int64_t N, int64_t K, const float*
         tmBhi = make_map_bf16(bfT.p, nrows, K, ldt, npad);
         tmBlo = tmBhi;
     } else {
-        hi.alloc(c, (size_t)nrows * ldt); lo.alloc(c, (size_t)nrows * ldt);
-        launch_split_transpose(c, Y, ldy, K, (int)N, nrows, hi.p, lo.p, ldt);
-        tmBhi = make_map_f32(hi.p, nrows, K, ldt, npad);
-        tmBlo = make_map_f32(lo.p, nrows, K, ldt, npad);
+        hi.alloc(c, (size_t)N * ldt); lo.alloc(c, (size_t)N * ldt);
+        launch_split_transpose(c, Y, ldy, K, (int)N, (int)N, hi.p, lo.p, ldt);
+        tmBhi = make_map_f32(hi.p, N, K, ldt, npad);
+        tmBlo = make_map_f32(lo.p, N, K, ldt, npad);
     }
     Tf32Params prm;
     prm.M = (int)M; prm.N = (int)N; prm.K = (int)K; prm.npad = npad;

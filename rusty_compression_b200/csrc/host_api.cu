@@ -76,6 +76,26 @@ static void rc_trace(rc_ctx* c, const char* label) {
     c->trace_t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// The generators of the large test matrices leave multi-GB temporaries in the stream-ordered pool (kept there by the
+// release threshold of rc_ctx_create).  Next to a matrix that fills most of the device (config 4 at 2 GPUs: 137 GB of
+// 180) those cached blocks push every later workspace allocation into the allocator's out-of-memory path (trim, retry:
+// hundreds of ms per call, measured 590 ms for one Cholesky-QR2 panel), so a generator hands them back when it is done.
+void rc_cache_release(rc_ctx* c) {
+    for (auto& kv : c->block_cache) {
+        cudaFreeAsync(kv.second.p, kv.second.freed_on);
+        c->event_pool.push_back(kv.second.freed_at);
+    }
+    c->block_cache.clear();
+    c->cached_bytes = 0;
+}
+static void trim_pool(rc_ctx* c) {
+    cudaMemPool_t pool;
+    rc_cache_release(c);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return;
+    for (int i = 0; i < 2; ++i) if (c->aux_stream[i]) cudaStreamSynchronize(c->aux_stream[i]);
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+}
+
 // ============================================================================ GEMM dispatch
 // Replaces ndarray `.dot` (reference N5).  f64/c64 contractions with a plain or (conj-)transposed
 // left operand go to the TMA-fed DMMA kernels; everything else to the generic SIMT tiles.
@@ -190,13 +210,13 @@ bool finish_deferred(rc_ctx* c) {
     RC_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < n; ++i) {
         if (!cholqr2_acceptable(h.data() + 8 * i, c->deferred[i].single)) { ok = false; c->cholqr_fallbacks++; c->cholqr_used--; }
-        cudaFreeAsync(c->deferred[i].status, c->stream);
+        rc_dev_free(c, c->deferred[i].status);
     }
     c->deferred.clear();
     return ok;
 }
 void drop_deferred(rc_ctx* c) {
-    for (auto& d : c->deferred) cudaFreeAsync(d.status, c->stream);
+    for (auto& d : c->deferred) rc_dev_free(c, d.status);
     c->deferred.clear();
 }
 
@@ -234,7 +254,14 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
              DevBuf<T>& q1, DevBuf<T>& rinv2, DevBuf<T>& rfac, int64_t& lds) {
     if (c->qr_mode == 1 || c->force_householder) return false;
     const int64_t m_all = m;    // (local rows; the Gram matrices are summed across shards)
-    if ((!sharded && m_all < 4 * w) || w > chol_max_width(c, dtype) || w < 2) return false;
+    // (one CTA holds Gram matrices up to chol_max_width; twice that with one level of 2 x 2 blocking, chol_inv_blocked: the
+    // 138-column c64 sketch of config 5 is ONE Cholesky-QR2 instead of two panels with block Gram-Schmidt between them.
+    // Double precision only: in single precision the acceptance window is diag(R1) within 2e2, which a wide sketch of
+    // a decaying spectrum does not meet as a whole -- config 4's 266 columns span 4 decades, measured: the rejected
+    // full-width attempt cost 8 ms -- while its 92-column panels do)
+    const bool single_prec = (dtype == RC_F32 || dtype == RC_C32);
+    const int64_t wlim = (single_prec ? 1 : 2) * chol_max_width(c, dtype);
+    if ((!sharded && m_all < 4 * w) || w > wlim || w < 2) return false;
     lds = rc_pad_ld(dtype, w);
     DevBuf<T> g(c, (size_t)w * lds), r1(c, (size_t)w * lds), rinv1(c, (size_t)w * lds), r2(c, (size_t)w * lds);
     DevBuf<double> status(c, 8);
@@ -244,7 +271,7 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
         if (sharded && lds != w) RC_CUDA(cudaMemsetAsync(g.p, 0, sizeof(T) * w * lds, c->stream));   // padding is summed too
         gemm<T>(c, RC_OP_H, RC_OP_N, w, w, m, x, ldx, x, ldx, g.p, lds, rc_one<T>(), rc_zero<T>());
         if (sharded) comm_allreduce_sum(c, g.p, (size_t)w * lds, dtype);      // one all-reduce of the Gram matrix
-        return chol_inv<T>(c, g.p, lds, w, rr, ri, lds, st);
+        return chol_inv_blocked<T>(c, g.p, lds, w, rr, ri, lds, st);
     };
     // Both rounds are enqueued back to back and their status words are read with ONE host synchronisation at
     // the end (a sync after each Cholesky left the GPU idle for a launch round trip twice per panel).  If round 1
@@ -295,6 +322,11 @@ void panel_qr(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, 
     int64_t wpan = std::min(wmax, c->qr_mode == 1 ? wmax : chol_max_width(c, dtype));
     const bool single = (dtype == RC_F32 || dtype == RC_C32);
     (void)single;
+    // f32 on tcgen05: every Gram-type product of a panel is tiled 128 (output rows) x one chunk of <= 96 columns, and each
+    // (tile, chunk) item streams all m rows: a 133-column panel pays 2 x 2 items per product, a panel of <= 96 columns
+    // pays one (config 4, l = 266: three panels of 92 / 92 / 82 instead of two of 133 -- 12 instead of 24 items per
+    // sketch, K = 92 instead of 133 in the small-K products)
+    if (dtype == RC_F32 && c->gemm_impl == 0 && c->qr_mode != 1 && m >= 4096) wpan = std::min<int64_t>(wpan, 96);
     int64_t npan = (w + wpan - 1) / wpan;
     int64_t wp = (w + npan - 1) / npan;
     {   // panel starts on 16-byte boundaries (TMA operand alignment), as long as the panel still fits
@@ -302,6 +334,7 @@ void panel_qr(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, 
         const int64_t up = (wp + e - 1) / e * e;
         if (up <= wpan) wp = up;
     }
+
     ldq = rc_pad_ld(dtype, w);                        // 16-byte row pitch: the tensor-pipe GEMMs can take it
     qfull.alloc(c, (size_t)m * ldq);
     r0.alloc(c, (size_t)w * w);
@@ -316,6 +349,9 @@ void panel_qr(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, 
                 if (sharded && ldt != cw) RC_CUDA(cudaMemsetAsync(t.p, 0, sizeof(T) * c0 * ldt, c->stream));
                 gemm<T>(c, RC_OP_H, RC_OP_N, c0, cw, m, qfull.p, ldq, yp, ldy, t.p, ldt, rc_one<T>(), rc_zero<T>());
                 if (sharded) comm_allreduce_sum(c, t.p, (size_t)c0 * ldt, dtype);
+                // (the subtraction stays a separate bandwidth kernel: folded into the epilogue of the tcgen05 GEMM -- one thread
+                // per output row, so its loads are as uncoalesced as its stores -- the short-K product took 0.9 ms instead of
+                // 0.3 + 0.45 ms at m = 2^20, l = 92)
                 gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, c0, qfull.p, ldq, t.p, ldt, proj.p, ldt, rc_one<T>(), rc_zero<T>());
                 k_sub<T>(c, yp, ldy, yp, ldy, proj.p, ldt, m, cw);                    // Y_p -= Q (Q^H Y_p)
                 k_add<T>(c, r0.p + c0, w, r0.p + c0, w, t.p, ldt, c0, cw);             // R0[0:c0, c0:c0+cw] += t
@@ -349,7 +385,7 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
     DevBuf<T> wc(c, (size_t)w * w), vbuf(c, (size_t)w * w), tau(c, (size_t)w);
     DevBuf<int> dind(c, (size_t)w);
     MatPtr r(mat_new(c, dtype, w, w));
-    MatPtr q(mat_new(c, dtype, m, ncq));
+    MatPtr q;                                   // (allocated where it is formed: m x ncq is GBs for the tall shards)
     DevBuf<T> q1(c, (size_t)w * ncq);
 
     rc_trace(c, nullptr);
@@ -362,11 +398,13 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
         DevBuf<T> tq(c, (size_t)w * rc_pad_ld(dtype, ncq));
         const int64_t ldtq = rc_pad_ld(dtype, ncq);
         gemm<T>(c, RC_OP_N, RC_OP_N, w, ncq, w, crinv2.p, lds, q1.p, ncq, tq.p, ldtq, rc_one<T>(), rc_zero<T>());
+        q.reset(mat_new(c, dtype, m, ncq));
         gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, cq1.p, lds, tq.p, ldtq, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
     } else if (w <= wmax) {
         DistTsqr<T> ts;
         ts.factor(c, y, ldy, m, w, sharded);
         small_pivqr<T>(c, ts.r(), w, w, ncq, r.get(), dind.p, q1.p, ncq, wc, vbuf, tau);
+        q.reset(mat_new(c, dtype, m, ncq));
         ts.apply(q1.p, ncq, ncq, P<T>(q.get()), q->ld);
     } else {
         DevBuf<T> qfull, r0p;
@@ -376,6 +414,7 @@ void pqr_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int64_t ncq, b
         DevBuf<T> q1p(c, (size_t)w * ldq1);
         small_pivqr<T>(c, r0p.p, w, w, ncq, r.get(), dind.p, q1p.p, ldq1, wc, vbuf, tau);
         rc_trace(c, "pqr_tall: pivoted QR of R");
+        q.reset(mat_new(c, dtype, m, ncq));
         gemm<T>(c, RC_OP_N, RC_OP_N, m, ncq, w, qfull.p, ldq, q1p.p, ldq1, P<T>(q.get()), q->ld, rc_one<T>(), rc_zero<T>());
         rc_trace(c, "pqr_tall: form Q1, Q = Qfull Q1");
     }
@@ -1048,6 +1087,10 @@ rc_status rc_ctx_destroy(rc_ctx* c) {
     {
         DeviceGuard dg(c->device);
         cudaStreamSynchronize(c->stream);
+        rc_cache_release(c);
+        cudaStreamSynchronize(c->stream);
+        for (cudaEvent_t ev : c->event_pool) cudaEventDestroy(ev);
+        c->event_pool.clear();
         try { comm_destroy(c); } catch (...) {}
         if (c->tile_counter) cudaFree(c->tile_counter);
         for (int i = 0; i < 2; ++i) {
@@ -1064,6 +1107,7 @@ rc_status rc_ctx_destroy(rc_ctx* c) {
 rc_status rc_ctx_set_stream(rc_ctx* c, void* s) {
     if (!c) return RC_INVALID_ARGUMENT;
     return guard(c, [&] {
+        rc_cache_release(c);                         // cached workspaces are tied to the stream they were freed on
         RC_CUDA(cudaStreamSynchronize(c->stream));
         if (c->own_stream) RC_CUDA(cudaStreamDestroy(c->stream));
         c->stream = (cudaStream_t)s;
@@ -1088,6 +1132,9 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
         else if (!strcmp(key, "pivot_precision")) c->pivot_f64 = (v != 0);
         else if (!strcmp(key, "speculate")) c->speculate = (int)v;
         else if (!strcmp(key, "fused_small_qr")) c->fused_small_qr = (int)v;
+        else if (!strcmp(key, "cluster_qr")) c->cluster_qr = (int)v;
+        else if (!strcmp(key, "workspace_cache")) { c->block_cache_on = (int)v; if (!v) rc_cache_release(c); }
+        else if (!strcmp(key, "release_workspaces")) { trim_pool(c); }
         else if (!strcmp(key, "overlap")) c->overlap = (int)v;
         else if (!strcmp(key, "reuse_range_b")) c->reuse_range_b = (int)v;
         else if (!strcmp(key, "trace")) c->trace = (int)v;
@@ -1104,6 +1151,9 @@ rc_status rc_ctx_get_counter(rc_ctx* c, const char* key, int64_t* out) {
         else if (!strcmp(key, "cholqr_used")) *out = c->cholqr_used;
         else if (!strcmp(key, "cholqr_fallbacks")) *out = c->cholqr_fallbacks;
         else if (!strcmp(key, "range_b_reused")) *out = c->range_b_reused;
+        else if (!strcmp(key, "workspace_cache_hits")) *out = c->cache_hits;
+        else if (!strcmp(key, "workspace_cache_misses")) *out = c->cache_misses;
+        else if (!strcmp(key, "workspace_cached_bytes")) *out = (int64_t)c->cached_bytes;
         else RC_THROW(RC_INVALID_ARGUMENT, "unknown counter '%s'", key);
     });
 }
@@ -1297,6 +1347,7 @@ rc_status rc_decaying_spectrum_matrix(rc_ctx* c, rc_dtype dt, int64_t rows, int6
             MatPtr vt(mat_conj_transpose<T>(c, v.get()));
             *out = low_rank_from_factors<T>(c, u.get(), sig, vt.get());
         });
+        trim_pool(c);
     });
 }
 
@@ -1320,6 +1371,7 @@ rc_status rc_tall_shard_matrix(rc_ctx* c, rc_dtype dt, int64_t rows, int64_t col
             MatPtr vt(mat_conj_transpose<T>(c, qr.q.get()));
             *out = low_rank_from_factors<T>(c, g.get(), sig, vt.get());
         });
+        trim_pool(c);
     });
 }
 

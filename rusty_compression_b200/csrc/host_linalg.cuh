@@ -26,14 +26,14 @@ inline rc_matrix* mat_new(rc_ctx* c, int dtype, int64_t rows, int64_t cols) {
     m->owns = true;
     m->id = rc_next_matrix_id();
     size_t bytes = (size_t)std::max<int64_t>(rows, 1) * m->ld * rc_dtype_size(dtype);
-    RC_CUDA(cudaMallocAsync(&m->data, bytes, c->stream));
+    m->data = rc_dev_alloc(c, bytes);
     return m.release();
 }
 inline void mat_free(rc_matrix* m) {
     if (!m) return;
     if (m->owns && m->data) {
         DeviceGuard dg(m->ctx->device);      // the *_free entry points are not routed through guard()
-        cudaFreeAsync(m->data, m->ctx->stream);
+        rc_dev_free(m->ctx, m->data);
     }
     if (m->companion) mat_free(m->companion);
     delete m;

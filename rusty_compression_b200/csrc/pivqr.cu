@@ -357,6 +357,167 @@ pivqr_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int cap, int 
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------
+// Medium factors (the w x w triangle of a wide sketch: 138 x 138 c64 at config 5, 266 x 266 in double at config 4) do
+// not fit one CTA's shared memory but fit a CLUSTER's: up to 8 CTAs, every column resident in the shared memory of its
+// owner, candidates exchanged through distributed shared memory (st.shared::cluster into every peer's slot table) and
+// ONE hardware cluster barrier per step instead of a grid-wide sync through L2; the winning column is read straight out
+// of its owner's shared memory.  Same pivot rule, same arithmetic as pivqr_kernel (the cooperative kernel spent ~18 000
+// cycles per step on these shapes, 14 000 of them in L2 round trips: publish, grid sync, slot reads, staged column).
+template <class T, int NT, int LPC>
+__global__ void __launch_bounds__(NT)
+pivqr_cluster_kernel(T* __restrict__ W, int64_t ldw, int p, int n, int kk, int nlmax,
+                     int* __restrict__ ind, T* __restrict__ vbuf, T* __restrict__ tau_out, T* __restrict__ diag) {
+    constexpr int NW = NT / 32;
+    constexpr int MAXG = 8;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xs = reinterpret_cast<T*>(smem_raw);                  // pivot column / reflector, p entries
+    T* scol = xs + p;                                        // nlmax resident columns, p entries each
+    double* vn = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(scol + (size_t)nlmax * p) + 7) & ~(uintptr_t)7);
+    int* lpos = reinterpret_cast<int*>(vn + nlmax);
+    __shared__ Cand c_slots[2][MAXG];                        // written by every CTA of the cluster (DSMEM)
+    __shared__ int c_disp[2][MAXG];
+    __shared__ Cand s_cand[NW];
+    __shared__ int s_disp[NW];
+    __shared__ double s_red[NW];
+    __shared__ T s_hs[3];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = (int)cluster.num_blocks(), b = (int)cluster.block_rank();
+    const int nl = (b < n) ? (n - b + G - 1) / G : 0;        // columns owned by this CTA: c = li * G + b
+
+    for (int li = warp; li < nl; li += NW) {
+        const T* src = W + (int64_t)(li * G + b) * ldw;
+        T* dst = scol + (size_t)li * p;
+        double a = 0.0;
+        for (int r = lane; r < p; r += 32) { T v = src[r]; dst[r] = v; a += rc_abs2(v); }
+        a = rc_warp_sum(a);
+        if (lane == 0) { vn[li] = sqrt(a); lpos[li] = li * G + b; }
+    }
+    __syncthreads();
+
+    for (int i = 0; i < kk; ++i) {
+        // (a) local candidates over owned, not yet pivoted columns
+        Cand best; best.val = -1.0; best.lpos = 0x7fffffff; best.phys = -1;
+        int disp = -1;
+        for (int li = tid; li < nl; li += NT) {
+            int lp = lpos[li];
+            if (lp >= i) {
+                Cand cnd; cnd.val = vn[li]; cnd.lpos = lp; cnd.phys = li * G + b;
+                if (better(cnd, best)) best = cnd;
+                if (lp == i) disp = li * G + b;
+            }
+        }
+        best = warp_best(best);
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) disp = max(disp, __shfl_xor_sync(0xffffffffu, disp, m));
+        if (lane == 0) { s_cand[warp] = best; s_disp[warp] = disp; }
+        __syncthreads();
+        if (warp == 0) {
+            Cand bb; bb.val = -1.0; bb.lpos = 0x7fffffff; bb.phys = -1;
+            int d = -1;
+            if (lane < NW) { bb = s_cand[lane]; d = s_disp[lane]; }
+            bb = warp_best(bb);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, m));
+            // lane g publishes this CTA's candidate into CTA g's slot table
+            if (lane < G) {
+                Cand* rs = cluster.map_shared_rank(&c_slots[i & 1][b], lane);
+                int* rd = cluster.map_shared_rank(&c_disp[i & 1][b], lane);
+                *rs = bb;
+                *rd = d;
+            }
+        }
+        // (b) one cluster barrier per step (release / acquire: the slot writes above are visible behind it)
+        cluster.sync();
+        // (c) winner: every thread reduces the G slots of its own table
+        Cand win; win.val = -1.0; win.lpos = 0x7fffffff; win.phys = -1;
+        int dc = -1;
+        for (int g = 0; g < G; ++g) {
+            const Cand cg_ = c_slots[i & 1][g];
+            if (better(cg_, win)) win = cg_;
+            dc = max(dc, c_disp[i & 1][g]);
+        }
+        const int pv = win.phys >= 0 ? win.phys : dc;          // (no winner: every norm is NaN, speculative run on garbage)
+        const int pv_lpos = win.phys >= 0 ? win.lpos : i;
+        if (tid == 0) {
+            if (dc >= 0 && dc != pv && (dc % G) == b) lpos[dc / G] = pv_lpos;
+            if ((pv % G) == b) lpos[pv / G] = i;
+        }
+        if (b == 0 && tid == 0) ind[i] = pv;
+        // (d) reflector from the pivot column, read out of its owner's shared memory (it is never written again)
+        const T* pcol = cluster.map_shared_rank(scol + (size_t)(pv / G) * p, pv % G);
+        double a = 0.0;
+        for (int r = i + tid; r < p; r += NT) {
+            T v = pcol[r];
+            xs[r] = v;
+            if (r > i) a += rc_abs2(v);
+        }
+        a = rc_warp_sum(a);
+        if (lane == 0) s_red[warp] = a;
+        __syncthreads();
+        if (warp == 0) {
+            double xnorm2 = (lane < NW) ? s_red[lane] : 0.0;
+            xnorm2 = rc_warp_sum(xnorm2);
+            T t0, t1, t2;
+            larfg_dev<T>(xs[i], xnorm2, t0, t1, t2);
+            if (lane == 0) { s_hs[0] = t0; s_hs[1] = t1; s_hs[2] = t2; }
+        }
+        __syncthreads();
+        const T tau = s_hs[0], scale = s_hs[1], beta = s_hs[2];
+        for (int r = i + 1 + tid; r < p; r += NT) xs[r] = xs[r] * scale;
+        __syncthreads();
+        if (b == 0) {
+            T* vcol = vbuf + (int64_t)i * p;
+            for (int r = tid; r < p; r += NT) vcol[r] = (r < i) ? rc_zero<T>() : (r == i ? rc_one<T>() : xs[r]);
+            if (tid == 0) { tau_out[i] = tau; diag[i] = beta; }
+        }
+        // (e) trailing update of the owned columns + exact partial norms: LPC lanes per column
+        const T ctau = rc_conj(tau);
+        {
+            constexpr int CPW = 32 / LPC;
+            const int sl = lane % LPC, sc = lane / LPC;
+            using R = RealOf<T>;
+            for (int q0 = 0; warp + q0 * NW < nl; q0 += CPW) {
+                const int li = warp + (q0 + sc) * NW;
+                const bool act = (li < nl) && (lpos[min(li, nl - 1)] > i);
+                T* col = scol + (size_t)min(li, nl - 1) * p;
+                T part = rc_zero<T>();
+                if (act)
+                    for (int r = i + 1 + sl; r < p; r += LPC) part = rc_cfma(xs[r], col[r], part);
+#pragma unroll
+                for (int m = LPC / 2; m > 0; m >>= 1) part = part + rc_shfl_xor(part, m);
+                T ci = rc_zero<T>(), f = rc_zero<T>();
+                R nrm = R(0);
+                if (act) {
+                    ci = col[i];
+                    f = ctau * (ci + part);
+                    for (int r = i + 1 + sl; r < p; r += LPC) {
+                        T v = col[r] - f * xs[r];
+                        col[r] = v;
+                        nrm += rc_real(v) * rc_real(v) + rc_imag(v) * rc_imag(v);
+                    }
+                }
+#pragma unroll
+                for (int m = LPC / 2; m > 0; m >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, m);
+                if (act && sl == 0) { col[i] = ci - f; vn[li] = sqrt((double)nrm); }
+            }
+        }
+        __syncthreads();   // xs is rewritten next step; lpos / vn written by single lanes are read by the block
+    }
+    for (int li = tid; li < nl; li += NT) {
+        int lp = lpos[li];
+        if (lp >= kk) ind[lp] = li * G + b;
+    }
+    for (int li = warp; li < nl; li += NW) {
+        T* dst = W + (int64_t)(li * G + b) * ldw;
+        const T* src = scol + (size_t)li * p;
+        for (int r = lane; r < p; r += 32) dst[r] = src[r];
+    }
+    cluster.sync();        // no CTA may exit while a peer can still read its shared memory
+}
+
 // Small factors (the l x l R of a sketch): one CTA, everything in shared memory, and the serial part
 // of a step (argmax -> pivot column -> ?larfg scalars) done by ONE warp, so a step costs two block
 // barriers instead of seven.  Same pivot rule and numerics as pivqr_kernel.
@@ -727,6 +888,32 @@ __global__ void form_q_kernel(const T* __restrict__ vbuf, const T* __restrict__ 
 
 }  // namespace
 
+// Cluster route (pivqr_cluster_kernel): false when the factor does not fit 8 CTAs' shared memory or the launch is refused.
+template <class T>
+static bool pivqr_cluster_launch(rc_ctx* c, T* wc, int64_t ldw, int p, int n, int kk, int* ind, T* vbuf, T* tau, T* diag, size_t lim) {
+    if (c->cluster_qr == 0) return false;
+    constexpr int NT = 1024;
+    int G = 8;
+    while (G > 2 && n < 32 * (G / 2)) G /= 2;                 // at least ~32 columns per CTA
+    const int nlmax = (n + G - 1) / G;
+    const size_t smem = ((size_t)p + (size_t)nlmax * p) * sizeof(T) + (size_t)nlmax * (sizeof(double) + sizeof(int)) + 64;
+    if (smem + 8192 > lim) return false;
+    void (*kern)(T*, int64_t, int, int, int, int, int*, T*, T*, T*) =
+        p <= 160 ? pivqr_cluster_kernel<T, NT, 8> : (p <= 320 ? pivqr_cluster_kernel<T, NT, 16> : pivqr_cluster_kernel<T, NT, 32>);
+    RC_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, (const void*)kern, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return false; }
+    RC_CUDA(cudaLaunchKernelEx(&cfg, kern, wc, ldw, p, n, kk, nlmax, ind, vbuf, tau, diag));
+    RC_COUNT_LAUNCH(c);
+    return true;
+}
+
 template <class T>
 static void pivqr_factor_native(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_t n, T* r, int64_t ldr, int* ind,
                                 T* vbuf, T* tau) {
@@ -747,6 +934,8 @@ static void pivqr_factor_native(rc_ctx* c, T* wc, int64_t ldw, int64_t p, int64_
             pivqr_small_kernel<T, NTS, 32><<<1, NTS, smem_all, c->stream>>>(wc, ldw, pi, ni, kk, ind, vbuf, tau, diag.p);
         }
         RC_CHECK_LAUNCH(c);
+    } else if (pivqr_cluster_launch<T>(c, wc, ldw, pi, ni, kk, ind, vbuf, tau, diag.p, lim)) {
+        // medium factor: a cluster of CTAs holds every column in (distributed) shared memory
     } else {
         constexpr int NT = 1024;
         constexpr int NW = NT / 32;

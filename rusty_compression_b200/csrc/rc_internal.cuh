@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <map>
+#include <unordered_map>
 
 #include "../../include/rc_api.h"
 #include "rc_scalar.cuh"
@@ -59,6 +61,7 @@ struct rc_ctx {
     // Speculative execution (host_api.cu, DeferScope): inside a deferred region the Cholesky-QR2 panels do not read
     // their status words back (no host synchronisation in the middle of a pipeline); the words are collected here and
     // checked once at the end, and a failed check re-runs the region with the Householder TSQR forced.
+    int cluster_qr = 1;           // option "cluster_qr": medium pivoted QRs in the thread-block-cluster kernel (pivqr.cu)
     int fused_small_qr = 1;       // option "fused_small_qr": small pivoted QRs in the fused one-CTA kernel (pivqr.cu)
     int speculate = 1;            // option "speculate"
     int overlap = 1;              // option "overlap": independent stages on auxiliary streams
@@ -77,6 +80,14 @@ struct rc_ctx {
     // communicator (row-sharded multi-GPU)
     void* comm = nullptr;
     int rank = 0, nranks = 1;
+    // workspace cache (rc_dev_alloc / rc_dev_free below): freed device blocks of >= 1 MiB, per stream, by size
+    struct CachedBlock { void* p; cudaStream_t freed_on; cudaEvent_t freed_at; };
+    std::unordered_map<void*, size_t> live_blocks;                                   // cacheable blocks handed out
+    std::multimap<size_t, CachedBlock> block_cache;                                  // size -> free blocks
+    std::vector<cudaEvent_t> event_pool;
+    size_t cached_bytes = 0;
+    int64_t cache_hits = 0, cache_misses = 0;
+    int block_cache_on = 1;       // option "workspace_cache"
 };
 
 struct rc_matrix {
@@ -120,6 +131,76 @@ inline size_t rc_dtype_size(int dt) {
 }
 inline int rc_real_dtype(int dt) { return dt & 1; }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Device workspaces.  Every pipeline allocates and frees dozens of buffers per call, many of them GBs (the tall shards
+// of config 4: Y, Q, projections, split operand copies).  Straight cudaMallocAsync / cudaFreeAsync left that to the
+// driver's stream-ordered pool, whose reuse of large, differently sized, short-lived blocks only settled after five or
+// six identical passes (measured at 2^22 x 8192 f32, 137 GB resident: 6.5 s, 1.7 s, 2.1 s, 0.49 s, 0.65 s, 0.25 s per
+// pass; 40-400 ms at 2^20 rows) -- the kernels themselves took 0.20 s.  So blocks of 1 MiB ... 8 GiB are cached here: a
+// freed block keeps an event recorded on the stream it was freed on and is handed out again to the next request it fits
+// without wasting more than a quarter of it; a request from ANOTHER stream first waits for that event.  That is CUDA's
+// own rule (memory freed on a stream may be reused by work ordered after the free) and makes every pass after the first
+// allocation-free.  Small blocks and cache misses go to cudaMallocAsync; when that runs out of memory the cache is
+// released and the request retried.
+void rc_cache_release(rc_ctx* c);        // hand every cached block back to the driver (host_api.cu)
+inline void* rc_dev_alloc(rc_ctx* c, size_t bytes) {
+    if (bytes == 0) return nullptr;
+    constexpr size_t kMin = (size_t)1 << 20, kMax = (size_t)8 << 30;     // (operators of tens of GB are not worth caching)
+    void* p = nullptr;
+    const bool cacheable = c->block_cache_on && bytes >= kMin && bytes <= kMax;
+    if (cacheable) {
+        // best fit, preferring a block freed on this stream (no cross-stream dependence: the two power-iteration trips
+        // run on two streams and should not wait for each other's frees)
+        auto it = c->block_cache.end();
+        {
+            int looked = 0;
+            for (auto j = c->block_cache.lower_bound(bytes); j != c->block_cache.end() && j->first <= bytes + bytes / 4 && looked < 16; ++j, ++looked) {
+                if (j->second.freed_on == c->stream) { it = j; break; }
+                if (it == c->block_cache.end()) it = j;
+            }
+        }
+        if (it != c->block_cache.end()) {
+            const rc_ctx::CachedBlock blk = it->second;
+            if (blk.freed_on != c->stream) cudaStreamWaitEvent(c->stream, blk.freed_at, 0);
+            c->event_pool.push_back(blk.freed_at);
+            c->live_blocks[blk.p] = it->first;
+            c->cached_bytes -= it->first;
+            c->block_cache.erase(it);
+            c->cache_hits++;
+            return blk.p;
+        }
+        c->cache_misses++;
+    }
+    cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
+    if (e == cudaErrorMemoryAllocation && c->cached_bytes > 0) {
+        cudaGetLastError();
+        rc_cache_release(c);
+        cudaStreamSynchronize(c->stream);           // (frees on the auxiliary streams become visible to this one)
+        for (int i = 0; i < 2; ++i) if (c->aux_stream[i]) cudaStreamSynchronize(c->aux_stream[i]);
+        e = cudaMallocAsync(&p, bytes, c->stream);
+    }
+    if (e != cudaSuccess) {
+        rc_status st = (e == cudaErrorMemoryAllocation) ? RC_OUT_OF_MEMORY : RC_CUDA_ERROR;
+        RC_THROW(st, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    if (cacheable) c->live_blocks[p] = bytes;
+    return p;
+}
+inline void rc_dev_free(rc_ctx* c, void* p) {
+    if (!p) return;
+    auto it = c->live_blocks.find(p);
+    if (it == c->live_blocks.end()) { cudaFreeAsync(p, c->stream); return; }
+    const size_t bytes = it->second;
+    c->live_blocks.erase(it);
+    if (!c->block_cache_on) { cudaFreeAsync(p, c->stream); return; }
+    cudaEvent_t ev = nullptr;
+    if (!c->event_pool.empty()) { ev = c->event_pool.back(); c->event_pool.pop_back(); }
+    else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); cudaFreeAsync(p, c->stream); return; }
+    cudaEventRecord(ev, c->stream);
+    c->block_cache.emplace(bytes, rc_ctx::CachedBlock{p, c->stream, ev});
+    c->cached_bytes += bytes;
+}
+
 // Stream-ordered device buffer.
 template <class T>
 struct DevBuf {
@@ -132,10 +213,10 @@ struct DevBuf {
         release();
         c = ctx;
         n = count;
-        if (count) RC_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), ctx->stream));
+        if (count) p = static_cast<T*>(rc_dev_alloc(ctx, count * sizeof(T)));
     }
     void release() {
-        if (p) cudaFreeAsync(p, c->stream);
+        if (p) rc_dev_free(c, p);
         p = nullptr;
     }
     ~DevBuf() { release(); }
@@ -274,6 +355,10 @@ void trsm_upper(rc_ctx*, const T* u, int64_t ldu, bool u_transposed, int64_t k, 
 template <class T>
 bool chol_inv(rc_ctx*, const T* g, int64_t ldg, int64_t w, T* r, T* rinv, int64_t ldo, double* status_dev);
 int64_t chol_max_width(rc_ctx*, int dtype);
+// Same contract for w <= 2 * chol_max_width: one level of 2 x 2 blocking around the one-CTA kernel (small GEMMs for the
+// off-diagonal blocks).
+template <class T>
+bool chol_inv_blocked(rc_ctx*, const T* g, int64_t ldg, int64_t w, T* r, T* rinv, int64_t ldo, double* status_dev);
 
 // ------------------------------------------------------------------ comm.cu
 void comm_get_unique_id(void* out128);

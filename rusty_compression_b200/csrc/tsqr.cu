@@ -495,11 +495,11 @@ int64_t tsqr_max_width(rc_ctx* c, int dtype) {
 template <class T>
 TsqrFactor<T>::~TsqrFactor() {
     for (auto& L : levels) {
-        if (L.owns_v && L.v) cudaFreeAsync(L.v, ctx->stream);
-        if (L.tau) cudaFreeAsync(L.tau, ctx->stream);
-        if (L.tpan) cudaFreeAsync(L.tpan, ctx->stream);
+        if (L.owns_v && L.v) rc_dev_free(ctx, L.v);
+        if (L.tau) rc_dev_free(ctx, L.tau);
+        if (L.tpan) rc_dev_free(ctx, L.tpan);
     }
-    if (r) cudaFreeAsync(r, ctx->stream);
+    if (r) rc_dev_free(ctx, r);
 }
 
 template <class T>
@@ -518,10 +518,10 @@ void tsqr_factor(rc_ctx* c, T* y, int64_t ld, int64_t m, int64_t w, TsqrFactor<T
         int64_t nblocks = (cur_rows + block - 1) / block;
         typename TsqrFactor<T>::Level L;
         L.v = cur; L.ldv = cur_ld; L.rows = cur_rows; L.block = block; L.nblocks = nblocks; L.owns_v = owns; L.tri = tri;
-        RC_CUDA(cudaMallocAsync((void**)&L.tau, sizeof(T) * nblocks * w, c->stream));
-        RC_CUDA(cudaMallocAsync((void**)&L.tpan, sizeof(T) * nblocks * npan * NB * NB, c->stream));
+        L.tau = static_cast<T*>(rc_dev_alloc(c, sizeof(T) * nblocks * w));
+        L.tpan = static_cast<T*>(rc_dev_alloc(c, sizeof(T) * nblocks * npan * NB * NB));
         T* rstack = nullptr;
-        RC_CUDA(cudaMallocAsync((void**)&rstack, sizeof(T) * nblocks * w * w, c->stream));
+        rstack = static_cast<T*>(rc_dev_alloc(c, sizeof(T) * nblocks * w * w));
         size_t smem = factor_smem<T>(w, sp, block);
         if (tri) {
             RC_CUDA(cudaFuncSetAttribute(house_block_qr_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

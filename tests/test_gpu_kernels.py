@@ -200,7 +200,7 @@ def test_norms_and_rel_diff(api, dtype):
 
 @pytest.mark.parametrize("qr_mode", [0, 1], ids=["cholqr2-auto", "householder-tsqr"])
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2000, 40), (300, 74), (5000, 7), (64, 64), (150, 100)])
+@pytest.mark.parametrize("shape", [(2000, 40), (300, 74), (5000, 7), (64, 64), (150, 100), (8192, 200)])
 def test_tall_pivoted_qr_matches_lapack(api, dtype, shape, qr_mode):
     """Tall route (Cholesky-QR2 fast path with fallback / Householder TSQR) + pivot-on-R against
     ?geqp3/?orgqr: same pivots, |R| equal, Q orthonormal, Q R = A P."""
@@ -221,6 +221,33 @@ def test_tall_pivoted_qr_matches_lapack(api, dtype, shape, qr_mode):
     if order is not None:
         q0, r0, ind0 = ref.pivoted_qr_with_order(a, order)
     assert np.max(np.abs(np.abs(np.diagonal(r)) - np.abs(np.diagonal(r0))) / np.abs(r0[0, 0])) < tol
+
+
+@pytest.mark.parametrize("cluster", [1, 0], ids=["cluster", "cooperative"])
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (3000, 200)), (np.complex128, (2000, 138)), (np.float32, (4000, 266)),
+                                         (np.float64, (260, 300)), (np.complex64, (1500, 150))],
+                         ids=["f64-200", "c64-138", "f32-266", "f64-260x300", "c32-150"])
+def test_medium_pivoted_qr_cluster_route(api, dtype, shape, cluster):
+    """The w x w triangle of a wide sketch (config 5: 138 x 138 c64, config 4: 266 x 266 in double) does not fit one CTA:
+    thread-block-cluster kernel (columns in distributed shared memory, one cluster barrier per step) against the
+    cooperative grid kernel and against ?geqp3."""
+    a = ref.random_approximate_low_rank_matrix(shape, 1.0, 1e-3, dtype, seed=15)
+    ctx = api.default_context()
+    ctx.set_option("cluster_qr", cluster)
+    try:
+        q, r, ind = api.pivoted_qr(a)
+    finally:
+        ctx.set_option("cluster_qr", 1)
+    single = dtype in (np.float32, np.complex64)
+    k = min(shape)
+    assert sorted(ind.tolist()) == list(range(shape[1]))
+    assert np.max(np.abs(np.conj(q.T).dot(q) - np.eye(k))) < (2e-5 if single else 1e-12)
+    assert relerr(q.dot(r), a[:, ind]) < (1e-5 if single else 1e-13)
+    q0, r0, ind0 = ref.pivoted_qr(a)
+    order = adjudicate(a, ind, ind0, label=f"medium {shape} {np.dtype(dtype).name} cluster={cluster}")
+    if order is not None:
+        q0, r0, ind0 = ref.pivoted_qr_with_order(a, order)
+    assert np.max(np.abs(np.abs(np.diagonal(r)) - np.abs(np.diagonal(r0))) / np.abs(r0[0, 0])) < (2e-4 if single else 1e-9)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
