@@ -89,10 +89,20 @@ const char* rc_last_error_string(rc_ctx* ctx);
  * "reuse_range_b" (1 = compute_from_range_estimate reuses the B = Q^H A the adaptive sampler built),
  * "dmma_tail" (1 = a ragged last 8-column group of the FP64 tensor-pipe GEMM is formed with DFMAs,
  * 0 = padded DMMA; same results up to summation order in those columns), "trace" (1 = stage timer
- * on stderr; synchronises at every mark). */
+ * on stderr; synchronises at every mark),
+ * "speculate" (1 = no host synchronisation inside the power-iteration sampler: the Cholesky-QR2 status words are checked
+ * once at the end and a rejected panel re-runs the sampler on Householder TSQR), "overlap" (1 = independent stages on
+ * auxiliary streams), "fused_small_qr" (1 = small pivoted QRs in the fused one-CTA kernel), "cluster_qr" (1 = medium
+ * pivoted QRs -- the factor fits 8 CTAs' shared memory -- in the thread-block-cluster kernel, 0 = cooperative grid
+ * kernel), "tf32_ring" (A/B variants of the tcgen05 TF32 kernel: 0 default, 1 = six TMEM split stages, 2 = high part
+ * from shared memory), "workspace_cache" (1 = device blocks of 1 MiB .. 8 GiB are cached per context and reused in
+ * stream order; 0 = every allocation goes to cudaMallocAsync), "release_workspaces" (any value: empty the cache and trim
+ * the device memory pool now).
+ * A handle created through a context must be freed before rc_ctx_destroy: the free routines reach into the context. */
 rc_status rc_ctx_set_option(rc_ctx* ctx, const char* key, int64_t value);
 /* Counters: "kernel_launches" (own kernels launched so far), "gemm_flops", "h2d_bytes",
- * "d2h_bytes", "cholqr_used", "cholqr_fallbacks".  rc_ctx_reset_counters zeroes them. */
+ * "d2h_bytes", "cholqr_used", "cholqr_fallbacks", "range_b_reused", "workspace_cache_hits", "workspace_cache_misses",
+ * "workspace_cached_bytes".  rc_ctx_reset_counters zeroes them. */
 rc_status rc_ctx_get_counter(rc_ctx* ctx, const char* key, int64_t* out);
 rc_status rc_ctx_reset_counters(rc_ctx* ctx);
 
