@@ -249,9 +249,15 @@ cudaEvent_t aux_event(rc_ctx* c, int i) {
 // Cholesky breaks down -- the caller falls back to the unconditionally stable Householder TSQR
 // with Y untouched.  Backward error and orthogonality are O(eps) in the accepted regime
 // (Yamamoto et al. 2015), the same class as Householder, which is what pivot parity needs.
+// panel_scale (optional, host, in/out): the largest diagonal entry of R over the panels of a wider factorisation so far.
+// With it the status words are read back at once (no speculation) and a panel whose smallest diagonal entry is at most
+// 1e2 eps sqrt(m) times that scale is REJECTED however well conditioned it is relative to itself: a panel that has no
+// direction of its own left after the projection is rounding noise, and a Cholesky-QR2 of noise is orthogonal to the
+// previous panels only to eps x (norm before the projection / norm of the noise) -- the loss compounds from panel to
+// panel (measured on an exact rank-50 1500 x 900 matrix: 3e-15, 2e-14, 9e-12, 1e-6, 0.6).
 template <class T>
 bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, int dtype,
-             DevBuf<T>& q1, DevBuf<T>& rinv2, DevBuf<T>& rfac, int64_t& lds) {
+             DevBuf<T>& q1, DevBuf<T>& rinv2, DevBuf<T>& rfac, int64_t& lds, double* panel_scale = nullptr) {
     if (c->qr_mode == 1 || c->force_householder) return false;
     const int64_t m_all = m;    // (local rows; the Gram matrices are summed across shards)
     // (one CTA holds Gram matrices up to chol_max_width; twice that with one level of 2 x 2 blocking, chol_inv_blocked: the
@@ -284,7 +290,7 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
     if (!gram_chol(q1.p, lds, r2.p, rinv2.p, status.p + 4)) return false;
     rfac.alloc(c, (size_t)w * lds);
     gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, r2.p, lds, r1.p, lds, rfac.p, lds, rc_one<T>(), rc_zero<T>());
-    if (c->defer_depth > 0) {
+    if (c->defer_depth > 0 && !panel_scale) {
         // speculative: carry on as if both rounds were accepted; the status words are checked at the end of the
         // deferred region (finish_deferred), which re-runs it on the Householder path when a panel was not acceptable
         c->deferred.push_back({status.take(), single});
@@ -294,6 +300,12 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
     RC_CUDA(cudaMemcpyAsync(h, status.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     RC_CUDA(cudaStreamSynchronize(c->stream));
     if (!cholqr2_acceptable(h, single)) { c->cholqr_fallbacks++; return false; }
+    if (panel_scale) {
+        const double eps = single ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
+        const double m_glob = (double)(sharded ? (int64_t)c->nranks * m : m);
+        if (!(h[1] > 1.0e2 * eps * std::sqrt(m_glob) * std::max(*panel_scale, h[2]))) { c->cholqr_fallbacks++; return false; }
+        *panel_scale = std::max(*panel_scale, h[2]);
+    }
     rc_trace(c, "  cholqr2: 2 x (gram + chol), q1 = Y rinv1");
     c->cholqr_used++;
     return true;
@@ -339,6 +351,7 @@ void panel_qr(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, 
     qfull.alloc(c, (size_t)m * ldq);
     r0.alloc(c, (size_t)w * w);
     k_fill<T>(c, r0.p, w, w, w, rc_zero<T>());
+    double scale = 0.0;                               // largest |r_jj| over the panels so far (null-direction threshold)
     for (int64_t c0 = 0; c0 < w; c0 += wp) {
         int64_t cw = std::min(wp, w - c0);
         T* yp = y + c0;
@@ -360,18 +373,79 @@ void panel_qr(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, 
         }
         DevBuf<T> pq1, prinv2, prfac;
         int64_t lds = 0;
-        if (cholqr2<T>(c, yp, ldy, m, cw, sharded, dtype, pq1, prinv2, prfac, lds)) {
+        if (cholqr2<T>(c, yp, ldy, m, cw, sharded, dtype, pq1, prinv2, prfac, lds, &scale)) {
             rc_trace(c, "pqr_tall: panel cholqr2");
             gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, cw, pq1.p, lds, prinv2.p, lds, qfull.p + c0, ldq, rc_one<T>(), rc_zero<T>());
             k_copy<T>(c, r0.p + c0 * w + c0, w, prfac.p, lds, cw, cw);
             rc_trace(c, "pqr_tall: panel Q = q1 rinv2");
         } else {
+            // Householder fallback: the projected panel is ill-conditioned or rank-deficient (a low-rank operator sampled
+            // with more columns than its rank, an exactly rank-deficient dense matrix, the zero matrix).  Its TSQR is
+            // Y_p = Q_p R_pp with Q_p orthonormal, but the directions that belong to (numerically) zero rows of R_pp are
+            // whatever the reflectors leave -- unit vectors for a zero panel -- and Q_p is orthogonal to the previous
+            // panels only to eps * cond(Y_p).  ?geqp3 returns an orthonormal Q whatever the rank, so:
+            //   1. null directions (|r_jj| <= 8 eps sqrt(m) x the largest diagonal entry so far) are replaced by
+            //      Gaussian vectors (they multiply rows of R_pp that are zero to that level),
+            //   2. Q_p is orthogonalised against the previous panels (twice) and factored again, Q_p = Q_prev T + Q_p' R',
+            //   3. R0 takes the correction: R0[0:c0, panel] += T R_pp, R0[panel, panel] = R' R_pp.
             DistTsqr<T> ts;
             ts.factor(c, yp, ldy, m, cw, sharded);
-            k_copy<T>(c, r0.p + c0 * w + c0, w, ts.r(), cw, cw, cw);
-            DevBuf<T> eye(c, (size_t)cw * cw);
+            DevBuf<T> eye(c, (size_t)cw * cw), rpp(c, (size_t)cw * cw);
+            k_copy<T>(c, rpp.p, cw, ts.r(), cw, cw, cw);
             k_eye<T>(c, eye.p, cw, cw, cw);
-            ts.apply(eye.p, cw, cw, qfull.p + c0, ldq);
+            const int64_t ldz = rc_pad_ld(dtype, cw);
+            DevBuf<T> z(c, (size_t)m * ldz);
+            ts.apply(eye.p, cw, cw, z.p, ldz);
+            {
+                const double eps = single ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
+                const int64_t m_glob = sharded ? (int64_t)c->nranks * m : m;
+                std::vector<T> hr((size_t)cw * cw);
+                RC_CUDA(cudaMemcpyAsync(hr.data(), rpp.p, sizeof(T) * cw * cw, cudaMemcpyDeviceToHost, c->stream));
+                RC_CUDA(cudaStreamSynchronize(c->stream));
+                for (int64_t j = 0; j < cw; ++j) { const double d = rc_abs(hr[(size_t)j * cw + j]); if (d == d) scale = std::max(scale, d); }
+                std::vector<int> hflags((size_t)cw);
+                int64_t nnull = 0;
+                // (8 eps sqrt(m): the level of the rounding noise in R_pp itself -- the replaced directions cost
+                // |r_jj| in the reconstruction, so a larger window would show: 1e3 gave 1e-3 relative in f32)
+                const double thr = 8.0 * eps * std::sqrt((double)m_glob) * scale;
+                for (int64_t j = 0; j < cw; ++j) { hflags[j] = !(rc_abs(hr[(size_t)j * cw + j]) > thr) ? 1 : 0; nnull += hflags[j]; }   // (NaN counts as null)
+                if (nnull > 0) {
+                    DevBuf<int> flags(c, (size_t)cw);
+                    RC_CUDA(cudaMemcpyAsync(flags.p, hflags.data(), sizeof(int) * cw, cudaMemcpyHostToDevice, c->stream));
+                    DevBuf<T> noise(c, (size_t)m * ldz);
+                    k_gaussian<T>(c, noise.p, m, cw, ldz, 0x9e3779b97f4a7c15ull + (uint64_t)c0, 900u + (uint32_t)c->rank, 0);
+                    k_replace_flagged_columns<T>(c, z.p, ldz, noise.p, ldz, m, cw, flags.p, 1.0 / std::sqrt((double)m_glob));
+                    RC_CUDA(cudaStreamSynchronize(c->stream));            // (hflags is read by the copy above)
+                }
+            }
+            DevBuf<T> tacc;
+            if (c0 > 0) {
+                const int64_t ldt = rc_pad_ld(dtype, cw);
+                tacc.alloc(c, (size_t)c0 * ldt);
+                DevBuf<T> t(c, (size_t)c0 * ldt), proj(c, (size_t)m * ldt);
+                k_fill<T>(c, tacc.p, c0, cw, ldt, rc_zero<T>());
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (sharded && ldt != cw) RC_CUDA(cudaMemsetAsync(t.p, 0, sizeof(T) * c0 * ldt, c->stream));
+                    gemm<T>(c, RC_OP_H, RC_OP_N, c0, cw, m, qfull.p, ldq, z.p, ldz, t.p, ldt, rc_one<T>(), rc_zero<T>());
+                    if (sharded) comm_allreduce_sum(c, t.p, (size_t)c0 * ldt, dtype);
+                    gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, c0, qfull.p, ldq, t.p, ldt, proj.p, ldt, rc_one<T>(), rc_zero<T>());
+                    k_sub<T>(c, z.p, ldz, z.p, ldz, proj.p, ldt, m, cw);
+                    k_add<T>(c, tacc.p, ldt, tacc.p, ldt, t.p, ldt, c0, cw);
+                }
+                // R0[0:c0, panel] += T R_pp
+                DevBuf<T> trp(c, (size_t)c0 * cw);
+                gemm<T>(c, RC_OP_N, RC_OP_N, c0, cw, cw, tacc.p, ldt, rpp.p, cw, trp.p, cw, rc_one<T>(), rc_zero<T>());
+                k_add<T>(c, r0.p + c0, w, r0.p + c0, w, trp.p, cw, c0, cw);
+            }
+            DistTsqr<T> ts2;
+            ts2.factor(c, z.p, ldz, m, cw, sharded);
+            ts2.apply(eye.p, cw, cw, qfull.p + c0, ldq);
+            // R0[panel, panel] = R' R_pp
+            DevBuf<T> rr(c, (size_t)cw * cw);
+            gemm<T>(c, RC_OP_N, RC_OP_N, cw, cw, cw, ts2.r(), cw, rpp.p, cw, rr.p, cw, rc_one<T>(), rc_zero<T>());
+            k_triu<T>(c, rr.p, cw, cw, cw);
+            k_copy<T>(c, r0.p + c0 * w + c0, w, rr.p, cw, cw, cw);
+            rc_trace(c, "pqr_tall: panel Householder fallback (re-orthogonalised)");
         }
     }
 }

@@ -318,6 +318,22 @@ template <class T> void k_add(rc_ctx* c, T* dst, int64_t ldd, const T* a, int64_
     add_kernel<T><<<nblocks_for(rows * cols), TB, 0, c->stream>>>(dst, ldd, a, lda, b, ldb, rows, cols);
     RC_CHECK_LAUNCH(c);
 }
+// dst[:, j] = factor * src[:, j] for the flagged columns j
+template <class T>
+__global__ void replace_flagged_columns_kernel(T* __restrict__ dst, int64_t ldd, const T* __restrict__ src, int64_t lds,
+                                               int64_t rows, int64_t cols, const int* __restrict__ flags, RealOf<T> factor) {
+    const int64_t total = rows * cols;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / cols, j = e - i * cols;
+        if (flags[j]) dst[i * ldd + j] = src[i * lds + j] * factor;
+    }
+}
+template <class T> void k_replace_flagged_columns(rc_ctx* c, T* dst, int64_t ldd, const T* src, int64_t lds, int64_t rows, int64_t cols,
+                                                  const int* flags, double factor) {
+    if (rows * cols == 0) return;
+    replace_flagged_columns_kernel<T><<<nblocks_for(rows * cols), TB, 0, c->stream>>>(dst, ldd, src, lds, rows, cols, flags, (RealOf<T>)factor);
+    RC_CHECK_LAUNCH(c);
+}
 template <class T> void k_gaussian(rc_ctx* c, T* p, int64_t rows, int64_t cols, int64_t ld, uint64_t seed, uint32_t stream, int64_t row_offset) {
     if (rows * cols == 0) return;
     gaussian_kernel<T><<<nblocks_for(rows * cols), TB, 0, c->stream>>>(p, rows, cols, ld, seed, stream, row_offset);
@@ -388,6 +404,7 @@ template void k_cast<c32, c64>(rc_ctx*, c32*, int64_t, const c64*, int64_t, int6
     template void k_sub<T>(rc_ctx*, T*, int64_t, const T*, int64_t, const T*, int64_t, int64_t, int64_t); \
     template void k_add<T>(rc_ctx*, T*, int64_t, const T*, int64_t, const T*, int64_t, int64_t, int64_t); \
     template void k_gaussian<T>(rc_ctx*, T*, int64_t, int64_t, int64_t, uint64_t, uint32_t, int64_t);     \
+    template void k_replace_flagged_columns<T>(rc_ctx*, T*, int64_t, const T*, int64_t, int64_t, int64_t, const int*, double); \
     template void k_helmholtz<T>(rc_ctx*, T*, int64_t, int64_t, int64_t, uint64_t, double, double, int64_t); \
     template void k_col_norms2<T>(rc_ctx*, const T*, int64_t, int64_t, int64_t, double*);                 \
     template void k_fro2<T>(rc_ctx*, const T*, int64_t, int64_t, int64_t, double*);                       \

@@ -256,6 +256,9 @@ template <class T> void k_sub(rc_ctx*, T* dst, int64_t ldd, const T* a, int64_t 
 template <class T> void k_add(rc_ctx*, T* dst, int64_t ldd, const T* a, int64_t lda, const T* b, int64_t ldb, int64_t rows, int64_t cols);
 // Philox Gaussian fill (row-major, element index = (row_offset + i) * cols + j)
 template <class T> void k_gaussian(rc_ctx*, T* p, int64_t rows, int64_t cols, int64_t ld, uint64_t seed, uint32_t stream, int64_t row_offset);
+// dst[:, j] = factor * src[:, j] for the flagged columns j
+template <class T> void k_replace_flagged_columns(rc_ctx*, T* dst, int64_t ldd, const T* src, int64_t lds, int64_t rows, int64_t cols,
+                                                  const int* flags, double factor);
 template <class T> void k_helmholtz(rc_ctx*, T* a, int64_t rows, int64_t cols, int64_t ld, uint64_t seed, double kappa, double shift, int64_t row_offset);
 // squared column norms (double), one per column: out[j] = sum_i |a_ij|^2
 template <class T> void k_col_norms2(rc_ctx*, const T* a, int64_t lda, int64_t rows, int64_t cols, double* out);

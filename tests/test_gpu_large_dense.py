@@ -100,3 +100,52 @@ def test_large_dense_svd_matches_gesdd(api, dtype, shape):
     # the SVD container on top: to_qr (pivoted QR of diag(s) vt, src/svd.rs:150-163) at size
     svd = api.SVD.compute_from(a)
     assert relerr(svd.to_qr().to_mat(), a) < (5e-5 if single else 1e-11)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32], ids=["f64", "c64", "f32"])
+def test_rank_deficient_inputs_keep_q_orthonormal(api, dtype):
+    """?geqp3 / ?orgqr and ?gesdd return orthonormal factors whatever the rank.  The panel route (block Gram-Schmidt
+    between column panels) has to work for that: an exactly rank-deficient dense matrix, the zero matrix, duplicated
+    columns, and a sketch with more columns than the operator has rank leave whole panels without a direction of
+    their own (Householder fallback with re-orthogonalisation and Gaussian completion, panel_qr in host_api.cu)."""
+    rng = np.random.default_rng(31)
+    single = np.dtype(dtype) == np.dtype(np.float32)
+    cplx = np.dtype(dtype).kind == "c"
+    tol_o, tol_r = (5e-5, 1e-5) if single else (1e-11, 1e-12)
+
+    def gauss(r, c):
+        g = rng.standard_normal((r, c))
+        return (g + 1j * rng.standard_normal((r, c)) if cplx else g).astype(dtype)
+
+    def check_qr(a, label):
+        q, r, ind = api.pivoted_qr(a)
+        k = min(a.shape)
+        assert sorted(ind.tolist()) == list(range(a.shape[1])), label
+        assert np.max(np.abs(np.conj(q.T).dot(q) - np.eye(k))) < tol_o, label
+        assert np.linalg.norm(q.dot(r) - a[:, ind]) <= tol_r * max(np.linalg.norm(a), 1e-30) + 1e-30, label
+        d = np.abs(np.diagonal(r))
+        assert np.all(d[:-1] >= d[1:] * (1 - 1e-3) - (1e-4 if single else 1e-10) * max(d[0], 1e-30)), label
+
+    check_qr(gauss(1500, 50) @ gauss(50, 900), "exact rank 50, 1500 x 900")
+    check_qr(gauss(700, 40) @ gauss(40, 1600), "exact rank 40, 700 x 1600")
+    check_qr(np.zeros((1000, 700), dtype), "zero 1000 x 700")
+    dup = gauss(1200, 300)
+    dup[:, 150:] = dup[:, :150]
+    check_qr(dup, "duplicated columns")
+    # SVD of an exactly rank-deficient matrix: singular values and the leading singular vectors
+    a = gauss(900, 30) @ gauss(30, 600)
+    u, s, vt = api.compute_svd(a)
+    s0 = np.linalg.svd(a.astype(np.complex128 if cplx else np.float64), compute_uv=False)
+    # (f32: the 570 singular values behind the rank sit at the roundoff level of the working precision, eps sqrt(m) s_0)
+    assert np.max(np.abs(s - s0)) / s0[0] < (1e-4 if single else 1e-12)
+    assert np.max(np.abs(s[:30] - s0[:30]) / s0[:30]) < (2e-5 if single else 1e-12)
+    assert np.linalg.norm((u * s).dot(vt) - a) / np.linalg.norm(a) < (2e-5 if single else 1e-12)
+    assert np.max(np.abs(np.conj(u[:, :30].T).dot(u[:, :30]) - np.eye(30))) < (2e-4 if single else 1e-10)
+    assert np.max(np.abs(vt[:30].dot(np.conj(vt[:30].T)) - np.eye(30))) < (2e-4 if single else 1e-10)
+    # a sketch with more columns than the operator has rank: the range basis must still be orthonormal
+    op = gauss(4096, 100) @ gauss(100, 1024)
+    q = api.sample_range_by_rank(op, 290, 10, seed=3)
+    assert q.shape == (4096, 290)
+    assert np.max(np.abs(np.conj(q.T).dot(q) - np.eye(290))) < tol_o
+    proj = q[:, :128].dot(np.conj(q[:, :128].T).dot(op))
+    assert np.linalg.norm(proj - op) / np.linalg.norm(op) < (1e-4 if single else 1e-10)      # the first 100+ columns span the range
