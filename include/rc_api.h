@@ -94,7 +94,8 @@ const char* rc_last_error_string(rc_ctx* ctx);
  * once at the end and a rejected panel re-runs the sampler on Householder TSQR), "overlap" (1 = independent stages on
  * auxiliary streams), "fused_small_qr" (1 = small pivoted QRs in the fused one-CTA kernel), "cluster_qr" (1 = medium
  * pivoted QRs -- the factor fits 8 CTAs' shared memory -- in the thread-block-cluster kernel, 0 = cooperative grid
- * kernel), "tf32_ring" (A/B variants of the tcgen05 TF32 kernel: 0 default, 1 = six TMEM split stages, 2 = high part
+ * kernel), "svd_precondition" (1 = the SVD of a matrix too wide for one CTA runs Jacobi on R^H of a pivoted QR; 0 = on the
+ * unpivoted triangle), "tf32_ring" (A/B variants of the tcgen05 TF32 kernel: 0 default, 1 = six TMEM split stages, 2 = high part
  * from shared memory), "workspace_cache" (1 = device blocks of 1 MiB .. 8 GiB are cached per context and reused in
  * stream order; 0 = every allocation goes to cudaMallocAsync), "release_workspaces" (any value: empty the cache and trim
  * the device memory pool now).

@@ -618,10 +618,34 @@ void svd_tall(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, int dtype, boo
         DevBuf<T> ur(c, (size_t)w * w);
         jacobi_svd<T>(c, ts.r(), w, w, w, ur.p, w, ds.p, P<T>(wm.get()), wm->ld, info.p);
         ts.apply(ur.p, w, w, P<T>(um.get()), um->ld);
+    } else if (!sharded && c->svd_precondition) {
+        // Wide panels (a general dense matrix, SVD::compute_from of src/svd.rs:165-169), preconditioned: column-pivoted
+        // QR first (the GEMM-shaped large-dense route of pivoted_qr_impl), then one-sided Jacobi on R^H instead of on
+        // an unpivoted triangle.  The rows of a rank-revealing R are graded and nearly orthogonal, so the iteration
+        // converges in a few sweeps instead of ten or more (the preconditioning of LAPACK's ?gejsv; every sweep of the
+        // whole-GPU kernel is n - 1 grid-wide rounds over an n x n matrix in L2):
+        //   A P = Q R,  R^H = Uj S Wj^H  =>  A = (Q Wj) S (P Uj)^H.
+        rc_matrix view;
+        view.ctx = c; view.dtype = dtype; view.rows = m; view.cols = w; view.ld = ldy; view.data = y; view.owns = false;
+        QrParts qr;
+        qr.want_ind = true;
+        pivoted_qr_impl<T>(c, &view, false, w, true, qr);
+        MatPtr g(mat_conj_transpose<T>(c, qr.r.get()));                      // R^H, w x w lower triangular
+        const int64_t ldu = rc_pad_ld(dtype, w);
+        DevBuf<T> uj(c, (size_t)w * ldu), wj(c, (size_t)w * ldu);
+        jacobi_svd<T>(c, P<T>(g.get()), g->ld, w, w, uj.p, ldu, ds.p, wj.p, ldu, info.p);
+        gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, P<T>(qr.q.get()), qr.q->ld, wj.p, ldu, P<T>(um.get()), um->ld, rc_one<T>(), rc_zero<T>());
+        // W = P Uj: row ind[i] of W is row i of Uj
+        std::vector<int> inv((size_t)w);
+        for (int64_t i = 0; i < w; ++i) inv[(size_t)qr.ind[(size_t)i]] = (int)i;
+        DevBuf<int> dinv(c, (size_t)w);
+        RC_CUDA(cudaMemcpyAsync(dinv.p, inv.data(), sizeof(int) * w, cudaMemcpyHostToDevice, c->stream));
+        k_gather_rows<T>(c, P<T>(wm.get()), wm->ld, uj.p, ldu, w, w, dinv.p);
+        RC_CUDA(cudaStreamSynchronize(c->stream));                            // (inv is read by the copy above)
     } else {
-        // Wide panels (a general dense matrix, SVD::compute_from of src/svd.rs:165-169): unpivoted QR by column
-        // panels (all GEMM-shaped), Jacobi on the w x w triangle -- one CTA if it fits shared memory, else the
-        // cooperative whole-GPU kernel -- and U = Qfull Ur.
+        // Wide panels, row-sharded input (or option "svd_precondition" = 0): unpivoted QR by column panels (all
+        // GEMM-shaped), Jacobi on the w x w triangle -- one CTA if it fits shared memory, else the cooperative
+        // whole-GPU kernel -- and U = Qfull Ur.
         DevBuf<T> qfull, r0;
         int64_t ldq = 0;
         panel_qr<T>(c, y, ldy, m, w, sharded, dtype, qfull, ldq, r0);
@@ -1207,6 +1231,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
         else if (!strcmp(key, "speculate")) c->speculate = (int)v;
         else if (!strcmp(key, "fused_small_qr")) c->fused_small_qr = (int)v;
         else if (!strcmp(key, "cluster_qr")) c->cluster_qr = (int)v;
+        else if (!strcmp(key, "svd_precondition")) c->svd_precondition = (int)v;
         else if (!strcmp(key, "workspace_cache")) { c->block_cache_on = (int)v; if (!v) rc_cache_release(c); }
         else if (!strcmp(key, "release_workspaces")) { trim_pool(c); }
         else if (!strcmp(key, "overlap")) c->overlap = (int)v;

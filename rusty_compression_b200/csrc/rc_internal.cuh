@@ -61,6 +61,7 @@ struct rc_ctx {
     // Speculative execution (host_api.cu, DeferScope): inside a deferred region the Cholesky-QR2 panels do not read
     // their status words back (no host synchronisation in the middle of a pipeline); the words are collected here and
     // checked once at the end, and a failed check re-runs the region with the Householder TSQR forced.
+    int svd_precondition = 1;     // option "svd_precondition": wide SVDs run Jacobi on R^H of a pivoted QR (host_api.cu: svd_tall)
     int cluster_qr = 1;           // option "cluster_qr": medium pivoted QRs in the thread-block-cluster kernel (pivqr.cu)
     int fused_small_qr = 1;       // option "fused_small_qr": small pivoted QRs in the fused one-CTA kernel (pivqr.cu)
     int speculate = 1;            // option "speculate"
