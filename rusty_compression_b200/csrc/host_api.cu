@@ -249,15 +249,18 @@ cudaEvent_t aux_event(rc_ctx* c, int i) {
 // Cholesky breaks down -- the caller falls back to the unconditionally stable Householder TSQR
 // with Y untouched.  Backward error and orthogonality are O(eps) in the accepted regime
 // (Yamamoto et al. 2015), the same class as Householder, which is what pivot parity needs.
-// panel_scale (optional, host, in/out): the largest diagonal entry of R over the panels of a wider factorisation so far.
-// With it the status words are read back at once (no speculation) and a panel whose smallest diagonal entry is at most
-// 1e2 eps sqrt(m) times that scale is REJECTED however well conditioned it is relative to itself: a panel that has no
-// direction of its own left after the projection is rounding noise, and a Cholesky-QR2 of noise is orthogonal to the
-// previous panels only to eps x (norm before the projection / norm of the noise) -- the loss compounds from panel to
-// panel (measured on an exact rank-50 1500 x 900 matrix: 3e-15, 2e-14, 9e-12, 1e-6, 0.6).
+// panel_scale (optional, host, in/out): the largest diagonal entry of R over the panels of a wider factorisation so far
+// (total width full_w).  With it the status words are read back at once (no speculation) and a panel whose smallest
+// diagonal entry is at most 10 eps sqrt(full_w) times that scale is REJECTED however well conditioned it is relative to
+// itself: a panel that has no direction of its own left after the projection is rounding noise (measured ~50 eps of the
+// scale at full_w = 900 in f64 and at full_w = 266 in f32, i.e. ~3 eps sqrt(full_w): the error of Q (Q^H y), not of the
+// length-m dot products), and a Cholesky-QR2 of noise is orthogonal to the previous panels only to eps x (norm before
+// the projection / norm of the noise) -- the loss compounds from panel to panel (measured on an exact rank-50
+// 1500 x 900 matrix: 3e-15, 2e-14, 9e-12, 1e-6, 0.6).  The window must not be wider than that: the last panel of
+// config 4's f32 sketch holds legitimate directions at 7e-5 of the scale.
 template <class T>
 bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, int dtype,
-             DevBuf<T>& q1, DevBuf<T>& rinv2, DevBuf<T>& rfac, int64_t& lds, double* panel_scale = nullptr) {
+             DevBuf<T>& q1, DevBuf<T>& rinv2, DevBuf<T>& rfac, int64_t& lds, double* panel_scale = nullptr, int64_t full_w = 0) {
     if (c->qr_mode == 1 || c->force_householder) return false;
     const int64_t m_all = m;    // (local rows; the Gram matrices are summed across shards)
     // (one CTA holds Gram matrices up to chol_max_width; twice that with one level of 2 x 2 blocking, chol_inv_blocked: the
@@ -302,8 +305,7 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
     if (!cholqr2_acceptable(h, single)) { c->cholqr_fallbacks++; return false; }
     if (panel_scale) {
         const double eps = single ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
-        const double m_glob = (double)(sharded ? (int64_t)c->nranks * m : m);
-        if (!(h[1] > 1.0e2 * eps * std::sqrt(m_glob) * std::max(*panel_scale, h[2]))) { c->cholqr_fallbacks++; return false; }
+        if (!(h[1] > 10.0 * eps * std::sqrt((double)std::max<int64_t>(full_w, w)) * std::max(*panel_scale, h[2]))) { c->cholqr_fallbacks++; return false; }
         *panel_scale = std::max(*panel_scale, h[2]);
     }
     rc_trace(c, "  cholqr2: 2 x (gram + chol), q1 = Y rinv1");
@@ -373,7 +375,7 @@ void panel_qr(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, 
         }
         DevBuf<T> pq1, prinv2, prfac;
         int64_t lds = 0;
-        if (cholqr2<T>(c, yp, ldy, m, cw, sharded, dtype, pq1, prinv2, prfac, lds, &scale)) {
+        if (cholqr2<T>(c, yp, ldy, m, cw, sharded, dtype, pq1, prinv2, prfac, lds, &scale, w)) {
             rc_trace(c, "pqr_tall: panel cholqr2");
             gemm<T>(c, RC_OP_N, RC_OP_N, m, cw, cw, pq1.p, lds, prinv2.p, lds, qfull.p + c0, ldq, rc_one<T>(), rc_zero<T>());
             k_copy<T>(c, r0.p + c0 * w + c0, w, prfac.p, lds, cw, cw);
@@ -384,7 +386,7 @@ void panel_qr(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, 
             // Y_p = Q_p R_pp with Q_p orthonormal, but the directions that belong to (numerically) zero rows of R_pp are
             // whatever the reflectors leave -- unit vectors for a zero panel -- and Q_p is orthogonal to the previous
             // panels only to eps * cond(Y_p).  ?geqp3 returns an orthonormal Q whatever the rank, so:
-            //   1. null directions (|r_jj| <= 8 eps sqrt(m) x the largest diagonal entry so far) are replaced by
+            //   1. null directions (|r_jj| <= eps sqrt(w) x the largest diagonal entry so far) are replaced by
             //      Gaussian vectors (they multiply rows of R_pp that are zero to that level),
             //   2. Q_p is orthogonalised against the previous panels (twice) and factored again, Q_p = Q_prev T + Q_p' R',
             //   3. R0 takes the correction: R0[0:c0, panel] += T R_pp, R0[panel, panel] = R' R_pp.
@@ -405,9 +407,11 @@ void panel_qr(rc_ctx* c, T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, 
                 for (int64_t j = 0; j < cw; ++j) { const double d = rc_abs(hr[(size_t)j * cw + j]); if (d == d) scale = std::max(scale, d); }
                 std::vector<int> hflags((size_t)cw);
                 int64_t nnull = 0;
-                // (8 eps sqrt(m): the level of the rounding noise in R_pp itself -- the replaced directions cost
-                // |r_jj| in the reconstruction, so a larger window would show: 1e3 gave 1e-3 relative in f32)
-                const double thr = 8.0 * eps * std::sqrt((double)m_glob) * scale;
+                // (eps sqrt(w): below the rounding noise of a projected panel, ~3 eps sqrt(w) -- what has to go are the
+                // STRUCTURED leftovers of exactly zero rows (unit vectors); a direction at the noise level is random
+                // already and the re-orthogonalisation below deals with it.  The replaced directions cost |r_jj| in
+                // the reconstruction, so a wide window shows: 1e3 eps sqrt(m) gave 1e-3 relative in f32.)
+                const double thr = eps * std::sqrt((double)w) * scale;
                 for (int64_t j = 0; j < cw; ++j) { hflags[j] = !(rc_abs(hr[(size_t)j * cw + j]) > thr) ? 1 : 0; nnull += hflags[j]; }   // (NaN counts as null)
                 if (nnull > 0) {
                     DevBuf<int> flags(c, (size_t)cw);

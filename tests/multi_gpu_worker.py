@@ -84,6 +84,23 @@ def main():
             assert abs(ra - ra_ref) <= max(tol, 1e-8) * ra_ref + (5e-7 if tol > 1e-6 else 0.0), (dtype, ra, ra_ref)
             print(f"[multi-gpu x{world}] {np.dtype(dtype).name}: sv err {err_s:.2e}, rec {rec:.3e} (ref {rec_ref:.3e}), "
                   f"id err {e:.3e} (ref {e_ref:.3e}), adaptive rank {hist[-1][0]}", flush=True)
+    # --- a sketch with more columns than the operator has rank, row-sharded (f64: 300 columns of a rank-100 operator, wider
+    #     than one Cholesky / TSQR panel): the later panels have no direction of their own, every rank must take the same
+    #     Householder fallback with Gaussian completion, and the gathered range basis must be orthonormal and span range(A)
+    rng = np.random.default_rng(17)
+    m, n, rk = 8192, 1024, 100
+    a = rng.standard_normal((m, rk)).dot(rng.standard_normal((rk, n)))
+    rows = m // world
+    op = api.DeviceMatrix.from_numpy(a[rank * rows:(rank + 1) * rows], ctx=ctx).set_shard(m, rank * rows)
+    q = api.sample_range_by_rank(op, 290, 10, seed=11, ctx=ctx, device=True)
+    q_full = gather_rows(q.to_numpy())
+    if rank == 0:
+        orth = np.max(np.abs(q_full.T.dot(q_full) - np.eye(290)))
+        lead = q_full[:, :128]
+        res = np.linalg.norm(a - lead.dot(lead.T.dot(a))) / np.linalg.norm(a)
+        print(f"[multi-gpu x{world}] rank-100 operator sampled with 300 columns (f64, sharded): |Q^T Q - I| {orth:.2e}, "
+              f"residual of the leading 128 columns {res:.2e}", flush=True)
+        assert orth < 1e-11 and res < 1e-10
     # --- config-4 shape: row-sharded tall-skinny range finder, f32, rank 256 (+10), n = 8192 (the sketch, l = 266, is wider
     #     than one TSQR panel: panel path with all-reduced projections).  m = 2^19 by default (16 GiB of A, the size SURVEY
     #     8(d) prescribes for the CPU side of config 4); RC_TEST_CONFIG4_ROWS overrides it.
