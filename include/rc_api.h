@@ -123,6 +123,16 @@ rc_status rc_matrix_create(rc_ctx* ctx, rc_dtype dtype, int64_t rows, int64_t co
 /* Upload a strided host view (strides in elements), like `mat.assign(&arr)` (src/pivoted_qr.rs:29). */
 rc_status rc_matrix_from_host(rc_ctx* ctx, rc_dtype dtype, const void* host, int64_t rows,
                               int64_t cols, int64_t row_stride, int64_t col_stride, rc_matrix** out);
+/* Pipelined upload of a row-major host view (row stride in elements, unit column stride; pinned memory for a
+ * transfer that really is asynchronous): returns as soon as the copy is queued on the context's copy stream, so
+ * the transfer of the next operator overlaps the kernels working on the current one.  The handle must go through
+ * rc_matrix_await before ANY other use.  rc_matrix_await orders the context stream behind the copy (it does not
+ * block the host unless `block_host` != 0); the host buffer must stay valid and unmodified until the copy is
+ * complete (rc_matrix_await with block_host = 1, or any later rc_ctx_synchronize / blocking call on the context).
+ * No counterpart in the reference (a host library has no transfer to hide). */
+rc_status rc_matrix_from_host_async(rc_ctx* ctx, rc_dtype dtype, const void* host, int64_t rows,
+                                    int64_t cols, int64_t row_stride, rc_matrix** out);
+rc_status rc_matrix_await(rc_ctx* ctx, rc_matrix* m, int block_host);
 /* Borrow device memory (row-major, leading dimension `ld` elements); never freed by the library. */
 rc_status rc_matrix_wrap_device(rc_ctx* ctx, rc_dtype dtype, void* device_ptr, int64_t rows,
                                 int64_t cols, int64_t ld, rc_matrix** out);

@@ -37,6 +37,8 @@ SIGNATURES = {
     "rc_ctx_comm_info": (c_int, [H, POINTER(c_int), POINTER(c_int)]),
     "rc_matrix_create": (c_int, [H, c_int, c_int64, c_int64, PH]),
     "rc_matrix_from_host": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, PH]),
+    "rc_matrix_from_host_async": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, PH]),
+    "rc_matrix_await": (c_int, [H, H, c_int]),
     "rc_matrix_wrap_device": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, PH]),
     "rc_column_id_col_ind_len": (c_size_t, [H]),
     "rc_row_id_row_ind_len": (c_size_t, [H]),

@@ -165,6 +165,32 @@ class DeviceMatrix:
         return DeviceMatrix(ctx, h)
 
     @staticmethod
+    def from_numpy_async(arr, ctx=None):
+        """Pipelined upload (rc_matrix_from_host_async): returns while the copy runs on the context's copy stream.
+        `arr` must be a row-major 2-D array (pinned memory for a truly asynchronous transfer) that stays alive and
+        unmodified until the copy is complete; call `.await_upload()` before any other use of the handle."""
+        ctx = ctx or default_context()
+        if arr.dtype not in DTYPE_CODE:
+            raise TypeError(f"unsupported dtype {arr.dtype}")
+        es = arr.dtype.itemsize
+        if arr.ndim != 2 or (arr.size and (arr.strides[1] != es or arr.strides[0] % es or arr.strides[0] < arr.shape[1] * es)):
+            raise ValueError("from_numpy_async takes a row-major 2-D array")
+        rs = arr.strides[0] // es if arr.size else arr.shape[1]
+        h = c_void_p()
+        ctx.check(ctx.lib.rc_matrix_from_host_async(ctx.h, DTYPE_CODE[arr.dtype], c_void_p(arr.ctypes.data), arr.shape[0],
+                                                    arr.shape[1], rs, ctypes.byref(h)))
+        m = DeviceMatrix(ctx, h)
+        m._upload_src = arr                      # keeps the host buffer alive while the copy is in flight
+        return m
+
+    def await_upload(self, block_host=False):
+        """Order the context stream behind a pipelined upload (and, with block_host, wait for it on the host)."""
+        self.ctx.check(self.ctx.lib.rc_matrix_await(self.ctx.h, self.h, 1 if block_host else 0))
+        if block_host:
+            self._upload_src = None
+        return self
+
+    @staticmethod
     def wrap_device(ptr, rows, cols, ld, dtype, ctx=None):
         ctx = ctx or default_context()
         h = c_void_p()

@@ -258,6 +258,32 @@ bool chol_inv_blocked(rc_ctx* c, const T* g, int64_t ldg, int64_t w, T* r, T* ri
     return true;
 }
 
+// G += factor * max_j Re(G_jj) * I  (the shift of the first round of shifted Cholesky-QR3, host_api.cu: cholqr2)
+namespace {
+template <class T>
+__global__ void __launch_bounds__(256) chol_shift_kernel(T* __restrict__ g, int64_t ldg, int w, double factor) {
+    __shared__ double s_red[8];
+    double mx = 0.0;
+    for (int j = threadIdx.x; j < w; j += 256) mx = fmax(mx, (double)rc_real(g[(int64_t)j * ldg + j]));
+    for (int m = 16; m > 0; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = 0.0;
+    for (int i = 0; i < 8; ++i) mx = fmax(mx, s_red[i]);
+    const T shift = rc_make<T>(factor * mx, 0.0);
+    for (int j = threadIdx.x; j < w; j += 256) g[(int64_t)j * ldg + j] = g[(int64_t)j * ldg + j] + shift;
+}
+}  // namespace
+template <class T>
+void chol_shift(rc_ctx* c, T* g, int64_t ldg, int64_t w, double factor) {
+    chol_shift_kernel<T><<<1, 256, 0, c->stream>>>(g, ldg, (int)w, factor);
+    RC_CHECK_LAUNCH(c);
+}
+template void chol_shift<float>(rc_ctx*, float*, int64_t, int64_t, double);
+template void chol_shift<double>(rc_ctx*, double*, int64_t, int64_t, double);
+template void chol_shift<c32>(rc_ctx*, c32*, int64_t, int64_t, double);
+template void chol_shift<c64>(rc_ctx*, c64*, int64_t, int64_t, double);
+
 int64_t chol_max_width(rc_ctx* c, int dtype) {
     size_t lim = (c->smem_optin ? c->smem_optin : (size_t)227 * 1024) - 8192;
     int64_t w = 1;

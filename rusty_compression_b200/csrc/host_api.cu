@@ -183,14 +183,22 @@ void download_ind(rc_ctx* c, const int* dind, int64_t n, std::vector<uint64_t>& 
 }
 
 
-// Acceptance test of a Cholesky-QR2 panel from its two status words (chol.cu): round 1 without breakdown and with
-// diag(R1) spanning less than 1e6 (2e2 in single precision), round 2 without breakdown and with a Gram matrix of q1
-// within 0.25 of I.
-bool cholqr2_acceptable(const double* h, bool single) {
+// Acceptance test of a Cholesky-QR2 panel from its status words (chol.cu; 4 per round: breakdown flag, min and max of
+// diag(R), max |G - I|): round 1 without breakdown, round 2 without breakdown and with a Gram matrix of q1 within 0.25
+// of I, and one of
+//   (a) diag(R1) spanning less than 1e6 (2e2 in single precision), or
+//   (b) double precision: q1 orthonormal to 1e-3 already (and diag(R2) within a factor 2).  G2 - I is the backward
+//       error of round 1 in the scaling of the columns of Y, so this accepts GRADED sketches whatever their diagonal
+//       spans -- Cholesky is invariant under column scaling, and the sketches of a power iteration (Z = A^H q,
+//       Y = A w with q, w ordered by a pivoted QR) have columns graded like the spectrum: measured on a 74-column
+//       sketch over twelve decades, diag(R1) spans 2e12 and max |G2 - I| = 1e-13.
+bool cholqr2_acceptable(const double* h, bool single, bool shifted = false) {
     const double max_ratio = single ? 2.0e2 : 1.0e6;
-    const bool ok1 = h[0] == 0.0 && h[1] > 0.0 && h[2] / h[1] <= max_ratio;
+    const bool ok0 = !shifted || (h[8] == 0.0 && h[9] > 0.0 && h[12] == 0.0 && h[13] > 0.0);   // the two shifted rounds
     const bool ok2 = h[4] == 0.0 && h[5] > 0.0 && h[7] <= 0.25;
-    return ok1 && ok2;
+    const bool ok1 = h[0] == 0.0 && h[1] > 0.0 &&
+                     (h[2] / h[1] <= max_ratio || (!single && ok2 && h[7] <= 1.0e-3 && h[6] / h[5] <= 2.0));
+    return ok0 && ok1 && ok2;
 }
 
 // Deferred (speculative) region: see rc_ctx::defer_depth.  finish_deferred() reads all collected status words with
@@ -204,12 +212,15 @@ bool finish_deferred(rc_ctx* c) {
     bool ok = true;
     const size_t n = c->deferred.size();
     if (n == 0) { RC_CUDA(cudaStreamSynchronize(c->stream)); return true; }
-    std::vector<double> h(8 * n);
+    std::vector<double> h(16 * n);
     for (size_t i = 0; i < n; ++i)
-        RC_CUDA(cudaMemcpyAsync(h.data() + 8 * i, c->deferred[i].status, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        RC_CUDA(cudaMemcpyAsync(h.data() + 16 * i, c->deferred[i].status, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     RC_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < n; ++i) {
-        if (!cholqr2_acceptable(h.data() + 8 * i, c->deferred[i].single)) { ok = false; c->cholqr_fallbacks++; c->cholqr_used--; }
+        if (!cholqr2_acceptable(h.data() + 16 * i, c->deferred[i].single, c->deferred[i].shifted)) {
+            ok = false; c->cholqr_fallbacks++; c->cholqr_used--;
+            if (c->deferred[i].shifted) c->cholqr_shifted--;
+        }
         rc_dev_free(c, c->deferred[i].status);
     }
     c->deferred.clear();
@@ -219,6 +230,26 @@ void drop_deferred(rc_ctx* c) {
     for (auto& d : c->deferred) rc_dev_free(c, d.status);
     c->deferred.clear();
 }
+// Early check inside a deferred region (the status words collected so far may have been written on the auxiliary
+// streams): true when every speculative panel so far was acceptable.
+bool check_deferred_now(rc_ctx* c) {
+    for (int i = 0; i < 2; ++i) if (c->aux_stream[i]) RC_CUDA(cudaStreamSynchronize(c->aux_stream[i]));
+    return finish_deferred(c);
+}
+// Non-speculative redo of a rejected panel on the next route down (shifted Cholesky-QR where it applies, with the
+// Householder TSQR behind it; the Householder TSQR at once in single precision).
+struct RedoScope {
+    rc_ctx* c;
+    int saved_depth;
+    bool saved_shifted, saved_householder;
+    RedoScope(rc_ctx* ctx, int dtype) : c(ctx), saved_depth(ctx->defer_depth), saved_shifted(ctx->force_shifted),
+                                        saved_householder(ctx->force_householder) {
+        const bool single = (dtype == RC_F32 || dtype == RC_C32);
+        c->defer_depth = 0;
+        if (c->shifted_cholqr && !single) c->force_shifted = true; else c->force_householder = true;
+    }
+    ~RedoScope() { c->defer_depth = saved_depth; c->force_shifted = saved_shifted; c->force_householder = saved_householder; }
+};
 
 // Work on an auxiliary stream (with its own tile-scheduler scratch) for the lifetime of the scope.  Everything the
 // library enqueues -- kernels, stream-ordered allocations and frees, collectives -- follows c->stream.
@@ -258,11 +289,92 @@ cudaEvent_t aux_event(rc_ctx* c, int i) {
 // the projection / norm of the noise) -- the loss compounds from panel to panel (measured on an exact rank-50
 // 1500 x 900 matrix: 3e-15, 2e-14, 9e-12, 1e-6, 0.6).  The window must not be wider than that: the last panel of
 // config 4's f32 sketch holds legitimate directions at 7e-5 of the scale.
+// shifted = true: shifted Cholesky-QR (Fukaya, Kannan, Nakatsukasa, Yamamoto, Yanagisawa 2020, "sCholQR3", with the
+// shifted round applied twice).  A round on G + s I cannot break down and divides cond(Y) by ~1/sqrt(s_rel); two of
+// them bring any sketch with cond(Y) up to ~1e16 below 1e6, which the two plain rounds then finish to O(u)
+// orthogonality: R = R2 R1 R0b R0a, residual O(u ||Y||) like the Householder route, all of it GEMM-shaped (four rounds
+// = 0.9 ms for 65 536 x 74 in double against 1.8 ms for the TSQR tree).  The shift is s = 100 u (sqrt(m) + w) w max_j G_jj:
+// the paper's bound 11 (m w + w (w + 1)) u ||Y||^2 assumes worst-case (linear in m) error growth in the Gram matrix and,
+// at m = 65 536, leaves cond ~ 6e7 after one round of a twelve-decade sketch (measured: rejected); the accumulation
+// error of a length-m dot product grows like sqrt(m), which this shift still covers ~100 times over, and a Cholesky
+// that breaks down regardless is caught by its status word like any other (-> Householder TSQR).
+template <class T>
+bool cholqr_rounds(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, int dtype, bool shifted,
+                   DevBuf<T>& q1, DevBuf<T>& rinv2, DevBuf<T>& rfac, int64_t& lds, double* panel_scale, int64_t full_w) {
+    lds = rc_pad_ld(dtype, w);
+    DevBuf<T> g(c, (size_t)w * lds), r1(c, (size_t)w * lds), rinv1(c, (size_t)w * lds), r2(c, (size_t)w * lds);
+    DevBuf<double> status(c, 16);
+    double h[16];
+    const bool single = (dtype == RC_F32 || dtype == RC_C32);
+    auto gram_chol = [&](const T* x, int64_t ldx, T* rr, T* ri, double* st, double shift_factor) -> bool {
+        if (sharded && lds != w) RC_CUDA(cudaMemsetAsync(g.p, 0, sizeof(T) * w * lds, c->stream));   // padding is summed too
+        gemm<T>(c, RC_OP_H, RC_OP_N, w, w, m, x, ldx, x, ldx, g.p, lds, rc_one<T>(), rc_zero<T>());
+        if (sharded) comm_allreduce_sum(c, g.p, (size_t)w * lds, dtype);      // one all-reduce of the Gram matrix
+        if (shift_factor > 0.0) chol_shift<T>(c, g.p, lds, w, shift_factor);
+        return chol_inv_blocked<T>(c, g.p, lds, w, rr, ri, lds, st);
+    };
+    DevBuf<T> ya, yb, r0;
+    if (shifted) {
+        const double u = single ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
+        const double m_glob = sharded ? (double)m * c->nranks : (double)m;     // (upper bound of the global row count)
+        const double s_rel = 100.0 * u * (std::sqrt(m_glob) + (double)w) * (double)w;
+        DevBuf<T> r0a(c, (size_t)w * lds), r0b(c, (size_t)w * lds), rinv0(c, (size_t)w * lds);
+        if (!gram_chol(y, ldy, r0a.p, rinv0.p, status.p + 8, s_rel)) return false;
+        ya.alloc(c, (size_t)m * lds);
+        gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, y, ldy, rinv0.p, lds, ya.p, lds, rc_one<T>(), rc_zero<T>());
+        if (!gram_chol(ya.p, lds, r0b.p, rinv0.p, status.p + 12, s_rel)) return false;
+        yb.alloc(c, (size_t)m * lds);
+        gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, ya.p, lds, rinv0.p, lds, yb.p, lds, rc_one<T>(), rc_zero<T>());
+        ya.release();
+        r0.alloc(c, (size_t)w * lds);
+        gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, r0b.p, lds, r0a.p, lds, r0.p, lds, rc_one<T>(), rc_zero<T>());
+        y = yb.p; ldy = lds;
+    } else {
+        RC_CUDA(cudaMemsetAsync(status.p + 8, 0, 8 * sizeof(double), c->stream));
+    }
+    // Both rounds are enqueued back to back and their status words are read with ONE host synchronisation at
+    // the end (a sync after each Cholesky left the GPU idle for a launch round trip twice per panel).  If round 1
+    // broke down, round 2 ran on garbage: its loops are data independent, nothing it wrote is used, and Y is
+    // untouched for the Householder fallback.
+    if (!gram_chol(y, ldy, r1.p, rinv1.p, status.p, 0.0)) return false;
+    q1.alloc(c, (size_t)m * lds);
+    gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, y, ldy, rinv1.p, lds, q1.p, lds, rc_one<T>(), rc_zero<T>());
+    yb.release();
+    rinv2.alloc(c, (size_t)w * lds);
+    if (!gram_chol(q1.p, lds, r2.p, rinv2.p, status.p + 4, 0.0)) return false;
+    rfac.alloc(c, (size_t)w * lds);
+    gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, r2.p, lds, r1.p, lds, rfac.p, lds, rc_one<T>(), rc_zero<T>());
+    if (shifted) {
+        DevBuf<T> r21(c, (size_t)w * lds);
+        k_copy<T>(c, r21.p, lds, rfac.p, lds, w, w);
+        gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, r21.p, lds, r0.p, lds, rfac.p, lds, rc_one<T>(), rc_zero<T>());
+    }
+    if (c->defer_depth > 0 && !panel_scale) {
+        // speculative: carry on as if both rounds were accepted; the status words are checked at the end of the
+        // deferred region (finish_deferred), which re-runs it on the next route when a panel was not acceptable
+        c->deferred.push_back({status.take(), single, shifted});
+        c->cholqr_used++;
+        if (shifted) c->cholqr_shifted++;
+        return true;
+    }
+    RC_CUDA(cudaMemcpyAsync(h, status.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    RC_CUDA(cudaStreamSynchronize(c->stream));
+    if (!cholqr2_acceptable(h, single, shifted)) return false;
+    if (panel_scale) {
+        const double eps = single ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
+        if (!(h[1] > 10.0 * eps * std::sqrt((double)std::max<int64_t>(full_w, w)) * std::max(*panel_scale, h[2]))) return false;
+        *panel_scale = std::max(*panel_scale, h[2]);
+    }
+    rc_trace(c, shifted ? "  shifted cholqr: 4 x (gram + chol), 3 x apply" : "  cholqr2: 2 x (gram + chol), q1 = Y rinv1");
+    c->cholqr_used++;
+    if (shifted) c->cholqr_shifted++;
+    return true;
+}
+
 template <class T>
 bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool sharded, int dtype,
              DevBuf<T>& q1, DevBuf<T>& rinv2, DevBuf<T>& rfac, int64_t& lds, double* panel_scale = nullptr, int64_t full_w = 0) {
     if (c->qr_mode == 1 || c->force_householder) return false;
-    const int64_t m_all = m;    // (local rows; the Gram matrices are summed across shards)
     // (one CTA holds Gram matrices up to chol_max_width; twice that with one level of 2 x 2 blocking, chol_inv_blocked: the
     // 138-column c64 sketch of config 5 is ONE Cholesky-QR2 instead of two panels with block Gram-Schmidt between them.
     // Double precision only: in single precision the acceptance window is diag(R1) within 2e2, which a wide sketch of
@@ -270,47 +382,21 @@ bool cholqr2(rc_ctx* c, const T* y, int64_t ldy, int64_t m, int64_t w, bool shar
     // full-width attempt cost 8 ms -- while its 92-column panels do)
     const bool single_prec = (dtype == RC_F32 || dtype == RC_C32);
     const int64_t wlim = (single_prec ? 1 : 2) * chol_max_width(c, dtype);
-    if ((!sharded && m_all < 4 * w) || w > wlim || w < 2) return false;
-    lds = rc_pad_ld(dtype, w);
-    DevBuf<T> g(c, (size_t)w * lds), r1(c, (size_t)w * lds), rinv1(c, (size_t)w * lds), r2(c, (size_t)w * lds);
-    DevBuf<double> status(c, 8);
-    double h[8];
-    const bool single = (dtype == RC_F32 || dtype == RC_C32);
-    auto gram_chol = [&](const T* x, int64_t ldx, T* rr, T* ri, double* st) -> bool {
-        if (sharded && lds != w) RC_CUDA(cudaMemsetAsync(g.p, 0, sizeof(T) * w * lds, c->stream));   // padding is summed too
-        gemm<T>(c, RC_OP_H, RC_OP_N, w, w, m, x, ldx, x, ldx, g.p, lds, rc_one<T>(), rc_zero<T>());
-        if (sharded) comm_allreduce_sum(c, g.p, (size_t)w * lds, dtype);      // one all-reduce of the Gram matrix
-        return chol_inv_blocked<T>(c, g.p, lds, w, rr, ri, lds, st);
-    };
-    // Both rounds are enqueued back to back and their status words are read with ONE host synchronisation at
-    // the end (a sync after each Cholesky left the GPU idle for a launch round trip twice per panel).  If round 1
-    // broke down, round 2 ran on garbage: its loops are data independent, nothing it wrote is used, and Y is
-    // untouched for the Householder fallback.
-    if (!gram_chol(y, ldy, r1.p, rinv1.p, status.p)) return false;
-    q1.alloc(c, (size_t)m * lds);
-    gemm<T>(c, RC_OP_N, RC_OP_N, m, w, w, y, ldy, rinv1.p, lds, q1.p, lds, rc_one<T>(), rc_zero<T>());
-    rinv2.alloc(c, (size_t)w * lds);
-    if (!gram_chol(q1.p, lds, r2.p, rinv2.p, status.p + 4)) return false;
-    rfac.alloc(c, (size_t)w * lds);
-    gemm<T>(c, RC_OP_N, RC_OP_N, w, w, w, r2.p, lds, r1.p, lds, rfac.p, lds, rc_one<T>(), rc_zero<T>());
-    if (c->defer_depth > 0 && !panel_scale) {
-        // speculative: carry on as if both rounds were accepted; the status words are checked at the end of the
-        // deferred region (finish_deferred), which re-runs it on the Householder path when a panel was not acceptable
-        c->deferred.push_back({status.take(), single});
-        c->cholqr_used++;
-        return true;
+    if ((!sharded && m < 4 * w) || w > wlim || w < 2) return false;
+    // the shifted route: double precision, whole sketches only (the panels of a wider factorisation have their own
+    // rank-deficiency handling in panel_qr)
+    const bool may_shift = c->shifted_cholqr && !single_prec && !panel_scale;
+    if (c->force_shifted && may_shift)
+        return cholqr_rounds<T>(c, y, ldy, m, w, sharded, dtype, true, q1, rinv2, rfac, lds, panel_scale, full_w);
+    if (cholqr_rounds<T>(c, y, ldy, m, w, sharded, dtype, false, q1, rinv2, rfac, lds, panel_scale, full_w)) return true;
+    if (c->defer_depth > 0 && !panel_scale) return false;      // (not reached: a speculative attempt reports success)
+    c->cholqr_fallbacks++;
+    if (may_shift) {
+        q1.release(); rinv2.release(); rfac.release();
+        if (cholqr_rounds<T>(c, y, ldy, m, w, sharded, dtype, true, q1, rinv2, rfac, lds, panel_scale, full_w)) return true;
+        c->cholqr_fallbacks++;
     }
-    RC_CUDA(cudaMemcpyAsync(h, status.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    RC_CUDA(cudaStreamSynchronize(c->stream));
-    if (!cholqr2_acceptable(h, single)) { c->cholqr_fallbacks++; return false; }
-    if (panel_scale) {
-        const double eps = single ? 5.9604644775390625e-08 : 1.1102230246251565e-16;
-        if (!(h[1] > 10.0 * eps * std::sqrt((double)std::max<int64_t>(full_w, w)) * std::max(*panel_scale, h[2]))) { c->cholqr_fallbacks++; return false; }
-        *panel_scale = std::max(*panel_scale, h[2]);
-    }
-    rc_trace(c, "  cholqr2: 2 x (gram + chol), q1 = Y rinv1");
-    c->cholqr_used++;
-    return true;
+    return false;
 }
 
 // Pivoted QR of the small w x w factor of a tall panel (row-major `rf`): R (into r), pivots (dind) and the first ncq
@@ -801,6 +887,10 @@ rc_matrix* sample_power_once(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p
             const rc_matrix* start = (c->true_power_iteration && cur.get()) ? cur.get() : y0.get();
             QrParts q1; q1.want_ind = false;
             pivoted_qr_impl<T>(c, start, false, -1, false, q1);      // :145-146 (all columns of Q)
+            if (index == 0 && c->defer_depth > 0 && !check_deferred_now(c)) {   // (see the two-stream branch below)
+                RedoScope redo(c, a->dtype);
+                pivoted_qr_impl<T>(c, start, false, -1, false, q1);
+            }
             MatPtr z(conj_matmat_impl<T>(c, a, q1.q.get()));          // :148
             QrParts q2; q2.want_ind = false;
             pivoted_qr_impl<T>(c, z.get(), false, -1, true, q2);     // :148-149
@@ -830,6 +920,21 @@ rc_matrix* sample_power_once(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p
                     default: tr.ynew.reset(matmat_impl<T>(c, a, tr.q2.q.get())); break;                               // :150
                 }
             }
+            if (stage == 0 && c->defer_depth > 0 && !check_deferred_now(c)) {
+                // Y0 = A Omega is the one sketch of the pipeline whose columns are not graded: when the operator's
+                // spectrum falls by more than ~7 decades over the sketch width its Gram matrix is numerically singular
+                // and the plain Cholesky-QR2 is rejected.  The later sketches (Z = A^H q, Y = A w) inherit the column
+                // order of a pivoted QR, are graded like the spectrum and pass (cholqr2_acceptable, rule (b)).  So the
+                // first factorisation is checked here -- one host round trip, ~30 us, at a point where nothing else can
+                // run anyway -- and redone at once on the shifted route, instead of finding out at the end of the
+                // pipeline and running all of it again (measured on a twelve-decade sketch at configs[1] size: 37 ms
+                // with the Householder re-run of the whole pipeline, 24 ms on Householder TSQR throughout).
+                RedoScope redo(c, a->dtype);
+                for (int64_t t = 0; t < it_count; ++t) {
+                    StreamScope on_aux(c, (int)(t & 1));
+                    pivoted_qr_impl<T>(c, y0.get(), false, -1, false, trips[(size_t)t].q1);
+                }
+            }
         }
         for (int s = 0; s < 2; ++s) {                            // join: everything below (and every free) follows both
             cudaEvent_t ev = aux_event(c, 1 + s);
@@ -855,20 +960,33 @@ rc_matrix* sample_power_impl(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t p
     RC_REQUIRE(omega->rows == n && omega->cols == l, "omega must be %lld x %lld", (long long)n, (long long)l);
     if (!c->speculate || c->qr_mode == 1 || c->defer_depth > 0) return sample_power_once<T>(c, a, k, p, it_count, omega);
     // Speculative pass: no host synchronisation inside the pipeline (the Cholesky-QR2 panels are assumed acceptable,
-    // pivot vectors are not downloaded); one synchronisation at the end checks every panel's status word, and a
-    // rejected panel re-runs the sampler on the unconditionally stable Householder TSQR.
+    // pivot vectors are not downloaded); one synchronisation at the end checks every panel's status word.  A rejected
+    // panel re-runs the sampler, first (double precision) with every tall QR on the shifted Cholesky-QR3 -- still
+    // speculative, still GEMM-shaped -- and then on the unconditionally stable Householder TSQR.
+    auto speculative_pass = [&](MatPtr& q) -> bool {
+        bool ok = false;
+        try {
+            DeferScope defer(c);
+            q.reset(sample_power_once<T>(c, a, k, p, it_count, omega));
+            ok = true;
+        } catch (...) {
+            drop_deferred(c);
+            throw;
+        }
+        if (ok && finish_deferred(c)) return true;
+        q.reset(nullptr);
+        return false;
+    };
     MatPtr q;
-    bool ok = false;
-    try {
-        DeferScope defer(c);
-        q.reset(sample_power_once<T>(c, a, k, p, it_count, omega));
-        ok = true;
-    } catch (...) {
-        drop_deferred(c);
-        throw;
+    if (speculative_pass(q)) return q.release();
+    const bool single_prec = (a->dtype == RC_F32 || a->dtype == RC_C32);
+    if (c->shifted_cholqr && !single_prec) {
+        c->force_shifted = true;
+        bool ok = false;
+        try { ok = speculative_pass(q); } catch (...) { c->force_shifted = false; throw; }
+        c->force_shifted = false;
+        if (ok) return q.release();
     }
-    if (ok && finish_deferred(c)) return q.release();
-    q.reset(nullptr);
     c->force_householder = true;
     try {
         q.reset(sample_power_once<T>(c, a, k, p, it_count, omega));
@@ -1200,6 +1318,7 @@ rc_status rc_ctx_destroy(rc_ctx* c) {
             if (c->aux_tile_counter[i]) cudaFree(c->aux_tile_counter[i]);
         }
         for (int i = 0; i < 4; ++i) if (c->aux_event[i]) cudaEventDestroy(c->aux_event[i]);
+        if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
         if (c->own_stream) cudaStreamDestroy(c->stream);
     }
     delete c;
@@ -1233,6 +1352,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
         else if (!strcmp(key, "qr_mode")) c->qr_mode = (int)v;
         else if (!strcmp(key, "pivot_precision")) c->pivot_f64 = (v != 0);
         else if (!strcmp(key, "speculate")) c->speculate = (int)v;
+        else if (!strcmp(key, "shifted_cholqr")) c->shifted_cholqr = (int)v;
         else if (!strcmp(key, "fused_small_qr")) c->fused_small_qr = (int)v;
         else if (!strcmp(key, "cluster_qr")) c->cluster_qr = (int)v;
         else if (!strcmp(key, "svd_precondition")) c->svd_precondition = (int)v;
@@ -1253,6 +1373,7 @@ rc_status rc_ctx_get_counter(rc_ctx* c, const char* key, int64_t* out) {
         else if (!strcmp(key, "d2h_bytes")) *out = c->d2h_bytes;
         else if (!strcmp(key, "cholqr_used")) *out = c->cholqr_used;
         else if (!strcmp(key, "cholqr_fallbacks")) *out = c->cholqr_fallbacks;
+        else if (!strcmp(key, "cholqr_shifted")) *out = c->cholqr_shifted;
         else if (!strcmp(key, "range_b_reused")) *out = c->range_b_reused;
         else if (!strcmp(key, "workspace_cache_hits")) *out = c->cache_hits;
         else if (!strcmp(key, "workspace_cache_misses")) *out = c->cache_misses;
@@ -1263,7 +1384,7 @@ rc_status rc_ctx_get_counter(rc_ctx* c, const char* key, int64_t* out) {
 rc_status rc_ctx_reset_counters(rc_ctx* c) {
     if (!c) return RC_INVALID_ARGUMENT;
     c->launches = c->gemm_flops = c->h2d_bytes = c->d2h_bytes = 0;
-    c->cholqr_used = c->cholqr_fallbacks = c->range_b_reused = 0;
+    c->cholqr_used = c->cholqr_fallbacks = c->cholqr_shifted = c->range_b_reused = 0;
     return RC_OK;
 }
 
@@ -1315,6 +1436,44 @@ rc_status rc_matrix_from_host(rc_ctx* c, rc_dtype dt, const void* host, int64_t 
             c->h2d_bytes += rows * cols * (int64_t)es;
         }
         *out = m.release();
+    });
+}
+// Pipelined upload: the copy is queued on the context's copy stream and the call returns at once, so the transfer
+// of the NEXT operator runs under the kernels working on the current one (the PCIe link and the SMs are independent
+// resources; for configs[1] the 4 GiB upload is 78 ms against 16 ms of compute).  rc_matrix_await orders the context
+// stream behind the copy.
+rc_status rc_matrix_from_host_async(rc_ctx* c, rc_dtype dt, const void* host, int64_t rows, int64_t cols,
+                                    int64_t rs, rc_matrix** out) {
+    if (!c || !out) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        RC_REQUIRE(dt >= 0 && dt <= 3, "bad dtype");
+        RC_REQUIRE(host || rows * cols == 0, "null host pointer");
+        RC_REQUIRE(rows >= 0 && cols >= 0 && rs >= cols, "from_host_async takes a row-major view with row stride >= cols");
+        MatPtr m(mat_new(c, dt, rows, cols));
+        const size_t es = rc_dtype_size(dt);
+        if (rows * cols > 0) {
+            if (!c->copy_stream) RC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            // the buffer was allocated (or taken from the workspace cache) in the order of the context stream
+            cudaEvent_t ev;
+            RC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            m->upload_done = ev;
+            RC_CUDA(cudaEventRecord(ev, c->stream));
+            RC_CUDA(cudaStreamWaitEvent(c->copy_stream, ev, 0));
+            RC_CUDA(cudaMemcpy2DAsync(m->data, m->ld * es, host, rs * es, cols * es, rows, cudaMemcpyHostToDevice, c->copy_stream));
+            RC_CUDA(cudaEventRecord(ev, c->copy_stream));
+            c->h2d_bytes += rows * cols * (int64_t)es;
+        }
+        *out = m.release();
+    });
+}
+rc_status rc_matrix_await(rc_ctx* c, rc_matrix* m, int block_host) {
+    if (!c || !m) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] {
+        if (!m->upload_done) return;
+        if (block_host) RC_CUDA(cudaEventSynchronize(m->upload_done));
+        RC_CUDA(cudaStreamWaitEvent(c->stream, m->upload_done, 0));
+        RC_CUDA(cudaEventDestroy(m->upload_done));
+        m->upload_done = nullptr;
     });
 }
 rc_status rc_matrix_wrap_device(rc_ctx* c, rc_dtype dt, void* dptr, int64_t rows, int64_t cols, int64_t ld, rc_matrix** out) {

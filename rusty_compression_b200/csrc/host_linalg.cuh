@@ -31,6 +31,12 @@ inline rc_matrix* mat_new(rc_ctx* c, int dtype, int64_t rows, int64_t cols) {
 }
 inline void mat_free(rc_matrix* m) {
     if (!m) return;
+    if (m->upload_done) {                    // never awaited: the copy must not outlive the buffer it writes
+        DeviceGuard dg(m->ctx->device);
+        cudaStreamWaitEvent(m->ctx->stream, m->upload_done, 0);
+        cudaEventDestroy(m->upload_done);
+        m->upload_done = nullptr;
+    }
     if (m->owns && m->data) {
         DeviceGuard dg(m->ctx->device);      // the *_free entry points are not routed through guard()
         rc_dev_free(m->ctx, m->data);

@@ -68,13 +68,20 @@ struct rc_ctx {
     int overlap = 1;              // option "overlap": independent stages on auxiliary streams
     int defer_depth = 0;
     bool force_householder = false;
-    struct DeferredCheck { double* status; bool single; };
+    bool force_shifted = false;   // re-run of a speculative region on shifted Cholesky-QR3 (host_api.cu: cholqr2)
+    int shifted_cholqr = 1;       // option "shifted_cholqr": ill-conditioned double-precision sketches try a shifted first round
+                                  // before the Householder TSQR
+    int64_t cholqr_shifted = 0;   // counter "cholqr_shifted"
+    struct DeferredCheck { double* status; bool single; bool shifted; };
     std::vector<DeferredCheck> deferred;
     // auxiliary streams for independent stages (the two power-iteration trips of the reference are independent of
     // each other, quirk Q1), each with its own scratch for the dynamic GEMM tile scheduler
     cudaStream_t aux_stream[2] = {nullptr, nullptr};
     int* aux_tile_counter[2] = {nullptr, nullptr};
     cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
+    // upload stream of rc_matrix_from_host_async (created on first use): the next operator's host-to-device copy runs
+    // here while the context stream computes on the current one
+    cudaStream_t copy_stream = nullptr;
     // counters
     int64_t launches = 0, gemm_flops = 0, h2d_bytes = 0, d2h_bytes = 0;
     int* tile_counter = nullptr;   // device scratch for the dynamic GEMM tile scheduler
@@ -104,6 +111,8 @@ struct rc_matrix {
     // adaptive sampler, the factor B = Q^H A it already computed for the operator `companion_op_id`
     // (QR/SVD::compute_from_range_estimate reuse it instead of another pass over A)
     uint64_t id = 0;
+    // rc_matrix_from_host_async: recorded behind the upload on the context's copy stream; rc_matrix_await consumes it
+    cudaEvent_t upload_done = nullptr;
     rc_matrix* companion = nullptr;
     uint64_t companion_op_id = 0;
     // matrix-free operator (rc_operator_create): no data, products go through the caller's callbacks
@@ -359,6 +368,8 @@ void trsm_upper(rc_ctx*, const T* u, int64_t ldu, bool u_transposed, int64_t k, 
 template <class T>
 bool chol_inv(rc_ctx*, const T* g, int64_t ldg, int64_t w, T* r, T* rinv, int64_t ldo, double* status_dev);
 int64_t chol_max_width(rc_ctx*, int dtype);
+// G += factor * max_j Re(G_jj) * I on the device (no host round trip)
+template <class T> void chol_shift(rc_ctx*, T* g, int64_t ldg, int64_t w, double factor);
 // Same contract for w <= 2 * chol_max_width: one level of 2 x 2 blocking around the one-CTA kernel (small GEMMs for the
 // off-diagonal blocks).
 template <class T>

@@ -106,3 +106,31 @@ def test_argument_violations(api):
         api.SVD.compute_from(np.eye(8)).compress(api.ADAPTIVE(1e-3))   # no singular value below tol (quirk Q3)
     q, hist = api.sample_range_adaptive(a, 1e-12, 5, seed=2, max_rank=20)     # reaches full rank, then stops
     assert q.shape[1] <= 20 and hist[-1][1] < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex64])
+def test_pipelined_upload(api, dtype):
+    """rc_matrix_from_host_async / rc_matrix_await: two uploads in flight, results identical to the blocking route;
+    a handle freed without ever being awaited is safe."""
+    import torch
+    ctx = api.default_context()
+    td = torch.float64 if dtype == np.float64 else torch.complex64
+    hosts = [torch.empty((700, 300), dtype=td, pin_memory=True).numpy() for _ in range(3)]
+    for i, h in enumerate(hosts):
+        h[...] = rnd(h.shape, dtype, 20 + i)
+    padded = torch.empty((700, 320), dtype=td, pin_memory=True).numpy()
+    padded[:, :300] = hosts[0]
+    ops = [api.DeviceMatrix.from_numpy_async(h, ctx=ctx) for h in hosts]
+    view = api.DeviceMatrix.from_numpy_async(padded[:, :300], ctx=ctx)           # row stride > cols
+    never = api.DeviceMatrix.from_numpy_async(hosts[1], ctx=ctx)
+    never.free()
+    omega = rnd((300, 12), dtype, 3)
+    for op, h in zip(ops, hosts):
+        op.await_upload()
+        assert np.array_equal(op.to_numpy(), h)
+        y = op.matmat(api.DeviceMatrix.from_numpy(omega, ctx=ctx)).to_numpy()
+        y_ref = api.DeviceMatrix.from_numpy(h, ctx=ctx).matmat(api.DeviceMatrix.from_numpy(omega, ctx=ctx)).to_numpy()
+        assert np.array_equal(y, y_ref)
+    assert np.array_equal(view.await_upload(block_host=True).to_numpy(), hosts[0])
+    with pytest.raises(ValueError):
+        api.DeviceMatrix.from_numpy_async(hosts[0].T, ctx=ctx)

@@ -168,18 +168,39 @@ def test_c32_runs_on_tcgen05_through_real_expansion(api, shape):
 
 
 def test_cholqr2_falls_back_on_ill_conditioned_panels(api):
-    """A sketch with condition number ~1e12 must take the Householder TSQR route and stay orthonormal."""
+    """A sketch with condition number ~1e12 is rejected by the plain Cholesky-QR2 and taken by the shifted
+    Cholesky-QR3 (three GEMM-shaped rounds); with that route off, and beyond its reach (cond ~1e15), it goes to
+    the Householder TSQR.  Orthonormal and backward stable to roundoff on every route."""
     ctx = api.default_context()
     a = ref.random_approximate_low_rank_matrix((3000, 60), 1.0, 1e-12, np.float64, seed=9)
     ctx.reset_counters()
     q, r, ind = api.pivoted_qr(a)
-    assert ctx.counter("cholqr_fallbacks") >= 1 and ctx.counter("cholqr_used") == 0
+    assert ctx.counter("cholqr_fallbacks") == 1 and ctx.counter("cholqr_shifted") == 1 and ctx.counter("cholqr_used") == 1
     assert np.max(np.abs(q.T.dot(q) - np.eye(60))) < 1e-13
     assert relerr(q.dot(r), a[:, ind]) < 1e-13
+    q0, r0, ind0 = ref.pivoted_qr(a)
+    order = adjudicate(a, ind, ind0, label="shifted cholqr3 3000x60")
+    if order is not None:
+        q0, r0, ind0 = ref.pivoted_qr_with_order(a, order)
+    assert np.max(np.abs(np.abs(np.diagonal(r)) - np.abs(np.diagonal(r0))) / np.abs(r0[0, 0])) < 1e-13
+    ctx.set_option("shifted_cholqr", 0)
+    try:
+        ctx.reset_counters()
+        q, r, ind = api.pivoted_qr(a)
+        assert ctx.counter("cholqr_fallbacks") >= 1 and ctx.counter("cholqr_used") == 0
+        assert np.max(np.abs(q.T.dot(q) - np.eye(60))) < 1e-13
+        assert relerr(q.dot(r), a[:, ind]) < 1e-13
+    finally:
+        ctx.set_option("shifted_cholqr", 1)
+    hard = ref.random_approximate_low_rank_matrix((3000, 60), 1.0, 1e-15, np.float64, seed=9)
+    ctx.reset_counters()
+    q, r, ind = api.pivoted_qr(hard)
+    assert np.max(np.abs(q.T.dot(q) - np.eye(60))) < 1e-13
+    assert relerr(q.dot(r), hard[:, ind]) < 1e-13
     well = ref.random_approximate_low_rank_matrix((3000, 60), 1.0, 1e-3, np.float64, seed=9)
     ctx.reset_counters()
     q, r, ind = api.pivoted_qr(well)
-    assert ctx.counter("cholqr_used") == 1
+    assert ctx.counter("cholqr_used") == 1 and ctx.counter("cholqr_shifted") == 0
     assert np.max(np.abs(q.T.dot(q) - np.eye(60))) < 1e-13
 
 

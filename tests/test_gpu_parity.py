@@ -57,6 +57,40 @@ def test_rsvd_parity(api, dtype, it_count, qr_mode):
     assert abs(rec_dev - rec_ref) <= tol * rec_ref + (1e-6 if tol > 1e-6 else 0)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("shifted", [1, 0], ids=["shifted-cholqr3", "householder"])
+def test_rsvd_parity_steep_spectrum(api, dtype, shifted):
+    """The operators the crate is written for decay fast: here sigma_j = 10^(-j/6), so the 74-column sketch spans
+    twelve decades (cond ~1e12).  The speculative Cholesky-QR2 pass is rejected at its final check and the sampler is
+    re-run on the shifted Cholesky-QR3 (or, with that off, on the Householder TSQR); either way the result matches the
+    oracle: leading singular values to 1e-10 relative, the deep ones (down to 2e-11 of the first) and the range
+    residual (1.5e-11) to the roundoff of the norm of A."""
+    m, n, k, p, it_count = 4096, 1024, 64, 10, 2
+    a, _sig = decaying_spectrum_matrix(m, n, dtype, seed=77, r0=128, decade_every=6.0)
+    omega = random_gaussian((n, k + p), dtype, seed=42)
+    q_ref = ref.sample_range_power_iteration(a, k, p, it_count, ref.OmegaStream(dtype, blocks=[omega]))
+    svd_ref = ref.SVD.compute_from_range_estimate(q_ref, a)
+    ctx = api.default_context()
+    ctx.set_option("shifted_cholqr", shifted)
+    try:
+        ctx.reset_counters()
+        op = api.DeviceMatrix.from_numpy(a)
+        q_dev = api.sample_range_power_iteration(op, k, p, it_count, omega=omega)
+        used_shifted = ctx.counter("cholqr_shifted")
+        svd_dev = api.SVD.compute_from_range_estimate(q_dev, op)
+    finally:
+        ctx.set_option("shifted_cholqr", 1)
+    assert ctx.counter("cholqr_fallbacks") >= 1
+    assert (used_shifted >= 1) == bool(shifted)
+    assert np.max(np.abs(np.conj(q_dev.T).dot(q_dev) - np.eye(k))) < 1e-12
+    res_ref, res_dev = ref.range_residual(a, q_ref), ref.range_residual(a, q_dev)
+    assert abs(res_dev - res_ref) <= 1e-3 * res_ref, (res_dev, res_ref)      # residual 1.5e-11 of ||A||: 1e-5 of it is roundoff
+    s_ref, s_dev = svd_ref.s.astype(np.float64), svd_dev.s_f64()
+    lead = s_ref >= 1e-5 * s_ref[0]
+    assert np.max(np.abs(s_dev - s_ref)[lead] / s_ref[lead]) <= 1e-10
+    assert np.max(np.abs(s_dev - s_ref)) <= 1e-14 * s_ref[0]
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32, np.complex64])
 def test_column_and_two_sided_id_parity(api, dtype):
     """Config-5 pipeline at oracle scale: sample_range_by_rank -> QR::compute_from_range_estimate ->
