@@ -136,6 +136,20 @@ class Matrix {
         if (row_major.size() != rows * cols) throw InvalidArgument(RC_INVALID_ARGUMENT, "from_host: size mismatch");
         return from_host(ctx, row_major.data(), rows, cols, (ptrdiff_t)cols, 1);
     }
+    // Pipelined upload of a row-major host buffer (pinned memory for a truly asynchronous copy): returns at once, the
+    // copy runs on the context's copy stream under whatever the context stream is computing.  The result must go through
+    // await_upload() before any other use; `data` stays valid and unmodified until await_upload(true) returns (or any
+    // later blocking call on the context).  No counterpart in the reference (a host library has no transfer to hide).
+    static Matrix from_host_async(const Context& ctx, const A* data, size_t rows, size_t cols, ptrdiff_t row_stride) {
+        rc_matrix* h = nullptr;
+        ctx.check(rc_matrix_from_host_async(ctx.raw(), ScalarTraits<A>::dtype, data, (int64_t)rows, (int64_t)cols,
+                                            (int64_t)row_stride, &h));
+        return Matrix(ctx, h);
+    }
+    Matrix& await_upload(bool block_host = false) {
+        ctx_.check(rc_matrix_await(ctx_.raw(), h_.get(), block_host ? 1 : 0));
+        return *this;
+    }
     // RandomMatrix (src/random_matrix.rs:21-93), seeded
     static Matrix random_gaussian(const Context& ctx, size_t rows, size_t cols, uint64_t seed) {
         rc_matrix* h = nullptr;

@@ -58,6 +58,16 @@ impl Drop for Context { fn drop(&mut self) { unsafe { sys::rc_ctx_destroy(self.r
 pub struct DeviceMatrix<A: RcScalar> { pub(crate) ctx: Arc<Context>, pub(crate) h: *mut sys::rc_matrix, _a: PhantomData<A> }
 impl<A: RcScalar> Drop for DeviceMatrix<A> { fn drop(&mut self) { unsafe { sys::rc_matrix_free(self.h); } } }
 
+/// An upload in flight (`DeviceMatrix::from_array_async`); borrows the host array until it is consumed.
+pub struct PendingMatrix<'a, A: RcScalar> { m: DeviceMatrix<A>, _src: PhantomData<&'a A> }
+impl<'a, A: RcScalar> PendingMatrix<'a, A> {
+    /// Orders the context stream behind the copy and waits for it on the host (the borrow of the source ends here).
+    pub fn ready(self) -> Result<DeviceMatrix<A>> {
+        self.m.ctx.check(unsafe { sys::rc_matrix_await(self.m.ctx.raw, self.m.h, 1) })?;
+        Ok(self.m)
+    }
+}
+
 impl<A: RcScalar> DeviceMatrix<A> {
     /// Upload any ndarray view; the ABI takes element strides (like `mat.assign(&arr)`, src/pivoted_qr.rs:29).
     pub fn from_array<S: Data<Elem = A>>(ctx: &Arc<Context>, a: &ArrayBase<S, Ix2>) -> Result<Self> {
@@ -66,6 +76,16 @@ impl<A: RcScalar> DeviceMatrix<A> {
         ctx.check(unsafe { sys::rc_matrix_from_host(ctx.raw, A::DTYPE, a.as_ptr() as *const _, a.nrows() as i64,
                                                     a.ncols() as i64, rs, cs, &mut h) })?;
         Ok(DeviceMatrix { ctx: ctx.clone(), h, _a: PhantomData })
+    }
+    /// Pipelined upload of a row-major (standard layout) array that the caller keeps alive -- and pinned, for a truly
+    /// asynchronous copy -- until `ready`: the transfer runs on the context's copy stream under the kernels of the
+    /// current step.  The pending handle can only be used through `ready`, which orders the context stream behind it.
+    pub fn from_array_async<'a>(ctx: &Arc<Context>, a: &'a ArrayView2<'a, A>) -> Result<PendingMatrix<'a, A>> {
+        assert!(a.strides()[1] == 1 && a.strides()[0] >= a.ncols() as isize, "from_array_async takes a row-major view");
+        let mut h = ptr::null_mut();
+        ctx.check(unsafe { sys::rc_matrix_from_host_async(ctx.raw, A::DTYPE, a.as_ptr() as *const _, a.nrows() as i64,
+                                                          a.ncols() as i64, a.strides()[0] as i64, &mut h) })?;
+        Ok(PendingMatrix { m: DeviceMatrix { ctx: ctx.clone(), h, _a: PhantomData }, _src: PhantomData })
     }
     pub(crate) fn from_raw(ctx: &Arc<Context>, h: *mut sys::rc_matrix) -> Self { DeviceMatrix { ctx: ctx.clone(), h, _a: PhantomData } }
     pub(crate) fn download(ctx: &Arc<Context>, h: *const sys::rc_matrix) -> Result<Array2<A>> {
