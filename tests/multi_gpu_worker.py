@@ -84,6 +84,32 @@ def main():
             assert abs(ra - ra_ref) <= max(tol, 1e-8) * ra_ref + (5e-7 if tol > 1e-6 else 0.0), (dtype, ra, ra_ref)
             print(f"[multi-gpu x{world}] {np.dtype(dtype).name}: sv err {err_s:.2e}, rec {rec:.3e} (ref {rec_ref:.3e}), "
                   f"id err {e:.3e} (ref {e_ref:.3e}), adaptive rank {hist[-1][0]}", flush=True)
+    # --- steep spectrum, row-sharded (f64, sigma_j = 10^(-j/6): the 74-column sketch spans twelve decades): the plain
+    #     Cholesky-QR2 of Y0 = A Omega is rejected at the early check on every rank alike (the status words come from the
+    #     all-reduced Gram matrices) and redone on the shifted Cholesky-QR; the graded sketches of the power iteration pass
+    #     by their scaled backward error.  Same tolerances as tests/test_gpu_parity.py::test_rsvd_parity_steep_spectrum.
+    m, n, k, p = 4096, 1024, 64, 10
+    a, _ = decaying_spectrum_matrix(m, n, np.float64, seed=77, r0=128, decade_every=6.0)
+    omega = random_gaussian((n, k + p), np.float64, seed=42)
+    rows = m // world
+    op = api.DeviceMatrix.from_numpy(a[rank * rows:(rank + 1) * rows], ctx=ctx).set_shard(m, rank * rows)
+    ctx.reset_counters()
+    q = api.sample_range_power_iteration(op, k, p, 2, omega=omega, ctx=ctx, device=True)
+    shifted, rejected = ctx.counter("cholqr_shifted"), ctx.counter("cholqr_fallbacks")
+    svd = api.SVD.compute_from_range_estimate(q, op)
+    q_full, s = gather_rows(q.to_numpy()), svd.s_f64()
+    if rank == 0:
+        q_ref = ref.sample_range_power_iteration(a, k, p, 2, ref.OmegaStream(np.float64, blocks=[omega]))
+        s_ref = ref.SVD.compute_from_range_estimate(q_ref, a).s
+        res, res_ref = ref.range_residual(a, q_full), ref.range_residual(a, q_ref)
+        lead = s_ref >= 1e-5 * s_ref[0]
+        err_lead, err_abs = np.max(np.abs(s - s_ref)[lead] / s_ref[lead]), np.max(np.abs(s - s_ref)) / s_ref[0]
+        orth = np.max(np.abs(q_full.T.dot(q_full) - np.eye(k)))
+        print(f"[multi-gpu x{world}] steep spectrum f64 (sharded): shifted Cholesky-QR used {shifted} times after {rejected} rejections, "
+              f"|Q^T Q - I| {orth:.2e}, residual {res:.6e} (oracle {res_ref:.6e}), leading sv err {err_lead:.2e}, all sv err / s0 {err_abs:.2e}",
+              flush=True)
+        assert shifted >= 1 and rejected >= 1
+        assert orth < 1e-12 and abs(res - res_ref) <= 1e-3 * res_ref and err_lead <= 1e-10 and err_abs <= 1e-14
     # --- a sketch with more columns than the operator has rank, row-sharded (f64: 300 columns of a rank-100 operator, wider
     #     than one Cholesky / TSQR panel): the later panels have no direction of their own, every rank must take the same
     #     Householder fallback with Gaussian completion, and the gathered range basis must be orthonormal and span range(A)
