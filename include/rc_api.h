@@ -133,6 +133,11 @@ rc_status rc_matrix_from_host(rc_ctx* ctx, rc_dtype dtype, const void* host, int
 rc_status rc_matrix_from_host_async(rc_ctx* ctx, rc_dtype dtype, const void* host, int64_t rows,
                                     int64_t cols, int64_t row_stride, rc_matrix** out);
 rc_status rc_matrix_await(rc_ctx* ctx, rc_matrix* m, int block_host);
+/* Page-lock / unlock host memory the caller owns (e.g. the allocation behind an ndarray Array2, src/types.rs:58-71
+ * takes such arrays by reference): uploads from registered memory run at the full rate of the link and the
+ * asynchronous upload above does not block.  Wrappers of cudaHostRegister / cudaHostUnregister. */
+rc_status rc_host_register(rc_ctx* ctx, void* host, size_t bytes);
+rc_status rc_host_unregister(rc_ctx* ctx, void* host);
 /* Borrow device memory (row-major, leading dimension `ld` elements); never freed by the library. */
 rc_status rc_matrix_wrap_device(rc_ctx* ctx, rc_dtype dtype, void* device_ptr, int64_t rows,
                                 int64_t cols, int64_t ld, rc_matrix** out);

@@ -86,6 +86,9 @@ class Context {
         }
     }
     void synchronize() const { check(rc_ctx_synchronize(ctx_.get())); }
+    // page-lock / unlock host memory the caller owns (full-rate, truly asynchronous uploads from it)
+    void pin(void* host, size_t bytes) const { check(rc_host_register(ctx_.get(), host, bytes)); }
+    void unpin(void* host) const { check(rc_host_unregister(ctx_.get(), host)); }
     void set_option(const char* key, int64_t value) const { check(rc_ctx_set_option(ctx_.get(), key, value)); }
     int64_t counter(const char* key) const {
         int64_t v = 0;

@@ -41,6 +41,8 @@ extern "C" {
     pub fn rc_matrix_create(ctx: *mut rc_ctx, dtype: c_int, rows: i64, cols: i64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_matrix_from_host(ctx: *mut rc_ctx, dtype: c_int, host: *const c_void, rows: i64, cols: i64, row_stride: i64, col_stride: i64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_matrix_from_host_async(ctx: *mut rc_ctx, dtype: c_int, host: *const c_void, rows: i64, cols: i64, row_stride: i64, out: *mut *mut rc_matrix) -> c_int;
+    pub fn rc_host_register(ctx: *mut rc_ctx, host: *mut c_void, bytes: usize) -> c_int;
+    pub fn rc_host_unregister(ctx: *mut rc_ctx, host: *mut c_void) -> c_int;
     pub fn rc_matrix_await(ctx: *mut rc_ctx, m: *mut rc_matrix, block_host: c_int) -> c_int;
     pub fn rc_matrix_wrap_device(ctx: *mut rc_ctx, dtype: c_int, device_ptr: *mut c_void, rows: i64, cols: i64, ld: i64, out: *mut *mut rc_matrix) -> c_int;
     pub fn rc_matrix_to_host(ctx: *mut rc_ctx, m: *const rc_matrix, host: *mut c_void) -> c_int;

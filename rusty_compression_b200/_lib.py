@@ -39,6 +39,8 @@ SIGNATURES = {
     "rc_matrix_from_host": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, PH]),
     "rc_matrix_from_host_async": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, PH]),
     "rc_matrix_await": (c_int, [H, H, c_int]),
+    "rc_host_register": (c_int, [H, c_void_p, c_size_t]),
+    "rc_host_unregister": (c_int, [H, c_void_p]),
     "rc_matrix_wrap_device": (c_int, [H, c_int, c_void_p, c_int64, c_int64, c_int64, PH]),
     "rc_column_id_col_ind_len": (c_size_t, [H]),
     "rc_row_id_row_ind_len": (c_size_t, [H]),

@@ -101,6 +101,15 @@ class Context:
     def synchronize(self):
         self.check(self.lib.rc_ctx_synchronize(self.h))
 
+    def pin(self, arr):
+        """Page-lock the memory of a numpy array in place (rc_host_register) so that uploads from it run at the rate
+        of the link and `DeviceMatrix.from_numpy_async` does not block; undo with `unpin(arr)` before it is freed."""
+        self.check(self.lib.rc_host_register(self.h, c_void_p(arr.ctypes.data), arr.nbytes))
+        return arr
+
+    def unpin(self, arr):
+        self.check(self.lib.rc_host_unregister(self.h, c_void_p(arr.ctypes.data)))
+
     def set_stream(self, cuda_stream_ptr):
         self.check(self.lib.rc_ctx_set_stream(self.h, c_void_p(cuda_stream_ptr)))
 

@@ -1466,6 +1466,17 @@ rc_status rc_matrix_from_host_async(rc_ctx* c, rc_dtype dt, const void* host, in
         *out = m.release();
     });
 }
+// Page-lock (and unlock) host memory the caller already owns -- an ndarray allocation, say -- so that uploads from it
+// run at the full rate of the link and rc_matrix_from_host_async really is asynchronous (a copy from pageable memory
+// is staged through a driver bounce buffer and blocks the host).
+rc_status rc_host_register(rc_ctx* c, void* host, size_t bytes) {
+    if (!c || !host || bytes == 0) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { RC_CUDA(cudaHostRegister(host, bytes, cudaHostRegisterPortable)); });
+}
+rc_status rc_host_unregister(rc_ctx* c, void* host) {
+    if (!c || !host) return RC_INVALID_ARGUMENT;
+    return guard(c, [&] { RC_CUDA(cudaHostUnregister(host)); });
+}
 rc_status rc_matrix_await(rc_ctx* c, rc_matrix* m, int block_host) {
     if (!c || !m) return RC_INVALID_ARGUMENT;
     return guard(c, [&] {

@@ -125,6 +125,14 @@ int main() {
     auto svd = SVD<double>::compute_from_range_estimate(q, mat);
     expect(svd.rank() == 40 && rel_diff_fro(svd.to_mat(), mat) < 1e-1, "sample_range_power_iteration + SVD::compute_from_range_estimate");
     expect(max_col_norm(q) < 1.0 + 1e-12 && max_col_norm(q) > 1.0 - 1e-12, "max_col_norm of an orthonormal basis");
+    // pipelined upload (rc_matrix_from_host_async / rc_matrix_await): two operators in flight, same bytes as the blocking route
+    {
+        std::vector<double> h0(300 * 40), h1(300 * 40);
+        for (size_t i = 0; i < h0.size(); ++i) { h0[i] = std::sin(0.37 * (double)i); h1[i] = std::cos(0.11 * (double)i); }
+        auto a0 = Matrix<double>::from_host_async(ctx, h0.data(), 300, 40, 40);
+        auto a1 = Matrix<double>::from_host_async(ctx, h1.data(), 300, 40, 40);
+        expect(a0.await_upload().to_host() == h0 && a1.await_upload(true).to_host() == h1, "from_host_async / await_upload");
+    }
     std::printf("%d failure(s); %lld kernel launches\n", failures, (long long)ctx.counter("kernel_launches"));
     return failures == 0 ? 0 : 1;
 }

@@ -134,3 +134,10 @@ def test_pipelined_upload(api, dtype):
     assert np.array_equal(view.await_upload(block_host=True).to_numpy(), hosts[0])
     with pytest.raises(ValueError):
         api.DeviceMatrix.from_numpy_async(hosts[0].T, ctx=ctx)
+    # memory the caller owns (an ordinary numpy allocation), page-locked in place
+    own = np.ascontiguousarray(rnd((513, 129), dtype, 31))
+    ctx.pin(own)
+    try:
+        assert np.array_equal(api.DeviceMatrix.from_numpy_async(own, ctx=ctx).await_upload(block_host=True).to_numpy(), own)
+    finally:
+        ctx.unpin(own)
