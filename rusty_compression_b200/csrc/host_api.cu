@@ -271,6 +271,16 @@ cudaEvent_t aux_event(rc_ctx* c, int i) {
     if (!c->aux_event[i]) RC_CUDA(cudaEventCreateWithFlags(&c->aux_event[i], cudaEventDisableTiming));
     return c->aux_event[i];
 }
+// Share of the machine for everything launched inside the scope.  Every persistent kernel sizes its grid from
+// rc_ctx::sm_count (one CTA per SM for the tcgen05 kernels, two for the DMMA kernels), so two scopes whose budgets add
+// up to the device run side by side on two streams with every CTA of both resident at once -- no CTA of one ever
+// waits behind the persistent CTAs of the other, which is what serialises two full-size grids.
+struct SmBudget {
+    rc_ctx* c;
+    int saved;
+    SmBudget(rc_ctx* ctx, int sms) : c(ctx), saved(ctx->sm_count) { c->sm_count = std::max(1, std::min(sms, saved)); }
+    ~SmBudget() { c->sm_count = saved; }
+};
 
 // Cholesky-QR2 fast path for a tall, numerically full-rank panel (Y = Q R with Q = q1 * rinv2):
 // two rounds of Gram matrix (one TN GEMM + all-reduce across row shards) -> small Cholesky -> Y R^{-1}.
@@ -1041,26 +1051,76 @@ rc_matrix* sample_adaptive_impl(rc_ctx* c, const rc_matrix* a, double rel_tol_in
             cur = grown;
         }
         rc_trace(c, nullptr);
-        if (r > 0) {                                                             // :250-252
-            DevBuf<T> t(c, (size_t)r * s);
-            gemm<T>(c, RC_OP_H, RC_OP_N, r, s, m, P<T>(qbuf.get()), qbuf->ld, P<T>(y.get()), y->ld, t.p, s, rc_one<T>(), rc_zero<T>());
-            if (mat_sharded(a)) comm_allreduce_sum(c, t.p, (size_t)r * s, a->dtype);
-            gemm<T>(c, RC_OP_N, RC_OP_N, m, s, r, P<T>(qbuf.get()), qbuf->ld, t.p, s, P<T>(y.get()), y->ld, rc_make<T>(-1.0, 0.0), rc_one<T>());
+        // The next sketch Y' = A Omega' (:265-266) depends on nothing this trip computes: it is drawn and launched now, on
+        // an auxiliary stream with all but `side_sms` SMs, while the projection and the pivoted QR of the current sketch
+        // -- a chain of small, latency-bound kernels that could not use the machine anyway -- run on the SMs left over.
+        // Same draws in the same order, same products; only the order of issue changes (the reference computes A Omega'
+        // at the end of the trip whatever the trip finds).
+        const bool side = c->overlap && c->side_sms > 0 && !c->trace && !a->op_matmat && c->sm_count >= 8 * c->side_sms;
+        // How many SMs the chain gets.  The tcgen05 kernels (f32 / c32) hand 128-row work items to one persistent CTA per
+        // SM in rounds, and a CTA is rate-limited by its own ingest, so the product takes
+        // ceil(items / CTAs) x the time of one item: at config 3, 256 items take two rounds on 148 SMs and two rounds on
+        // 128 -- 20 SMs cost nothing (measured: 15.3 ms without the overlap, 14.5 / 13.8 ms with 8 / 16 SMs, 15.2 ms
+        // with 24 or 32, which push the product into a third round).  So the share is raised from `side_sms` up to three
+        // times that as long as the number of rounds stays what it is on the whole device.  The DMMA kernels (f64 / c64)
+        // draw 64-row tiles from a counter and slow down in proportion: they keep the minimum.
+        int side_n = c->side_sms;
+        if (side && (a->dtype == RC_F32 || a->dtype == RC_C32)) {
+            const int64_t cols = (a->dtype == RC_C32 ? 2 : 1) * s;
+            const int64_t items = ((m + 127) / 128) * ((cols + 95) / 96);
+            const int64_t rounds_full = (items + c->sm_count - 1) / c->sm_count;
+            for (int cand = 3 * c->side_sms; cand > c->side_sms; cand -= 2)
+                if ((items + (c->sm_count - cand) - 1) / (c->sm_count - cand) == rounds_full) { side_n = cand; break; }
         }
-        rc_trace(c, "adaptive: Y -= Q (Q^H Y)");
+        MatPtr om_next, y_next;
+        if (side) {
+            next_omega(om_next);                                                 // :265
+            cudaEvent_t ev_in = aux_event(c, 0), ev_out = aux_event(c, 1);
+            RC_CUDA(cudaEventRecord(ev_in, c->stream));
+            try {
+                StreamScope on_aux(c, 0);
+                SmBudget budget(c, c->sm_count - side_n);
+                RC_CUDA(cudaStreamWaitEvent(c->stream, ev_in, 0));
+                y_next.reset(matmat_impl<T>(c, a, om_next.get()));               // :266  A Omega'
+                RC_CUDA(cudaEventRecord(ev_out, c->stream));
+            } catch (...) {
+                if (c->aux_stream[0]) cudaStreamSynchronize(c->aux_stream[0]);
+                throw;
+            }
+        }
         QrParts qq;
-        pivoted_qr_impl<T>(c, y.get(), false, -1, true, qq);                     // :254
-        rc_trace(c, "adaptive: pivoted QR of Y");
+        try {
+            SmBudget budget(c, side ? side_n : c->sm_count);
+            if (r > 0) {                                                         // :250-252
+                DevBuf<T> t(c, (size_t)r * s);
+                gemm<T>(c, RC_OP_H, RC_OP_N, r, s, m, P<T>(qbuf.get()), qbuf->ld, P<T>(y.get()), y->ld, t.p, s, rc_one<T>(), rc_zero<T>());
+                if (mat_sharded(a)) comm_allreduce_sum(c, t.p, (size_t)r * s, a->dtype);
+                gemm<T>(c, RC_OP_N, RC_OP_N, m, s, r, P<T>(qbuf.get()), qbuf->ld, t.p, s, P<T>(y.get()), y->ld, rc_make<T>(-1.0, 0.0), rc_one<T>());
+            }
+            rc_trace(c, "adaptive: Y -= Q (Q^H Y)");
+            pivoted_qr_impl<T>(c, y.get(), false, -1, true, qq);                 // :254
+            rc_trace(c, "adaptive: pivoted QR of Y");
+        } catch (...) {
+            if (side && c->aux_stream[0]) cudaStreamSynchronize(c->aux_stream[0]);   // Y' is still being written
+            throw;
+        }
+        if (side) RC_CUDA(cudaStreamWaitEvent(c->stream, aux_event(c, 1), 0));
         const int64_t sq = qq.q->cols;
         MatPtr z(conj_matmat_impl<T>(c, a, qq.q.get()));                          // :256-260  (A^H q)
         rc_trace(c, "adaptive: A^H q");
         k_transpose<T>(c, P<T>(bbuf.get()) + r * bbuf->ld, bbuf->ld, P<T>(z.get()), z->ld, n, sq, true);
         k_copy<T>(c, P<T>(qbuf.get()) + r, qbuf->ld, P<T>(qq.q.get()), qq.q->ld, m, sq);   // :262
         r += sq;
-        omega = next_omega(om);                                                  // :265
-        rc_trace(c, "adaptive: append B, Q, draw Omega");
-        y.reset(matmat_impl<T>(c, a, omega));                                    // :266  A Omega
-        rc_trace(c, "adaptive: A Omega");
+        if (side) {
+            om.reset(om_next.release());
+            omega = om.get();
+            y.reset(y_next.release());
+        } else {
+            omega = next_omega(om);                                              // :265
+            rc_trace(c, "adaptive: append B, Q, draw Omega");
+            y.reset(matmat_impl<T>(c, a, omega));                                // :266  A Omega
+            rc_trace(c, "adaptive: A Omega");
+        }
         {
             DevBuf<T> t(c, (size_t)r * s);
             gemm<T>(c, RC_OP_N, RC_OP_N, r, s, n, P<T>(bbuf.get()), bbuf->ld, P<T>(omega), omega->ld, t.p, s, rc_one<T>(), rc_zero<T>());
@@ -1295,6 +1355,11 @@ rc_status rc_ctx_create(int device, rc_ctx** out) {
         RC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t thresh = ~0ull;
         RC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        // memory freed on one stream is not handed to another stream by making it WAIT for the free (the pool's default):
+        // that orders the small-kernel chain on one stream behind the big product on the other (measured: the overlap of
+        // the adaptive sampler did not happen at all); reuse is opportunistic -- only once the free has completed
+        int off = 0;
+        RC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
     });
     if (caller_device >= 0 && caller_device != device) cudaSetDevice(caller_device);   // leave the caller's device as it was
     if (st != RC_OK) { fprintf(stderr, "rc_ctx_create: %s\n", c->err.c_str()); delete c; return st; }
@@ -1359,6 +1424,7 @@ rc_status rc_ctx_set_option(rc_ctx* c, const char* key, int64_t v) {
         else if (!strcmp(key, "workspace_cache")) { c->block_cache_on = (int)v; if (!v) rc_cache_release(c); }
         else if (!strcmp(key, "release_workspaces")) { trim_pool(c); }
         else if (!strcmp(key, "overlap")) c->overlap = (int)v;
+        else if (!strcmp(key, "side_sms")) { RC_REQUIRE(v >= 0 && v <= 16, "side_sms: 0 (off) .. 16"); c->side_sms = (int)v; }
         else if (!strcmp(key, "reuse_range_b")) c->reuse_range_b = (int)v;
         else if (!strcmp(key, "trace")) c->trace = (int)v;
         else RC_THROW(RC_INVALID_ARGUMENT, "unknown option '%s'", key);

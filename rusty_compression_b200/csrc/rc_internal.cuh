@@ -66,6 +66,7 @@ struct rc_ctx {
     int fused_small_qr = 1;       // option "fused_small_qr": small pivoted QRs in the fused one-CTA kernel (pivqr.cu)
     int speculate = 1;            // option "speculate"
     int overlap = 1;              // option "overlap": independent stages on auxiliary streams
+    int side_sms = 8;             // option "side_sms": SMs left to the small-kernel chain that runs beside a big product (SmBudget)
     int defer_depth = 0;
     bool force_householder = false;
     bool force_shifted = false;   // re-run of a speculative region on shifted Cholesky-QR3 (host_api.cu: cholqr2)
@@ -148,9 +149,9 @@ inline int rc_real_dtype(int dt) { return dt & 1; }
 // six identical passes (measured at 2^22 x 8192 f32, 137 GB resident: 6.5 s, 1.7 s, 2.1 s, 0.49 s, 0.65 s, 0.25 s per
 // pass; 40-400 ms at 2^20 rows) -- the kernels themselves took 0.20 s.  So blocks of 1 MiB ... 8 GiB are cached here: a
 // freed block keeps an event recorded on the stream it was freed on and is handed out again to the next request it fits
-// without wasting more than a quarter of it; a request from ANOTHER stream first waits for that event.  That is CUDA's
-// own rule (memory freed on a stream may be reused by work ordered after the free) and makes every pass after the first
-// allocation-free.  Small blocks and cache misses go to cudaMallocAsync; when that runs out of memory the cache is
+// without wasting more than a quarter of it; a request from ANOTHER stream takes it only once that event has completed
+// (CUDA's own rule: memory freed on a stream may be reused by work ordered after the free).  Every pass after the first
+// is allocation-free.  Small blocks and cache misses go to cudaMallocAsync; when that runs out of memory the cache is
 // released and the request retried.
 void rc_cache_release(rc_ctx* c);        // hand every cached block back to the driver (host_api.cu)
 inline void* rc_dev_alloc(rc_ctx* c, size_t bytes) {
@@ -159,14 +160,20 @@ inline void* rc_dev_alloc(rc_ctx* c, size_t bytes) {
     void* p = nullptr;
     const bool cacheable = c->block_cache_on && bytes >= kMin && bytes <= kMax;
     if (cacheable) {
-        // best fit, preferring a block freed on this stream (no cross-stream dependence: the two power-iteration trips
-        // run on two streams and should not wait for each other's frees)
+        // best fit, preferring a block freed on this stream; a block freed on ANOTHER stream is taken only when the work
+        // that preceded its free has completed (cudaEventQuery) -- waiting for the event instead would order this stream
+        // behind whatever the other stream is running, e.g. the chain of small kernels behind the big product that runs
+        // beside it (SmBudget, host_api.cu), which is exactly the overlap the two streams exist for
         auto it = c->block_cache.end();
         {
             int looked = 0;
             for (auto j = c->block_cache.lower_bound(bytes); j != c->block_cache.end() && j->first <= bytes + bytes / 4 && looked < 16; ++j, ++looked) {
                 if (j->second.freed_on == c->stream) { it = j; break; }
-                if (it == c->block_cache.end()) it = j;
+                if (it == c->block_cache.end()) {
+                    const cudaError_t q = cudaEventQuery(j->second.freed_at);
+                    if (q == cudaSuccess) it = j;
+                    else (void)cudaGetLastError();                  // cudaErrorNotReady is recorded as the last error
+                }
             }
         }
         if (it != c->block_cache.end()) {
