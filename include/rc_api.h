@@ -91,8 +91,11 @@ const char* rc_last_error_string(rc_ctx* ctx);
  * 0 = padded DMMA; same results up to summation order in those columns), "trace" (1 = stage timer
  * on stderr; synchronises at every mark),
  * "speculate" (1 = no host synchronisation inside the power-iteration sampler: the Cholesky-QR2 status words are checked
- * once at the end and a rejected panel re-runs the sampler on Householder TSQR), "overlap" (1 = independent stages on
- * auxiliary streams), "fused_small_qr" (1 = small pivoted QRs in the fused one-CTA kernel), "cluster_qr" (1 = medium
+ * once at the end -- those of the first sketch right after its factorisation -- and a rejected panel is redone, or the
+ * sampler re-run, on the next route: shifted Cholesky-QR, then Householder TSQR), "shifted_cholqr" (1 = double-precision
+ * sketches the plain Cholesky-QR2 rejects try two shifted Cholesky rounds in front of it before the Householder TSQR;
+ * 0 = Householder at once), "overlap" (1 = independent stages on auxiliary streams), "side_sms" (SMs left to the
+ * small-kernel chain that runs beside a big product on another stream, default 8, 0 = no such overlap), "fused_small_qr" (1 = small pivoted QRs in the fused one-CTA kernel), "cluster_qr" (1 = medium
  * pivoted QRs -- the factor fits 8 CTAs' shared memory -- in the thread-block-cluster kernel, 0 = cooperative grid
  * kernel), "svd_precondition" (1 = the SVD of a matrix too wide for one CTA runs Jacobi on R^H of a pivoted QR; 0 = on the
  * unpivoted triangle), "tf32_ring" (A/B variants of the tcgen05 TF32 kernel: 0 default, 1 = six TMEM split stages, 2 = high part
@@ -102,7 +105,8 @@ const char* rc_last_error_string(rc_ctx* ctx);
  * A handle created through a context must be freed before rc_ctx_destroy: the free routines reach into the context. */
 rc_status rc_ctx_set_option(rc_ctx* ctx, const char* key, int64_t value);
 /* Counters: "kernel_launches" (own kernels launched so far), "gemm_flops", "h2d_bytes",
- * "d2h_bytes", "cholqr_used", "cholqr_fallbacks", "range_b_reused", "workspace_cache_hits", "workspace_cache_misses",
+ * "d2h_bytes", "cholqr_used", "cholqr_fallbacks" (rejections of a Cholesky-QR attempt), "cholqr_shifted" (panels
+ * factored on the shifted route), "range_b_reused", "workspace_cache_hits", "workspace_cache_misses",
  * "workspace_cached_bytes".  rc_ctx_reset_counters zeroes them. */
 rc_status rc_ctx_get_counter(rc_ctx* ctx, const char* key, int64_t* out);
 rc_status rc_ctx_reset_counters(rc_ctx* ctx);
