@@ -1056,7 +1056,13 @@ rc_matrix* sample_adaptive_impl(rc_ctx* c, const rc_matrix* a, double rel_tol_in
         // -- a chain of small, latency-bound kernels that could not use the machine anyway -- run on the SMs left over.
         // Same draws in the same order, same products; only the order of issue changes (the reference computes A Omega'
         // at the end of the trip whatever the trip finds).
-        const bool side = c->overlap && c->side_sms > 0 && !c->trace && !a->op_matmat && c->sm_count >= 8 * c->side_sms;
+        // (single precision only: the tcgen05 kernels are one CTA per SM, so SMs left out of their grid are EMPTY and can
+        // host the one-CTA kernels of the chain -- chol_inv_kernel 1024 threads x 64 registers, pivqr_fused_kernel
+        // 512 x 90, neither fits beside anything.  The DMMA products of f64 / c64 run two CTAs per SM, a smaller grid is
+        // placed breadth-first and leaves no SM empty, the chain waits for the product after all: measured neutral,
+        // 15.0 / 15.1 ms at f64 16384^2, profiles/r2_side_sms_ab.txt.)
+        const bool side = c->overlap && c->side_sms > 0 && !c->trace && !a->op_matmat && c->sm_count >= 8 * c->side_sms &&
+                          (a->dtype == RC_F32 || a->dtype == RC_C32);
         // How many SMs the chain gets.  The tcgen05 kernels (f32 / c32) hand 128-row work items to one persistent CTA per
         // SM in rounds, and a CTA is rate-limited by its own ingest, so the product takes
         // ceil(items / CTAs) x the time of one item: at config 3, 256 items take two rounds on 148 SMs and two rounds on
@@ -1065,7 +1071,7 @@ rc_matrix* sample_adaptive_impl(rc_ctx* c, const rc_matrix* a, double rel_tol_in
         // times that as long as the number of rounds stays what it is on the whole device.  The DMMA kernels (f64 / c64)
         // draw 64-row tiles from a counter and slow down in proportion: they keep the minimum.
         int side_n = c->side_sms;
-        if (side && (a->dtype == RC_F32 || a->dtype == RC_C32)) {
+        if (side) {
             const int64_t cols = (a->dtype == RC_C32 ? 2 : 1) * s;
             const int64_t items = ((m + 127) / 128) * ((cols + 95) / 96);
             const int64_t rounds_full = (items + c->sm_count - 1) / c->sm_count;

@@ -7,9 +7,15 @@ import numpy as np
 from rusty_compression_b200 import api
 
 ctx = api.default_context()
-vals = [int(v) for v in sys.argv[1:]] or [0, 4, 8, 16]
-n = 32768
-a = api.decaying_spectrum_matrix((n, n), np.float32, 1235, r0=1024, decade_every=64.0)
+args = sys.argv[1:]
+dtype = np.float32
+if args and args[0] in ("f32", "f64", "c64"):
+    dtype = {"f32": np.float32, "f64": np.float64, "c64": np.complex128}[args.pop(0)]
+vals = [int(v) for v in args] or [0, 4, 8, 16]
+n = 32768 if dtype == np.float32 else 16384
+a = (api.helmholtz_kernel_matrix((n, n), dtype) if dtype == np.complex128 else
+     api.decaying_spectrum_matrix((n, n), dtype, 1235, r0=1024, decade_every=64.0))
+print(f"{np.dtype(dtype).name} {n} x {n}")
 ref_hist = None
 for v in vals + vals[:1]:
     ctx.set_option("side_sms", v)
