@@ -172,7 +172,7 @@ inline void* rc_dev_alloc(rc_ctx* c, size_t bytes) {
                 if (it == c->block_cache.end()) {
                     const cudaError_t q = cudaEventQuery(j->second.freed_at);
                     if (q == cudaSuccess) it = j;
-                    else (void)cudaGetLastError();                  // cudaErrorNotReady is recorded as the last error
+                    else if (q == cudaErrorNotReady) (void)cudaGetLastError();   // (recorded as the last error; anything else stays)
                 }
             }
         }
