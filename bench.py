@@ -11,7 +11,9 @@ quirk Q1 included).  At N > 1 every rank owns a 65536-row block of a taller matr
 row-sharded; TSQR R-factors all-gathered, A^H Q partials all-reduced over NCCL).
 
 Prints ONE JSON line on rank 0.  `value` = algorithmic GFLOP/s with A resident in HBM;
-`e2e` = the same through the C ABI with host buffers (H2D of A and D2H of U, s, Vt timed).
+`e2e` = the same through the C ABI with pinned host buffers, every step's H2D of A (4 GiB) and D2H of U, s, Vt inside
+the timed region, run as a pipeline of depth 2 (rc_matrix_from_host_async: the upload of the next step's operator
+overlaps the kernels of the current step); `e2e.one_step_at_a_time` is the same with the blocking upload.
 
 BASELINE's metric is "rSVD/ID ... at 1/2/4/8 B200", so the same line carries the ID half and the sharded configs as
 sub-records (each timed like `value`: CUDA events on the launching stream, max over ranks; not part of `value`):
@@ -610,7 +612,7 @@ def main():
                 svd.s_f64()
                 op.free()
 
-        e2e_steps = max(4, min(args.steps, 10))
+        e2e_steps = max(4, min(args.steps, 20))
         ms_e2e = timed(lambda: run_pipelined(e2e_steps), 1, 1) / e2e_steps
         e2e = {"value": world * flops_rank / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s", "host_numa_cpus": numa_cpus,
                "h2d_bytes_per_step": m * n * 8, "d2h_bytes_per_step": (m * k + k + k * n) * 8,
