@@ -876,6 +876,7 @@ rc_matrix* sample_by_rank_impl(rc_ctx* c, const rc_matrix* a, int64_t k, int64_t
     MatPtr y(matmat_impl<T>(c, a, omega));                       // :111-112
     rc_trace(c, "by_rank: Y = A Omega");
     QrParts qr;
+    qr.want_ind = false;
     int64_t kk = std::min<int64_t>(mat_sharded(a) ? a->global_rows : a->rows, l);
     pivoted_qr_impl<T>(c, y.get(), false, std::min(k, kk), true, qr);   // :114-115 compress(RANK(k))
     return qr.q.release();
@@ -1095,6 +1096,7 @@ rc_matrix* sample_adaptive_impl(rc_ctx* c, const rc_matrix* a, double rel_tol_in
             }
         }
         QrParts qq;
+        qq.want_ind = false;                 // (the pivots of the sketch are not used: no download, no host synchronisation)
         try {
             SmBudget budget(c, side ? side_n : c->sm_count);
             if (r > 0) {                                                         // :250-252
