@@ -220,6 +220,32 @@ def test_adaptive_example_parity(api):
         api.sample_range_adaptive(a, 1e-9, 5, seed=11, max_rank=20)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64])
+def test_adaptive_side_stream_overlap_matches_the_serial_order(api, dtype):
+    """Single precision: the adaptive sampler launches the next sketch A Omega' on an auxiliary stream beside the
+    projection + pivoted QR of the current one (option side_sms, SM budgets).  Same draws in the same order: the rank
+    history equals that of the serial order (side_sms = 0) and of the oracle, the residual history agrees to f32
+    roundoff of the products (their split-K factor follows the grid), the range residual to 1e-4."""
+    m, n = 4096, 2048
+    a, _ = decaying_spectrum_matrix(m, n, dtype, seed=21, r0=256, decade_every=32.0)
+    stream = ref.OmegaStream(dtype, seed=5)
+    q_ref, hist_ref = ref.sample_range_adaptive(a, 1e-3, 32, stream)
+    ctx = api.default_context()
+    out = {}
+    try:
+        for side in (0, 8):
+            ctx.set_option("side_sms", side)
+            out[side] = api.sample_range_adaptive(a, 1e-3, 32, omega_blocks=stream.drawn)
+    finally:
+        ctx.set_option("side_sms", 8)
+    for side, (q_dev, hist_dev) in out.items():
+        assert [r for r, _ in hist_dev] == [r for r, _ in hist_ref], side
+        for (_, e_dev), (_, e_ref) in zip(hist_dev, hist_ref):
+            assert abs(e_dev - e_ref) <= 1e-3 * e_ref + 1e-6
+        r_ref, r_dev = ref.range_residual(a, q_ref), ref.range_residual(a, q_dev)
+        assert abs(r_dev - r_ref) <= 1e-4 * r_ref + 1e-7, (side, r_dev, r_ref)
+
+
 def test_device_generated_inputs_and_full_example(api):
     """examples/interpolative_decomposition.rs (500 x 100, k = 20) with the library's own generator."""
     a = api.random_approximate_low_rank_matrix((500, 100), 1.0, 1e-10, np.float64, seed=3)
